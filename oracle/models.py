@@ -1,0 +1,215 @@
+"""Numpy fit functions of the reference's examples (oracle only).
+
+Each function is ``f(x, p)`` with ``x`` a float array of shape ``(ny, nx)`` (the
+same row-major layout the device functors read) and ``p`` a flat vector that is
+either a float array or a ``dual.Dual``.  Returns the ``ny`` model values.
+
+Reference definitions being restated (paths relative to the reference tree):
+  multiexp        examples/y-vs-x.py:58-61, examples/y-noerr.py:70-73
+  multiexp_de     tests/test_lsqfit.py:1643-1649 (E = cumsum(dE))
+  simple          examples/simple.py:43-48
+  offset_exp      examples/uncorrelated.py:30-31
+  poly            tests/test_lsqfit.py:878-880
+  exp_poly        examples/empbayes.py:28-29
+  xerr_logistic   examples/x-err.py:40-43
+  NIST forms      examples/nist.py (line of each body given below)
+
+TEST INFRASTRUCTURE ONLY -- never imported by lsqfit_b200.
+"""
+import numpy as np
+
+from . import dual as D
+
+exp, log, cos, sin, arctan = D.exp, D.log, D.cos, D.sin, D.arctan
+pi = np.pi
+
+
+def _x(x, c=0):
+    x = np.asarray(x, dtype=float)
+    return x[:, c] if x.ndim == 2 else x
+
+
+def multiexp(x, p):
+    t = _x(x)
+    K = len(p) // 2
+    ans = 0.0
+    for k in range(K):
+        ans = ans + p[k] * exp(-p[K + k] * t)
+    return ans
+
+
+def multiexp_de(x, p):
+    t = _x(x)
+    K = len(p) // 2
+    E = D.cumsum(p[K:])
+    ans = 0.0
+    for k in range(K):
+        ans = ans + p[k] * exp(-E[k] * t)
+    return ans
+
+
+def simple(x, p):
+    """rows with x[:,1]==0: exp(a + x b); rows with x[:,1]==1: b/a."""
+    x = np.asarray(x, dtype=float)
+    t, kind = x[:, 0], x[:, 1]
+    a, b = p[0], p[1]
+    e = exp(a + b * t)
+    r = b / a
+    return e * (kind == 0) + r * (kind == 1)
+
+
+def offset_exp(x, p):
+    return p[0] + p[1] * exp(-p[2] * _x(x))
+
+
+def poly(x, p):
+    t = _x(x)
+    ans = 0.0
+    for n in range(len(p)):
+        ans = ans + p[n] * t ** n
+    return ans
+
+
+def exp_poly(x, p):
+    t = _x(x)
+    s = 0.0
+    for n in range(len(p)):
+        s = s + p[n] * t ** n
+    return exp(-s)
+
+
+def xerr_logistic(x, p):
+    """b0/(1+exp(b1 - b2 x_i))**(1/b3); the x_i are parameters p[4:]."""
+    b0, b1, b2, b3 = p[0], p[1], p[2], p[3]
+    xi = p[4:]
+    return b0 / ((1.0 + exp(b1 - b2 * xi)) ** (1.0 / b3))
+
+
+# ---- NIST StRD forms (examples/nist.py:<line>) ------------------------------
+
+def misra1a(x, b):          # :112 (also boxbod :1114)
+    return b[0] * (1 - exp(-b[1] * _x(x)))
+
+
+def chwirut(x, b):          # :145, :225
+    t = _x(x)
+    return exp(-b[0] * t) / (b[1] + b[2] * t)
+
+
+def lanczos(x, b):          # :249, :795, :822
+    t = _x(x)
+    return b[0] * exp(-b[1] * t) + b[2] * exp(-b[3] * t) + b[4] * exp(-b[5] * t)
+
+
+def gauss(x, b):            # :344, :441, :917
+    t = _x(x)
+    return (b[0] * exp(-b[1] * t) + b[2] * exp(-(t - b[3]) ** 2 / b[4] ** 2)
+            + b[5] * exp(-(t - b[6]) ** 2 / b[7] ** 2))
+
+
+def danwood(x, b):          # :462
+    t = _x(x)
+    return b[0] * exp(b[1] * np.log(t))     # x**b2 with x > 0
+
+
+def misra1b(x, b):          # :483
+    return b[0] * (1 - (1 + b[1] * _x(x) / 2) ** (-2))
+
+
+def misra1c(x, b):          # :940
+    return b[0] * (1 - (1 + 2 * b[1] * _x(x)) ** (-.5))
+
+
+def misra1d(x, b):          # :961
+    t = _x(x)
+    return b[0] * b[1] * t * ((1 + b[1] * t) ** (-1))
+
+
+def kirby2(x, b):           # :573
+    t = _x(x)
+    return (b[0] + b[1] * t + b[2] * t ** 2) / (1 + b[3] * t + b[4] * t ** 2)
+
+
+def hahn1(x, b):            # :659 (also thurber :1093)
+    t = _x(x)
+    return ((b[0] + b[1] * t + b[2] * t ** 2 + b[3] * t ** 3)
+            / (1 + b[4] * t + b[5] * t ** 2 + b[6] * t ** 3))
+
+
+def nelson(x, b):           # :723  (fitted to log(y), :719)
+    x = np.asarray(x, dtype=float)
+    x1, x2 = x[:, 0], x[:, 1]
+    return b[0] - b[1] * x1 * exp(-b[2] * x2)
+
+
+def mgh17(x, b):            # :749
+    t = _x(x)
+    return b[0] + b[1] * exp(-t * b[3]) + b[2] * exp(-t * b[4])
+
+
+def roszman1(x, b):         # :987
+    t = _x(x)
+    return b[0] - b[1] * t - arctan(b[2] / (t - b[3])) / pi
+
+
+def enso(x, b):             # :1043
+    t = _x(x)
+    return (b[0] + b[1] * cos(2 * pi * t / 12) + b[2] * sin(2 * pi * t / 12)
+            + b[4] * cos(2 * pi * t / b[3]) + b[5] * sin(2 * pi * t / b[3])
+            + b[7] * cos(2 * pi * t / b[6]) + b[8] * sin(2 * pi * t / b[6]))
+
+
+def mgh09(x, b):            # :1064 (also examples/p-corr.py:60-61)
+    t = _x(x)
+    return b[0] * (t ** 2 + t * b[1]) / (t ** 2 + t * b[2] + b[3])
+
+
+def rat42(x, b):            # :1134
+    return b[0] / (1 + exp(b[1] - b[2] * _x(x)))
+
+
+def mgh10(x, b):            # :1156
+    return b[0] * exp(b[1] / (_x(x) + b[2]))
+
+
+def eckerle4(x, b):         # :1190
+    t = _x(x)
+    return (b[0] / b[1]) * exp(-0.5 * ((t - b[2]) / b[1]) ** 2)
+
+
+def rat43(x, b):            # :1212
+    return b[0] / ((1 + exp(b[1] - b[2] * _x(x))) ** (1 / b[3]))
+
+
+def bennett5(x, b):         # :1291
+    return b[0] * (b[1] + _x(x)) ** (-1 / b[2])
+
+
+MODELS = dict(
+    multiexp=multiexp, multiexp_de=multiexp_de, simple=simple,
+    offset_exp=offset_exp, poly=poly, exp_poly=exp_poly,
+    xerr_logistic=xerr_logistic,
+    misra1a=misra1a, chwirut=chwirut, lanczos=lanczos, gauss=gauss,
+    danwood=danwood, misra1b=misra1b, misra1c=misra1c, misra1d=misra1d,
+    kirby2=kirby2, hahn1=hahn1, nelson=nelson, mgh17=mgh17,
+    roszman1=roszman1, enso=enso, mgh09=mgh09, rat42=rat42, mgh10=mgh10,
+    eckerle4=eckerle4, rat43=rat43, bennett5=bennett5,
+)
+
+# NIST problem name -> model form
+NIST_FORM = dict(
+    misra1a="misra1a", boxbod="misra1a", chwirut1="chwirut", chwirut2="chwirut",
+    lanczos1="lanczos", lanczos2="lanczos", lanczos3="lanczos",
+    gauss1="gauss", gauss2="gauss", gauss3="gauss", danwood="danwood",
+    misra1b="misra1b", misra1c="misra1c", misra1d="misra1d", kirby2="kirby2",
+    hahn1="hahn1", thurber="hahn1", nelson="nelson", mgh17="mgh17",
+    roszman1="roszman1", enso="enso", mgh09="mgh09", rat42="rat42",
+    mgh10="mgh10", eckerle4="eckerle4", rat43="rat43", bennett5="bennett5",
+)
+
+
+def value_and_jacobian(name, x, p):
+    """Model values f[ny] and G[ny, np] = df/dp via forward-mode AD."""
+    p = np.asarray(p, dtype=float)
+    out = MODELS[name](x, D.Dual.variables(p))
+    return D.value(out), D.deriv(out, p.size)

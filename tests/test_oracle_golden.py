@@ -1,0 +1,273 @@
+"""Pin the CPU oracle against the reference's own golden outputs (CPU only).
+
+Fixtures come from tests/golden/make_golden.py (generated from the reference
+tree: examples/*.out, examples/nist.py assert strings, NIST certified values,
+numeric pins in tests/test_lsqfit.py).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gvfmt
+from oracle.fit import nonlinear_fit
+from oracle.fitter import gammaQ, scipy_least_squares
+from oracle.whiten import PDF, cov_blocks
+from oracle import models as M
+
+
+def _expected_list(s):
+    return s[1:-1].replace(" +- ", "+-").split()
+
+
+def test_nist_all_27(nist_problems):
+    """examples/nist.py assert strings + examples/nist.out chi2/dof, Q, logGBF."""
+    assert len(nist_problems) == 27
+    for pr in nist_problems:
+        fit = nonlinear_fit(pr["form"], np.array(pr["x"]), pr["y"], pr["ysdev"],
+                            prior_mean=pr["prior_mean"], prior_cov=pr["prior_sdev"],
+                            p0=pr["p0"], tol=pr["tol"])
+        exp = _expected_list(pr["expected"])
+        for m, s, e in zip(fit.pmean, fit.p_sdev, exp):
+            assert gvfmt.agrees(m, s, e), (pr["name"], m, s, e)
+        o = pr["out"]
+        assert fit.dof == o["dof"]
+        assert gvfmt.agrees_g(fit.chi2 / fit.dof, o["chi2_dof"], 2), pr["name"]
+        assert gvfmt.agrees_g(fit.Q, o["Q"], 2), pr["name"]
+        assert gvfmt.agrees_g(fit.logGBF, o["logGBF"], 5), pr["name"]
+        # NIST certified values: priors are 200x wide, so p and sdev agree closely
+        cert, csd = np.array(pr["certified"]), np.array(pr["certified_sdev"])
+        if pr["name"] != "lanczos1":        # sigma_y ~ 1e-13: roundoff-dominated (nist.py:18-20)
+            assert np.max(np.abs(fit.pmean - cert) / csd) < 1e-3, pr["name"]
+        assert np.max(np.abs(fit.p_sdev / csd - 1)) < 1e-3, pr["name"]
+        # fit.p (D C D^T) and fit.palt (fit.cov) must agree (check_roundoff, __init__.py:884-895)
+        assert np.allclose(fit.p_sdev, fit.psdev, rtol=1e-5)
+
+
+def test_nist_model_values(nist_problems):
+    """oracle models == the reference's own fcn closures at start and certified points."""
+    for pr in nist_problems:
+        x = np.array(pr["x"])
+        f = M.MODELS[pr["form"]]
+        np.testing.assert_allclose(f(x, np.array(pr["p0"])), pr["f_p0"], rtol=1e-13, atol=0)
+        np.testing.assert_allclose(f(x, np.array(pr["certified"])), pr["f_cert"], rtol=1e-13, atol=0)
+
+
+def test_model_jacobians_fd():
+    """Dual-number Jacobians vs central finite differences for every model."""
+    rng = np.random.default_rng(1)
+    for name in M.MODELS:
+        npar = {"multiexp": 6, "multiexp_de": 6, "simple": 2, "offset_exp": 3, "poly": 5,
+                "exp_poly": 4, "xerr_logistic": 4 + 7, "misra1a": 2, "chwirut": 3,
+                "lanczos": 6, "gauss": 8, "danwood": 2, "misra1b": 2, "misra1c": 2,
+                "misra1d": 2, "kirby2": 5, "hahn1": 7, "nelson": 3, "mgh17": 5,
+                "roszman1": 4, "enso": 9, "mgh09": 4, "rat42": 3, "mgh10": 3,
+                "eckerle4": 3, "rat43": 4, "bennett5": 3}[name]
+        ny = 7
+        x = rng.uniform(0.5, 2.0, size=(ny, 2))
+        if name == "simple":
+            x[:, 1] = [0, 0, 0, 1, 0, 1, 0]
+        p = rng.uniform(0.5, 1.5, size=npar)
+        f, G = M.value_and_jacobian(name, x, p)
+        for j in range(npar):
+            h = 1e-6 * max(1.0, abs(p[j]))
+            pp, pm = p.copy(), p.copy()
+            pp[j] += h
+            pm[j] -= h
+            fd = (M.MODELS[name](x, pp) - M.MODELS[name](x, pm)) / (2 * h)
+            np.testing.assert_allclose(G[:, j], fd, rtol=2e-7, atol=1e-9, err_msg=name)
+
+
+def _simple_fit(ex):
+    ny = len(ex["ymean"])
+    ycov = np.zeros((ny, ny))
+    i = 0
+    for b in ex["ycov_blocks"]:
+        b = np.array(b)
+        ycov[i:i + len(b), i:i + len(b)] = b
+        i += len(b)
+    return nonlinear_fit(ex["model"], np.array(ex["x"]), ex["ymean"], ycov,
+                         prior_mean=ex["prior_mean"], prior_cov=ex["prior_sdev"])
+
+
+def test_simple(golden_examples):
+    """examples/simple.out:2-6 and the error budget :26-31 (pins D of _getp)."""
+    ex = golden_examples["simple"]
+    fit = _simple_fit(ex)
+    o = ex["out"]
+    for m, s, e in zip(fit.pmean, fit.p_sdev, o["p"]):
+        assert gvfmt.agrees(m, s, e)
+    assert fit.dof == o["dof"] and fit.svdn == o["svdn"]
+    assert gvfmt.agrees_g(fit.chi2 / fit.dof, o["chi2_dof"], 2)
+    assert gvfmt.agrees_g(fit.Q, o["Q"], 2)
+    assert gvfmt.agrees_g(fit.logGBF, o["logGBF"], 5)
+    fm, fc = fit.fcn_values_cov()
+    for m, s, e in zip(fm, np.sqrt(np.diag(fc)), o["fit"]):
+        assert gvfmt.agrees(m, s, e)
+    # error budget: partial sdev of outputs (a, b/a, b) from y and from prior
+    D = fit.D                              # d p / d (y, prior)
+    C = fit.yp_pdf.cov
+    a, b = fit.pmean
+    T = np.array([[1, 0], [-b / a ** 2, 1 / a], [0, 1]])    # outputs a, b/a, b
+    vals = np.array([a, b / a, b])
+    ny = fit.ny
+    Dy, Dp = T @ D[:, :ny], T @ D[:, ny:]
+    ey = np.sqrt(np.diag(Dy @ C[:ny, :ny] @ Dy.T)) / np.abs(vals) * 100
+    ep = np.sqrt(np.diag(Dp @ C[ny:, ny:] @ Dp.T)) / np.abs(vals) * 100
+    np.testing.assert_allclose(ey, o["budget"]["y"], atol=0.006)
+    np.testing.assert_allclose(ep, o["budget"]["prior"], atol=0.006)
+    np.testing.assert_allclose(np.sqrt(ey ** 2 + ep ** 2), o["budget"]["total"], atol=0.006)
+
+
+def _yvsx(ex, nexp, p0=None):
+    pm = np.concatenate([np.full(nexp, 0.5), np.arange(1, nexp + 1.)])
+    return nonlinear_fit("multiexp", np.array(ex["x"])[:, None], ex["ymean"], np.array(ex["ycov"]),
+                         prior_mean=pm, prior_cov=np.full(2 * nexp, 0.4), p0=p0)
+
+
+def test_y_vs_x(golden_examples):
+    """examples/y-vs-x.out: svdcut 1e-12 modifies exactly one mode; four fits."""
+    ex = golden_examples["y-vs-x"]
+    for nexp in (1, 2, 3, 4):
+        fit = _yvsx(ex, nexp)
+        o = ex["out"][str(nexp)]
+        assert fit.svdn == o["svdn"] and fit.dof == o["dof"]
+        assert gvfmt.agrees_g(fit.chi2 / fit.dof, o["chi2_dof"], 2)
+        assert gvfmt.agrees_g(fit.Q, o["Q"], 2)
+        assert gvfmt.agrees_g(fit.logGBF, o["logGBF"], 5)
+        for m, s, e in zip(fit.pmean, fit.p_sdev, o["p"]):
+            assert gvfmt.agrees(m, s, e), (nexp, m, s, e)
+        if nexp == 3:
+            a, E = fit.pmean[:3], fit.pmean[3:]
+            C = fit.p_cov
+            def ratio(i, j, off):
+                g = np.zeros(6)
+                g[off + i] = 1 / fit.pmean[off + j]
+                g[off + j] = -fit.pmean[off + i] / fit.pmean[off + j] ** 2
+                return fit.pmean[off + i] / fit.pmean[off + j], np.sqrt(g @ C @ g)
+            r = ex["ratios"]
+            assert gvfmt.agrees(*ratio(1, 0, 3), r["E1_E0"])
+            assert gvfmt.agrees(*ratio(2, 0, 3), r["E2_E0"])
+            assert gvfmt.agrees(*ratio(1, 0, 0), r["a1_a0"])
+            assert gvfmt.agrees(*ratio(2, 0, 0), r["a2_a0"])
+
+
+def test_p_corr(golden_examples):
+    """examples/p-corr.out: correlated prior block (2x2) + diag data."""
+    ex = golden_examples["p-corr"]
+    y = np.array([gvfmt.parse(s)[:2] for s in ex["y"]])
+    fit = nonlinear_fit(ex["model"], np.array(ex["x"])[:, None], y[:, 0], y[:, 1],
+                        prior_mean=ex["prior_mean"], prior_cov=np.array(ex["prior_cov"]))
+    o = ex["out"]
+    assert fit.dof == o["dof"] and fit.svdn == o["svdn"]
+    assert gvfmt.agrees_g(fit.chi2 / fit.dof, o["chi2_dof"], 2)
+    assert gvfmt.agrees_g(fit.Q, o["Q"], 2)
+    assert gvfmt.agrees_g(fit.logGBF, o["logGBF"], 5)
+    for m, s, e in zip(fit.pmean, fit.p_sdev, o["p"]):
+        assert gvfmt.agrees(m, s, e)
+    C = fit.p_cov
+    assert "%.4f" % (C[0, 1] / np.sqrt(C[0, 0] * C[1, 1])) == o["corr_p0_p1"]
+    p = fit.pmean
+    g = np.array([-p[1] / p[0] ** 2, 1 / p[0], 0, 0])
+    assert gvfmt.agrees(p[1] / p[0], np.sqrt(g @ C @ g), o["p1_p0"])
+    g = np.array([0, 0, -p[3] / p[2] ** 2, 1 / p[2]])
+    assert gvfmt.agrees(p[3] / p[2], np.sqrt(g @ C @ g), o["p3_p2"])
+
+
+def test_x_err(golden_examples):
+    """examples/x-err.out: 19 parameters, fcn(p) without x."""
+    ex = golden_examples["x-err"]
+    y = np.array([gvfmt.parse(s)[:2] for s in ex["y"]])
+    xp = np.array([gvfmt.parse(s)[:2] for s in ex["xprior"]])
+    bp = np.array([gvfmt.parse(s)[:2] for s in ex["bprior"]])
+    pm = np.concatenate([bp[:, 0], xp[:, 0]])
+    ps = np.concatenate([bp[:, 1], xp[:, 1]])
+    # the golden was printed by the reference's default fitter (gsl_multifit, Moré
+    # scaling); scipy's unscaled trf walks to a different local minimum from the default
+    # start, its scaled variant (x_scale='jac' == Moré) lands on the printed one.
+    fit = nonlinear_fit(ex["model"], np.zeros((len(y), 1)), y[:, 0], y[:, 1],
+                        prior_mean=pm, prior_cov=ps, x_scale="jac")
+    o = ex["out"]
+    assert fit.dof == o["dof"]
+    assert gvfmt.agrees_g(fit.chi2 / fit.dof, o["chi2_dof"], 2)
+    assert gvfmt.agrees_g(fit.Q, o["Q"], 2)
+    assert gvfmt.agrees_g(fit.logGBF, o["logGBF"], 5)
+    for m, s, e in zip(fit.pmean, fit.p_sdev, o["p"]):
+        assert gvfmt.agrees(m, s, e), (m, s, e)
+
+
+def test_gammaQ(golden_examples):
+    """tests/test_lsqfit.py:1887-1901"""
+    for a, x, gax, gxa in golden_examples["gammaQ"]:
+        np.testing.assert_allclose(gax, gammaQ(a, x), rtol=0.01)
+        np.testing.assert_allclose(gxa, gammaQ(x, a), rtol=0.01)
+
+
+def test_fitter_stopping_codes():
+    """tests/test_lsqfit.py:1754-1777 (scipy_least_squares called directly)."""
+    nx = 3
+    xans = np.arange(nx) + 1.
+
+    def f(x):
+        return (x - xans) ** 2 + (x - xans) ** 4
+
+    ans = scipy_least_squares(x0=np.ones(nx), n=nx, f=f, tol=(1e-15, 1e-8, 1e-15), method='trf')
+    np.testing.assert_allclose(ans.x, xans, rtol=1e-3)
+    assert ans.stopping_criterion == 2
+    ans = scipy_least_squares(x0=np.zeros(nx), n=nx, f=f, tol=(1e-8, 1e-15, 1e-15), method='lm')
+    np.testing.assert_allclose(ans.x, xans, rtol=1e-3)
+    assert ans.stopping_criterion == 1
+    ans = scipy_least_squares(x0=np.zeros(nx), n=nx, f=f, tol=(1e-15, 1e-8, 1e-15), method='dogbox')
+    assert ans.stopping_criterion == 2
+    np.testing.assert_allclose(ans.x, xans, rtol=1e-3)
+
+
+def test_fitters_two_point():
+    """tests/test_lsqfit.py:1811-1833: str(fit.p) == '[0.904(98) 2.17(19)]' for every method."""
+    for method in ("trf", "dogbox", "lm"):
+        fit = nonlinear_fit(lambda x, p: p, None, [0.9, 2.2], [0.1, 0.2],
+                            prior_mean=[1.0, 2.0], prior_cov=[0.5, 0.5], method=method)
+        assert gvfmt.agrees(fit.pmean[0], fit.p_sdev[0], "0.904(98)")
+        assert gvfmt.agrees(fit.pmean[1], fit.p_sdev[1], "2.17(19)")
+
+
+def test_whiten_pins():
+    """tests/test_lsqfit.py:960-962, 976-978 (1x1 weights), :1011-1017 (block inverse),
+    :932-943 (logdet) and the svdcut known answers of :581-589."""
+    pdf = PDF([1., 10., np.log(2.)], [2., 4., 2.], svdcut=0)
+    np.testing.assert_array_equal(pdf.i_invwgts[0][0], [0, 1, 2])
+    np.testing.assert_array_equal(pdf.i_invwgts[0][1], [0.5, 0.25, 0.5])
+    assert pdf.nchiv == 3 and pdf.nmod == 0
+    # correlated pair (0,2), index 1 alone  (test case 3, :1000-1017)
+    one_var = 1e-6
+    cov = np.diag([4.0 + one_var, 16.0, 16.0 + 4 * one_var])
+    cov[0, 2] = cov[2, 0] = 2 * one_var
+    pdf = PDF([1, 10, 2], cov, svdcut=0.0)
+    np.testing.assert_array_equal(pdf.i_invwgts[0][0], [1])
+    np.testing.assert_array_equal(pdf.i_invwgts[1][0], [0, 2])
+    np.testing.assert_allclose(pdf.icov(), np.linalg.inv(cov), rtol=1e-10)
+    np.testing.assert_allclose(pdf.logdet, np.log(np.linalg.det(cov)), rtol=1e-12)
+    # wavg pins (:581-589): data [(a+b)/2, (a+c)/2, a], a,b,c = 1(1); var = 1/(1^T C^-1 1)
+    cov = np.array([[0.5, 0.25, 0.5], [0.25, 0.5, 0.5], [0.5, 0.5, 1.0]])
+    one = np.ones(3)
+    pdf = PDF(one, cov, svdcut=1 - 1e-16)
+    np.testing.assert_allclose(1 / (one @ pdf.icov() @ one), 0.4561552812808828, rtol=1e-7)
+    pdf = PDF(one, cov, svdcut=1e-18)
+    np.testing.assert_allclose(1 / (one @ pdf.icov() @ one), 1. / 3., rtol=1e-7)
+    # doc/source/overview.rst:1569-1580: svdcut 1e-4 on [[1,1,0],[1,1,0],[0,0,1e-20]]
+    pdf = PDF(np.zeros(3), np.array([[1., 1, 0], [1, 1, 0], [0, 0, 1e-20]]), svdcut=1e-4)
+    np.testing.assert_allclose(pdf.cov, [[1.0001, 0.9999, 0], [0.9999, 1.0001, 0], [0, 0, 1e-20]],
+                               rtol=1e-12)
+    assert pdf.nmod == 1
+
+
+def test_whiten_negative_svdcut_drops_modes():
+    """tests/test_lsqfit.py:830-841 -- svdcut<0 removes modes, nchiv shrinks."""
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(6, 3))
+    cov = A @ A.T + 1e-14 * np.eye(6)
+    pdf = PDF(np.zeros(6), cov, svdcut=-1e-10)
+    assert pdf.nchiv == 3 and pdf.nmod == 3
+    blocks = cov_blocks(np.diag([1., 2, 3]))
+    assert list(blocks[0]) == [0, 1, 2] and blocks[1] == []
