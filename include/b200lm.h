@@ -1,0 +1,156 @@
+/* b200lm -- C ABI of the B200-native batched Levenberg-Marquardt engine.
+ *
+ * This is the drop-in boundary for ONE hot path of gplepage/lsqfit (v13.3.1):
+ *   whiten  ->  residual + Jacobian  ->  trust-region LM fit  ->  covariance propagation
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference tree).  The reference is Python; a maintainer binds these symbols with
+ * ctypes.  No torch / C++ types cross this boundary: plain
+ * pointers and sizes only.
+ *
+ * Conventions
+ *   - all matrices are row-major IEEE fp64; index arrays are int32
+ *   - pointers named d_* are CUDA DEVICE pointers on the handle's device;
+ *     pointers named h_* are HOST pointers
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream)
+ *   - every function returns 0 on success, a negative B200LM_E* code otherwise and
+ *     never throws; b200lm_last_error() gives the message.  Non-convergence of a
+ *     fit is data (status[] / stopping criterion), not an error -- the reference's
+ *     convention (src/lsqfit/_gsl.pyx:686-717, src/lsqfit/_scipy.py:177-181)
+ *   - a handle is thread-compatible: one handle per host thread
+ */
+#ifndef B200LM_H
+#define B200LM_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200LM_VERSION 100          /* 0.1.0 */
+
+#define B200LM_OK          0
+#define B200LM_EINVAL     -1        /* bad argument */
+#define B200LM_ENOFUNCTOR -2        /* (family, np) not in the device functor registry */
+#define B200LM_ECUDA      -3        /* CUDA runtime error */
+#define B200LM_ENOMEM     -4
+#define B200LM_ESIZE      -5        /* problem does not fit the kernel's shared-memory plan */
+
+typedef struct b200lm_handle_s* b200lm_handle;
+
+/* ---- library ------------------------------------------------------------------------ */
+int b200lm_version(void);
+/* message of the last failing call on `h` (or of the last failing call without a handle
+ * when h == NULL).  Mirrors the reference's fit.error convention. */
+const char* b200lm_last_error(b200lm_handle h);
+/* number of visible CUDA devices (0 if none / driver missing) */
+int b200lm_device_count(void);
+
+/* ---- device functor registry ---------------------------------------------------------
+ * The reference receives the fit function as an opaque Python callable
+ * (src/lsqfit/__init__.py:566, 1997-2042: flatfcn).  Here the model is one of a registry
+ * of CUDA device functors, selected by family name + number of parameters. */
+int b200lm_functor_count(void);
+int b200lm_functor_info(int i, int* family, int* np, int* nx, const char** name);
+int b200lm_functor_family(const char* name);            /* family id, or B200LM_ENOFUNCTOR */
+
+/* ---- plan ---------------------------------------------------------------------------
+ * One handle per (functor, ny, np, device).  noprior != 0 means fits without a prior
+ * (src/lsqfit/_utilities.pyx:74-75): the mean vector then has ny entries, otherwise
+ * N = ny + np entries (data means followed by prior means, :76-77). */
+int b200lm_create(int family, int ny, int np, int nx, int noprior, int device, b200lm_handle* out);
+void b200lm_destroy(b200lm_handle h);
+
+/* model constants: the x array of flatfcn.keywords['x'] (src/lsqfit/__init__.py:1997-2012),
+ * row-major [ny][nx].  Host pointer; copied once. */
+int b200lm_set_const(b200lm_handle h, const double* h_x, int n);
+
+/* whitening description == the reference's yp_pdf.i_invwgts
+ * (consumed at src/lsqfit/_utilities.pyx:59-61, 85-93):
+ *   entry 0 : ndiag 1x1 blocks, (diag_idx[i], diag_w[i] = 1/sigma)
+ *   entry k : block k with blk_nin[k] input indices blk_idx[...] and a
+ *             blk_nout[k] x blk_nin[k] row-major weight matrix W_k in blk_w[...]
+ *             (sum_i outer(W_k[i], W_k[i]) = inverse covariance of the block)
+ * Indices address the concatenated y(+)prior vector.  Host pointers; copied once.
+ * Residual order (chiv) = diag entries in the given order, then block rows. */
+int b200lm_set_weights(b200lm_handle h, int ndiag, const int* h_diag_idx, const double* h_diag_w,
+                       int nblk, const int* h_blk_nin, const int* h_blk_nout,
+                       const int* h_blk_idx, const double* h_blk_w);
+int b200lm_nchiv(b200lm_handle h);
+
+/* ---- the fit --------------------------------------------------------------------------
+ * Replaces   fit = FITTERS[fitter](p0, nf, chiv, tol=tol, maxit=maxit, **fitterargs)
+ * (src/lsqfit/__init__.py:662-664) and the plugin behind it (src/lsqfit/_scipy.py:115-181,
+ * src/lsqfit/_gsl.pyx:563-723) for a whole batch of B independent fits that share the
+ * model, x and whitening:
+ *   d_mean   [B][N] means of y(+)prior per fit (mean_stride = N) or one shared vector
+ *            (mean_stride = 0)  -- what bootstrapped_fit_iter / simulated_fit_iter vary
+ *            (src/lsqfit/__init__.py:1619-1623, 545-552)
+ *   d_p0     [B][np] starting points (p0_stride = np) or one shared start (p0_stride = 0)
+ *   xtol, gtol, ftol, maxit   as normalised at src/lsqfit/_scipy.py:124-132
+ *   scaler   1 = More' column scaling (GSL scaler='more', scipy x_scale='jac'); 0 = none
+ * Outputs (device): d_x [B][np], d_chi2 [B] (= sum f^2, __init__.py:667),
+ *   d_cov [B][np][np] (= inv(J^T J), __init__.py:668), d_logdet [B] (= log det J^T J,
+ *   __init__.py:712-719), d_nit [B] (function evaluations, _scipy.py:167),
+ *   d_status [B] solver status 0 maxit / 1 gtol / 2 ftol / 3 xtol / 4 ftol+xtol /
+ *   -1 non-finite start (map to stopping_criterion with {0:0,1:2,2:3,3:1,4:1},
+ *   _scipy.py:178-181); optional d_f [B][nchiv], d_J [B][nchiv][np] (NULL to skip). */
+int b200lm_fit_batch(b200lm_handle h, int B,
+                     const double* d_mean, long long mean_stride,
+                     const double* d_p0, long long p0_stride,
+                     double xtol, double gtol, double ftol, int maxit, int scaler,
+                     double* d_x, double* d_chi2, double* d_cov, double* d_logdet,
+                     int* d_nit, int* d_status, double* d_f, double* d_J, void* stream);
+
+/* Same call with HOST buffers: copies inputs to the device, runs the batch, copies the
+ * results back and synchronises.  This is the call the Python plugin makes for users
+ * whose data live in numpy arrays (and the path bench.py reports as `e2e`). */
+int b200lm_fit_batch_host(b200lm_handle h, int B,
+                          const double* h_mean, long long mean_stride,
+                          const double* h_p0, long long p0_stride,
+                          double xtol, double gtol, double ftol, int maxit, int scaler,
+                          double* h_x, double* h_chi2, double* h_cov, double* h_logdet,
+                          int* h_nit, int* h_status, double* h_f, double* h_J);
+
+/* totals of the last fit_batch on this handle: out[0] function evaluations, out[1] Jacobian
+ * evaluations, out[2] Cholesky factorisations.  Synchronises the handle's last stream. */
+int b200lm_last_stats(b200lm_handle h, unsigned long long out[3]);
+/* number of kernel launches issued through this handle so far */
+long long b200lm_launch_count(b200lm_handle h);
+
+/* ---- residual / Jacobian test hook ----------------------------------------------------
+ * chiv(p) and its Jacobian at B parameter vectors (src/lsqfit/_utilities.pyx:65-94 called
+ * with floats and with valder+p, src/lsqfit/_scipy.py:146-154).  d_f [B][nchiv],
+ * d_J [B][nchiv][np], d_chi2 [B]; any may be NULL. */
+int b200lm_residual_jacobian(b200lm_handle h, int B, const double* d_p, long long p_stride,
+                             const double* d_mean, long long mean_stride,
+                             double* d_f, double* d_J, double* d_chi2, void* stream);
+
+/* ---- whitening (svdcut / eps) ----------------------------------------------------------
+ * Replaces gvar.PDF(concat(y, prior), svdcut=, eps=) for the correlated blocks
+ * (call sites src/lsqfit/__init__.py:1895,1898; semantics doc/source/overview.rst:1546-1611).
+ * Batched over nblk blocks on `device`; block k is n[k] x n[k], stored contiguously one
+ * after another in d_cov (row-major).  Per block: D = diag^-1/2, corr = D cov D,
+ * eigen-decomposition by parallel Jacobi in shared memory, then
+ *   svdcut > 0 : eigenvalues < svdcut*max are replaced by svdcut*max (nmod counts them)
+ *   svdcut < 0 : those modes are dropped (nout[k] < n[k])
+ *   use_eps    : corr += eps*norm_inf(corr) I and inverse-Cholesky instead
+ * Outputs: d_w (same layout as d_cov) rows W[i] = val_i^-1/2 vec_i D, largest eigenvalue
+ * first, unused rows zero; d_cov_out the corrected covariance; d_nout, d_nmod [nblk];
+ * d_logdet [nblk] (log det of the corrected block).  h_n is a host array. */
+int b200lm_whiten(int device, int nblk, const int* h_n, const double* d_cov,
+                  double svdcut, double eps, int use_eps,
+                  double* d_w, double* d_cov_out, int* d_nout, int* d_nmod, double* d_logdet,
+                  void* stream);
+
+/* ---- covariance propagation -----------------------------------------------------------
+ * Replaces nonlinear_fit._getp (src/lsqfit/__init__.py:897-922) with its chivw call
+ * (src/lsqfit/_utilities.pyx:110-139):  D = cov . G^T . C^-1  (np x N, derivative of the
+ * best-fit parameters with respect to y(+)prior) and  cov(p) = D . C . D^T  with C the
+ * (svd-corrected) covariance of y(+)prior given densely in d_C [N][N] (shared by the batch).
+ * d_x, d_cov [B][...] are the fit results; outputs d_D [B][np][N], d_covp [B][np][np]. */
+int b200lm_propagate(b200lm_handle h, int B, const double* d_x, const double* d_cov,
+                     const double* d_C, double* d_D, double* d_covp, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LM_H */

@@ -1,0 +1,347 @@
+// C-ABI layer of libb200lm.so: plan objects, functor dispatch, launches.
+// Declarations and the reference interfaces they replace: include/b200lm.h.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include "../../include/b200lm.h"
+#include "handle.h"
+
+using namespace b200lm;
+
+static thread_local std::string g_err;
+
+namespace b200lm {
+int set_error(b200lm_handle_s* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    g_err = msg;
+    return code;
+}
+int cuda_fail(b200lm_handle_s* h, cudaError_t e, const char* what) {
+    return set_error(h, B200LM_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+void fill_params(b200lm_handle_s* h, FitParams& P) {
+    memset(&P, 0, sizeof(P));
+    P.ny = h->ny; P.np = h->np; P.N = h->N; P.nchiv = h->nchiv; P.nx = h->nx; P.noprior = h->noprior;
+    P.x = h->d_x;
+    P.nd_fn = h->nd_fn; P.dfn_idx = h->d_dfn_idx; P.dfn_w = h->d_dfn_w;
+    P.nd_pr = h->nd_pr; P.dpr_idx = h->d_dpr_idx; P.dpr_w = h->d_dpr_w;
+    P.nblk = h->nblk; P.blk = h->d_blk; P.blk_idx = h->d_blk_idx; P.blk_wt = h->d_blk_wt;
+    P.wt_total = h->wt_total;
+    P.rb = h->rb;
+    P.counter = h->d_counter;
+    P.stats = h->d_stats;
+}
+}  // namespace b200lm
+
+static std::vector<FunctorEntry>& registry() {
+    static std::vector<FunctorEntry> r;
+    if (r.empty()) {
+        int n = 0;
+        const FunctorEntry* e;
+        e = registry_multiexp(&n); r.insert(r.end(), e, e + n);
+        e = registry_nist_a(&n);   r.insert(r.end(), e, e + n);
+        e = registry_nist_b(&n);   r.insert(r.end(), e, e + n);
+        e = registry_misc(&n);     r.insert(r.end(), e, e + n);
+    }
+    return r;
+}
+
+#define CUDA_TRY(h, call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(h, e_, what); } while (0)
+
+template <class T>
+static cudaError_t upload(T** dst, const T* src, size_t n) {
+    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)dst, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+extern "C" {
+
+int b200lm_version(void) { return B200LM_VERSION; }
+
+const char* b200lm_last_error(b200lm_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int b200lm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int b200lm_functor_count(void) { return (int)registry().size(); }
+
+int b200lm_functor_info(int i, int* family, int* np, int* nx, const char** name) {
+    auto& r = registry();
+    if (i < 0 || i >= (int)r.size()) return set_error(nullptr, B200LM_EINVAL, "functor index out of range");
+    if (family) *family = r[i].family;
+    if (np) *np = r[i].np;
+    if (nx) *nx = r[i].nx;
+    if (name) *name = r[i].name;
+    return B200LM_OK;
+}
+
+int b200lm_functor_family(const char* name) {
+    if (!name) return B200LM_EINVAL;
+    for (auto& e : registry()) if (strcmp(e.name, name) == 0) return e.family;
+    return set_error(nullptr, B200LM_ENOFUNCTOR, std::string("unknown functor family: ") + name);
+}
+
+int b200lm_create(int family, int ny, int np, int nx, int noprior, int device, b200lm_handle* out) {
+    if (!out) return set_error(nullptr, B200LM_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (ny <= 0 || np <= 0) return set_error(nullptr, B200LM_EINVAL, "ny and np must be positive");
+    const FunctorEntry* fe = nullptr;
+    for (auto& e : registry()) if (e.family == family && e.np == np) { fe = &e; break; }
+    if (!fe) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "no device functor for family %d with np=%d", family, np);
+        return set_error(nullptr, B200LM_ENOFUNCTOR, buf);
+    }
+    if (nx != fe->nx) return set_error(nullptr, B200LM_EINVAL, "nx does not match the functor");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return set_error(nullptr, B200LM_ECUDA, "no CUDA device available (this engine has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return set_error(nullptr, B200LM_EINVAL, "bad device index");
+    CUDA_TRY(nullptr, cudaSetDevice(device), "cudaSetDevice");
+    b200lm_handle_s* h = new b200lm_handle_s();
+    h->device = device; h->fe = fe; h->ny = ny; h->np = np; h->nx = nx; h->noprior = noprior ? 1 : 0;
+    h->N = noprior ? ny : ny + np;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaGetDeviceProperties"); }
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_budget = prop.sharedMemPerBlockOptin;
+    e = cudaMalloc((void**)&h->d_counter, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_stats, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { b200lm_destroy(h); return cuda_fail(nullptr, e, "handle allocation"); }
+    *out = h;
+    return B200LM_OK;
+}
+
+void b200lm_destroy(b200lm_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_x);
+    cudaFree(h->d_dfn_idx); cudaFree(h->d_dfn_w); cudaFree(h->d_dpr_idx); cudaFree(h->d_dpr_w);
+    cudaFree(h->d_blk); cudaFree(h->d_blk_idx); cudaFree(h->d_blk_wt); cudaFree(h->d_wfull);
+    cudaFree(h->d_counter); cudaFree(h->d_stats); cudaFree(h->d_stage); cudaFree(h->d_scratch);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int b200lm_set_const(b200lm_handle h, const double* h_x, int n) {
+    if (!h || !h_x) return set_error(h, B200LM_EINVAL, "NULL argument");
+    if (n != h->ny * h->nx) return set_error(h, B200LM_EINVAL, "x must have ny*nx entries");
+    CUDA_TRY(h, cudaSetDevice(h->device), "cudaSetDevice");
+    CUDA_TRY(h, upload(&h->d_x, h_x, (size_t)n), "upload x");
+    h->have_const = true;
+    return B200LM_OK;
+}
+
+int b200lm_set_weights(b200lm_handle h, int ndiag, const int* diag_idx, const double* diag_w,
+                       int nblk, const int* blk_nin, const int* blk_nout,
+                       const int* blk_idx, const double* blk_w) {
+    if (!h) return set_error(h, B200LM_EINVAL, "NULL handle");
+    if (ndiag < 0 || nblk < 0 || (ndiag > 0 && (!diag_idx || !diag_w)) ||
+        (nblk > 0 && (!blk_nin || !blk_nout || !blk_idx || !blk_w)))
+        return set_error(h, B200LM_EINVAL, "bad weight description");
+    CUDA_TRY(h, cudaSetDevice(h->device), "cudaSetDevice");
+    const int N = h->N;
+    std::vector<char> seen(N, 0);
+    // 1x1 blocks: data rows first (in the given order), then prior rows -- this is the
+    // reference's chiv order because gvar lists 1x1 indices in ascending order.
+    std::vector<int> fn_idx, pr_idx; std::vector<double> fn_w, pr_w;
+    bool prior_seen = false;
+    for (int i = 0; i < ndiag; ++i) {
+        const int idx = diag_idx[i];
+        if (idx < 0 || idx >= N || seen[idx]) return set_error(h, B200LM_EINVAL, "diag index out of range or repeated");
+        seen[idx] = 1;
+        if (idx < h->ny) {
+            if (prior_seen) return set_error(h, B200LM_EINVAL, "diag indices must list data rows before prior rows");
+            fn_idx.push_back(idx); fn_w.push_back(diag_w[i]);
+        } else { prior_seen = true; pr_idx.push_back(idx); pr_w.push_back(diag_w[i]); }
+    }
+    std::vector<BlockDesc> blk(nblk);
+    std::vector<double> wt;
+    int idx_off = 0, chiv_off = ndiag, w_off = 0, rb = 64;
+    for (int k = 0; k < nblk; ++k) {
+        const int nin = blk_nin[k], nout = blk_nout[k];
+        if (nin <= 0 || nout < 0 || nout > nin) return set_error(h, B200LM_EINVAL, "bad block shape");
+        for (int j = 0; j < nin; ++j) {
+            const int idx = blk_idx[idx_off + j];
+            if (idx < 0 || idx >= N || seen[idx]) return set_error(h, B200LM_EINVAL, "block index out of range or repeated");
+            seen[idx] = 1;
+        }
+        BlockDesc& b = blk[k];
+        b.n_in = nin; b.n_out = nout; b.ldw = (nout + 7) & ~7; if (b.ldw == 0) b.ldw = 8;
+        b.idx_off = idx_off; b.wt_off = (int)wt.size(); b.chiv_off = chiv_off;
+        wt.resize(wt.size() + (size_t)nin * b.ldw, 0.0);
+        for (int r = 0; r < nout; ++r)
+            for (int j = 0; j < nin; ++j)
+                wt[b.wt_off + (size_t)j * b.ldw + r] = blk_w[w_off + (size_t)r * nin + j];
+        rb = std::max(rb, nout <= 64 ? nin : nin + 64);
+        idx_off += nin; w_off += nin * nout; chiv_off += nout;
+    }
+    for (int i = 0; i < N; ++i)
+        if (!seen[i]) return set_error(h, B200LM_EINVAL, "every y(+)prior entry must appear in exactly one block");
+    // does at least one warp fit?
+    if (h->fe->per_warp_bytes(rb) > h->smem_budget)
+        return set_error(h, B200LM_ESIZE, "correlated block too large for the per-warp shared-memory plan");
+    h->nd_fn = (int)fn_idx.size(); h->nd_pr = (int)pr_idx.size();
+    CUDA_TRY(h, upload(&h->d_dfn_idx, fn_idx.data(), fn_idx.size()), "upload weights");
+    CUDA_TRY(h, upload(&h->d_dfn_w, fn_w.data(), fn_w.size()), "upload weights");
+    CUDA_TRY(h, upload(&h->d_dpr_idx, pr_idx.data(), pr_idx.size()), "upload weights");
+    CUDA_TRY(h, upload(&h->d_dpr_w, pr_w.data(), pr_w.size()), "upload weights");
+    CUDA_TRY(h, upload(&h->d_blk, blk.data(), blk.size()), "upload weights");
+    CUDA_TRY(h, upload(&h->d_blk_idx, blk_idx, (size_t)idx_off), "upload weights");
+    CUDA_TRY(h, upload(&h->d_blk_wt, wt.data(), wt.size()), "upload weights");
+    h->nblk = nblk; h->wt_total = (int)wt.size(); h->rb = rb; h->nchiv = chiv_off;
+    h->h_diag_idx.assign(diag_idx, diag_idx + ndiag); h->h_diag_w.assign(diag_w, diag_w + ndiag);
+    h->h_blk = blk; h->h_blk_idx.assign(blk_idx, blk_idx + idx_off);
+    if (h->d_wfull) { cudaFree(h->d_wfull); h->d_wfull = nullptr; }
+    h->have_weights = true;
+    return B200LM_OK;
+}
+
+int b200lm_nchiv(b200lm_handle h) { return h ? h->nchiv : B200LM_EINVAL; }
+
+static int check_ready(b200lm_handle h) {
+    if (!h) return set_error(h, B200LM_EINVAL, "NULL handle");
+    if (!h->have_weights) return set_error(h, B200LM_EINVAL, "b200lm_set_weights has not been called");
+    if (!h->have_const) return set_error(h, B200LM_EINVAL, "b200lm_set_const has not been called");
+    return B200LM_OK;
+}
+
+int b200lm_fit_batch(b200lm_handle h, int B,
+                     const double* d_mean, long long mean_stride,
+                     const double* d_p0, long long p0_stride,
+                     double xtol, double gtol, double ftol, int maxit, int scaler,
+                     double* d_x, double* d_chi2, double* d_cov, double* d_logdet,
+                     int* d_nit, int* d_status, double* d_f, double* d_J, void* stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (B < 0 || !d_mean || !d_p0 || !d_x || !d_chi2 || !d_nit || !d_status)
+        return set_error(h, B200LM_EINVAL, "NULL required argument");
+    if ((mean_stride != 0 && mean_stride < h->N) || (p0_stride != 0 && p0_stride < h->np))
+        return set_error(h, B200LM_EINVAL, "bad stride");
+    if (scaler != 0 && scaler != 1) return set_error(h, B200LM_EINVAL, "scaler must be 0 or 1");
+    if (maxit < 1) return set_error(h, B200LM_EINVAL, "maxit must be >= 1");
+    if (B == 0) return B200LM_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device), "cudaSetDevice");
+    cudaStream_t s = (cudaStream_t)stream;
+    FitParams P;
+    fill_params(h, P);
+    P.B = B; P.mean = d_mean; P.mean_stride = mean_stride; P.p0 = d_p0; P.p0_stride = p0_stride;
+    P.xtol = xtol; P.gtol = gtol; P.ftol = ftol; P.maxit = maxit; P.scaler = scaler;
+    P.x_out = d_x; P.chi2 = d_chi2; P.cov = d_cov; P.logdet = d_logdet; P.nit = d_nit; P.status = d_status;
+    P.f_out = d_f; P.J_out = d_J;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s), "reset work queue");
+    CUDA_TRY(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), s), "reset stats");
+    CUDA_TRY(h, h->fe->fit(P, h->sm_count, h->smem_budget, s), "fit kernel launch");
+    h->last_stream = s;
+    h->launches += 1;
+    return B200LM_OK;
+}
+
+int b200lm_last_stats(b200lm_handle h, unsigned long long out[3]) {
+    if (!h || !out) return set_error(h, B200LM_EINVAL, "NULL argument");
+    CUDA_TRY(h, cudaSetDevice(h->device), "cudaSetDevice");
+    CUDA_TRY(h, cudaStreamSynchronize(h->last_stream), "stream sync");
+    unsigned long long tmp[4];
+    CUDA_TRY(h, cudaMemcpy(tmp, h->d_stats, sizeof tmp, cudaMemcpyDeviceToHost), "read stats");
+    out[0] = tmp[0]; out[1] = tmp[1]; out[2] = tmp[2];
+    return B200LM_OK;
+}
+
+long long b200lm_launch_count(b200lm_handle h) { return h ? h->launches : 0; }
+
+int b200lm_residual_jacobian(b200lm_handle h, int B, const double* d_p, long long p_stride,
+                             const double* d_mean, long long mean_stride,
+                             double* d_f, double* d_J, double* d_chi2, void* stream) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (B < 0 || !d_p || !d_mean) return set_error(h, B200LM_EINVAL, "NULL required argument");
+    if (B == 0) return B200LM_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device), "cudaSetDevice");
+    FitParams P;
+    fill_params(h, P);
+    P.B = B; P.mean = d_mean; P.mean_stride = mean_stride; P.p0 = d_p; P.p0_stride = p_stride;
+    P.f_out = d_f; P.J_out = d_J; P.chi2 = d_chi2;
+    CUDA_TRY(h, h->fe->resjac(P, h->sm_count, h->smem_budget, (cudaStream_t)stream), "resjac kernel launch");
+    h->last_stream = (cudaStream_t)stream;
+    h->launches += 1;
+    return B200LM_OK;
+}
+
+// ---- host-pointer variant ------------------------------------------------------------
+static int ensure_stage(b200lm_handle h, size_t dev_bytes, size_t pin_bytes) {
+    if (dev_bytes > h->stage_bytes) {
+        if (h->d_stage) cudaFree(h->d_stage);
+        h->d_stage = nullptr; h->stage_bytes = 0;
+        CUDA_TRY(h, cudaMalloc(&h->d_stage, dev_bytes), "staging allocation");
+        h->stage_bytes = dev_bytes;
+    }
+    if (pin_bytes > h->pinned_bytes) {
+        if (h->h_pinned) cudaFreeHost(h->h_pinned);
+        h->h_pinned = nullptr; h->pinned_bytes = 0;
+        CUDA_TRY(h, cudaMallocHost(&h->h_pinned, pin_bytes), "pinned allocation");
+        h->pinned_bytes = pin_bytes;
+    }
+    return B200LM_OK;
+}
+
+int b200lm_fit_batch_host(b200lm_handle h, int B,
+                          const double* h_mean, long long mean_stride,
+                          const double* h_p0, long long p0_stride,
+                          double xtol, double gtol, double ftol, int maxit, int scaler,
+                          double* h_x, double* h_chi2, double* h_cov, double* h_logdet,
+                          int* h_nit, int* h_status, double* h_f, double* h_J) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (B < 0 || !h_mean || !h_p0 || !h_x || !h_chi2 || !h_nit || !h_status)
+        return set_error(h, B200LM_EINVAL, "NULL required argument");
+    if (B == 0) return B200LM_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device), "cudaSetDevice");
+    const size_t np = h->np, N = h->N, nchiv = h->nchiv;
+    const size_t n_mean = mean_stride ? (size_t)B * mean_stride : N;
+    const size_t n_p0 = p0_stride ? (size_t)B * p0_stride : np;
+    // device layout (doubles): mean | p0 | x | chi2 | logdet | cov | f | J | nit,status (ints)
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off += (n + 1) & ~(size_t)1; return o; };
+    const size_t o_mean = take(n_mean), o_p0 = take(n_p0), o_x = take(B * np), o_chi2 = take(B),
+                 o_ld = take(B), o_cov = take(h_cov ? B * np * np : 0), o_f = take(h_f ? B * nchiv : 0),
+                 o_J = take(h_J ? B * nchiv * np : 0), o_int = take(B);   // 2 ints per double slot
+    rc = ensure_stage(h, off * sizeof(double), 0);
+    if (rc) return rc;
+    double* d = (double*)h->d_stage;
+    cudaStream_t s = h->own_stream;
+    CUDA_TRY(h, cudaMemcpyAsync(d + o_mean, h_mean, n_mean * sizeof(double), cudaMemcpyHostToDevice, s), "H2D mean");
+    CUDA_TRY(h, cudaMemcpyAsync(d + o_p0, h_p0, n_p0 * sizeof(double), cudaMemcpyHostToDevice, s), "H2D p0");
+    int* d_nit = (int*)(d + o_int);
+    int* d_status = d_nit + B;
+    rc = b200lm_fit_batch(h, B, d + o_mean, mean_stride, d + o_p0, p0_stride, xtol, gtol, ftol, maxit, scaler,
+                          d + o_x, d + o_chi2, h_cov ? d + o_cov : nullptr, d + o_ld, d_nit, d_status,
+                          h_f ? d + o_f : nullptr, h_J ? d + o_J : nullptr, (void*)s);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h_x, d + o_x, B * np * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H x");
+    CUDA_TRY(h, cudaMemcpyAsync(h_chi2, d + o_chi2, B * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H chi2");
+    if (h_logdet) CUDA_TRY(h, cudaMemcpyAsync(h_logdet, d + o_ld, B * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H logdet");
+    if (h_cov) CUDA_TRY(h, cudaMemcpyAsync(h_cov, d + o_cov, B * np * np * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H cov");
+    if (h_f) CUDA_TRY(h, cudaMemcpyAsync(h_f, d + o_f, B * nchiv * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H f");
+    if (h_J) CUDA_TRY(h, cudaMemcpyAsync(h_J, d + o_J, B * nchiv * np * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H J");
+    CUDA_TRY(h, cudaMemcpyAsync(h_nit, d_nit, B * sizeof(int), cudaMemcpyDeviceToHost, s), "D2H nit");
+    CUDA_TRY(h, cudaMemcpyAsync(h_status, d_status, B * sizeof(int), cudaMemcpyDeviceToHost, s), "D2H status");
+    CUDA_TRY(h, cudaStreamSynchronize(s), "stream sync");
+    return B200LM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+// The plan object behind b200lm_handle (internal).
+#pragma once
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "registry.h"
+
+struct b200lm_handle_s {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_budget = 0;
+    const b200lm::FunctorEntry* fe = nullptr;
+    int ny = 0, np = 0, nx = 0, noprior = 0, N = 0, nchiv = 0;
+    // device-resident problem description
+    double* d_x = nullptr;
+    int* d_dfn_idx = nullptr; double* d_dfn_w = nullptr; int nd_fn = 0;
+    int* d_dpr_idx = nullptr; double* d_dpr_w = nullptr; int nd_pr = 0;
+    b200lm::BlockDesc* d_blk = nullptr; int nblk = 0;
+    int* d_blk_idx = nullptr; double* d_blk_wt = nullptr; int wt_total = 0;
+    int rb = 64;
+    bool have_weights = false, have_const = false;
+    // host copies (used by propagate)
+    std::vector<int> h_diag_idx; std::vector<double> h_diag_w;
+    std::vector<b200lm::BlockDesc> h_blk; std::vector<int> h_blk_idx;
+    // whole whitening operator, dense [nchiv][N] (built lazily for propagate)
+    double* d_wfull = nullptr;
+    // work queue + statistics
+    int* d_counter = nullptr;
+    unsigned long long* d_stats = nullptr;
+    cudaStream_t last_stream = nullptr;
+    long long launches = 0;
+    // staging for the host-pointer API
+    void* d_stage = nullptr; size_t stage_bytes = 0;
+    void* h_pinned = nullptr; size_t pinned_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+    // scratch for propagate
+    double* d_scratch = nullptr; size_t scratch_bytes = 0;
+    std::string err;
+};
+
+namespace b200lm {
+int set_error(b200lm_handle_s* h, int code, const std::string& msg);
+int cuda_fail(b200lm_handle_s* h, cudaError_t e, const char* what);
+void fill_params(b200lm_handle_s* h, FitParams& P);
+}

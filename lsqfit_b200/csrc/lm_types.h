@@ -1,0 +1,58 @@
+// Internal plan / argument structures shared by the kernels and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace b200lm {
+
+// One correlated block of the whitening (entry k>=1 of the reference's
+// yp_pdf.i_invwgts, reference src/lsqfit/_utilities.pyx:90-93).
+struct BlockDesc {
+    int n_in;        // number of y(+)prior entries in the block
+    int n_out;       // number of residuals it produces (rows of W_k; < n_in if svdcut<0 dropped modes)
+    int ldw;         // leading dimension of the transposed weight matrix (>= n_out)
+    int idx_off;     // offset into blk_idx[]  (n_in entries: index into y(+)prior)
+    int wt_off;      // offset into blk_wt[]   (Wt[k*ldw + r] = W[r][k], n_in x ldw doubles)
+    int chiv_off;    // first residual slot of this block in chiv
+};
+
+struct FitParams {
+    // ---- problem description (shared by every fit of the batch) ----------
+    int ny, np, N, nchiv, nx, noprior;
+    const double* x;            // [ny][nx] functor constants
+    int nd_fn;                  // 1x1 blocks that are data rows
+    const int* dfn_idx;         //   data row index (< ny)
+    const double* dfn_w;        //   1/sigma
+    int nd_pr;                  // 1x1 blocks that are prior rows
+    const int* dpr_idx;         //   index into y(+)prior (>= ny)
+    const double* dpr_w;
+    int nblk;
+    const BlockDesc* blk;
+    const int* blk_idx;
+    const double* blk_wt;
+    int wt_total;               // doubles in blk_wt
+    int wt_in_smem;             // stage blk_wt in shared memory
+    int rb;                     // rows of the per-warp row buffer
+    int warps;                  // warps per CTA
+    // ---- batch ------------------------------------------------------------
+    int B;
+    const double* mean;         // [B][N] (mean_stride = N) or shared (mean_stride = 0)
+    long long mean_stride;
+    const double* p0;           // [B][np] or shared (p0_stride = 0)
+    long long p0_stride;
+    double xtol, gtol, ftol;
+    int maxit;
+    int scaler;                 // 0: none (scipy x_scale=1), 1: More' (scipy 'jac', GSL 'more')
+    // ---- outputs (any of f_out, J_out, cov, logdet may be null) ----------------
+    double* x_out;              // [B][np]
+    double* chi2;               // [B]
+    double* cov;                // [B][np][np]
+    double* logdet;             // [B]  log det(J^T J)
+    int* nit;                   // [B]  function evaluations (scipy nfev)
+    int* status;                // [B]  scipy status: 0 maxit, 1 gtol, 2 ftol, 3 xtol, 4 both, -1 non-finite start
+    double* f_out;              // [B][nchiv]
+    double* J_out;              // [B][nchiv][np]
+    int* counter;               // work-queue head (zeroed before launch)
+    unsigned long long* stats;  // [0] total nfev, [1] total jacobian evals, [2] total factorisations
+};
+
+}  // namespace b200lm

@@ -1,0 +1,147 @@
+"""Device whitening: the B200 replacement for ``gvar.PDF(y (+) prior, svdcut=, eps=)``.
+
+The reference builds ``yp_pdf`` at src/lsqfit/__init__.py:1895,1898 and reads
+``.mean .meanflat .nchiv .i_invwgts .logdet .nmod .nblocks .svdcut .eps`` from it
+(src/lsqfit/__init__.py:549-561,574,723; src/lsqfit/_utilities.pyx:59-61).  ``PDF``
+below offers the same attributes, but the eigen-decomposition / inverse-Cholesky of
+every correlated block runs in the CUDA kernel behind ``b200lm_whiten``
+(csrc/whiten.cu).  Finding the diagonal blocks of the covariance is integer
+graph work on the non-zero pattern and stays on the host.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def cov_blocks(cov):
+    """Diagonal blocks (connected components of the non-zero pattern) of ``cov``.
+
+    Returns ``(idx_1x1, [idx_block, ...])`` with sorted index arrays, blocks ordered by
+    their first index (cf. gvar.evalcov_blocks as used by gvar.PDF)."""
+    cov = np.asarray(cov)
+    n = cov.shape[0]
+    offdiag = (cov != 0)
+    np.fill_diagonal(offdiag, False)
+    label = -np.ones(n, dtype=np.int64)
+    if not offdiag.any():
+        return np.arange(n, dtype=np.intp), []
+    nlab = 0
+    rows_with = np.nonzero(offdiag.any(axis=1))[0]
+    for i in rows_with:
+        if label[i] >= 0:
+            continue
+        stack = [i]
+        label[i] = nlab
+        while stack:
+            j = stack.pop()
+            for k in np.nonzero(offdiag[j])[0]:
+                if label[k] < 0:
+                    label[k] = nlab
+                    stack.append(k)
+        nlab += 1
+    diag = np.nonzero(label < 0)[0].astype(np.intp)
+    blocks = [np.nonzero(label == l)[0].astype(np.intp) for l in range(nlab)]
+    blocks.sort(key=lambda b: b[0])
+    return diag, blocks
+
+
+class PDF(object):
+    """Whitened Gaussian distribution of y (+) prior (attribute-compatible with gvar.PDF
+    as far as lsqfit reads it)."""
+
+    def __init__(self, mean, cov, svdcut=1e-12, eps=None, device=0):
+        mean = np.array(mean, dtype=float).reshape(-1)
+        cov = np.asarray(cov, dtype=float)
+        if cov.ndim == 1:
+            sd = cov
+            cov = None
+        N = mean.size
+        if svdcut is not None:
+            eps = None          # reference: eps ignored when svdcut is given (__init__.py:240-245)
+        self.svdcut, self.eps = svdcut, eps
+        self.mean = mean
+        self.meanflat = mean
+        self.size = N
+        self.device = device
+        self.nmod = 0
+        self.nblocks = {}
+        self.logdet = 0.0
+        if cov is None:
+            idx0, blocks = np.arange(N, dtype=np.intp), []
+            sd0 = np.asarray(sd, dtype=float)
+            self._cov_diag_only = sd0 ** 2
+        else:
+            assert cov.shape == (N, N)
+            idx0, blocks = cov_blocks(cov)
+            sd0 = np.sqrt(cov[idx0, idx0])
+            self._cov_diag_only = None
+        self.cov_in = cov
+        self.i_invwgts = [(idx0, 1.0 / sd0)]
+        if idx0.size:
+            self.nblocks[1] = int(idx0.size)
+        self.logdet += 2.0 * float(np.sum(np.log(sd0)))
+        nchiv = int(idx0.size)
+        self._corrected_blocks = []
+        if blocks:
+            ns = np.array([b.size for b in blocks], dtype=np.int32)
+            flat = np.concatenate([cov[np.ix_(b, b)].reshape(-1) for b in blocks])
+            W, Cc, nout, nmod, logdet = whiten_blocks(ns, flat, svdcut, eps, device)
+            o = 0
+            for k, b in enumerate(blocks):
+                n = b.size
+                Wk = W[o:o + n * n].reshape(n, n)[:nout[k]].copy()
+                self.i_invwgts.append((b, Wk))
+                self._corrected_blocks.append((b, Cc[o:o + n * n].reshape(n, n).copy()))
+                self.nblocks[int(n)] = self.nblocks.get(int(n), 0) + 1
+                self.logdet += float(logdet[k])
+                self.nmod += int(nmod[k])
+                nchiv += int(nout[k])
+                o += n * n
+        self.nchiv = nchiv
+
+    @property
+    def cov(self):
+        """Corrected covariance of y (+) prior (the reference's ``yp_pdf.distribution``)."""
+        if self.cov_in is None:
+            return np.diag(self._cov_diag_only)
+        c = self.cov_in.copy()
+        for b, cb in self._corrected_blocks:
+            c[np.ix_(b, b)] = cb
+        return c
+
+    def copy_with_mean(self, mean):
+        """Simulated fits re-use the whitening and swap only the mean
+        (src/lsqfit/__init__.py:545-552)."""
+        import copy
+        new = copy.copy(self)
+        new.mean = np.array(mean, dtype=float).reshape(-1)
+        new.meanflat = new.mean
+        return new
+
+
+def whiten_blocks(ns, cov_flat, svdcut, eps, device=0):
+    """Run b200lm_whiten on concatenated row-major blocks.  Returns numpy arrays
+    (W_flat, cov_corrected_flat, nout, nmod, logdet)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("lsqfit_b200.whiten: no CUDA device (there is no CPU fallback)")
+    dev = torch.device("cuda", device)
+    nblk = len(ns)
+    ns = np.ascontiguousarray(ns, dtype=np.int32)
+    d_cov = torch.as_tensor(np.ascontiguousarray(cov_flat, dtype=np.float64)).to(dev)
+    d_w = torch.empty_like(d_cov)
+    d_cc = torch.empty_like(d_cov)
+    d_nout = torch.empty(nblk, dtype=torch.int32, device=dev)
+    d_nmod = torch.empty(nblk, dtype=torch.int32, device=dev)
+    d_ld = torch.empty(nblk, dtype=torch.float64, device=dev)
+    use_eps = 1 if (svdcut is None and eps is not None) else 0
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _cabi.check(_cabi.lib.b200lm_whiten(
+        device, nblk, ns.ctypes.data, d_cov.data_ptr(),
+        float(svdcut) if svdcut is not None else 0.0, float(eps) if eps is not None else 0.0, use_eps,
+        d_w.data_ptr(), d_cc.data_ptr(), d_nout.data_ptr(), d_nmod.data_ptr(), d_ld.data_ptr(),
+        C.c_void_p(stream)))
+    return (d_w.cpu().numpy(), d_cc.cpu().numpy(), d_nout.cpu().numpy(), d_nmod.cpu().numpy(),
+            d_ld.cpu().numpy())

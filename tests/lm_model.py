@@ -1,0 +1,167 @@
+"""Host model (numpy) of the DEVICE trust-region algorithm -- test infrastructure.
+
+The CUDA engine does not port scipy or GSL.  It runs a per-fit trust-region
+Levenberg-Marquardt iteration whose *decisions* (radius update, acceptance,
+termination, Levenberg parameter search) follow scipy's unbounded TRF
+(scipy/optimize/_lsq/trf.py: trf_no_bounds; common.py: solve_lsq_trust_region,
+update_tr_radius, check_termination -- the solver behind the reference's
+src/lsqfit/_scipy.py:156-161), but evaluates the secular equation with a
+Cholesky factorisation of the scaled normal matrix  d.J^T J.d + alpha I
+instead of an SVD of J.  This file restates that device algorithm in numpy so
+that (a) the design can be validated on CPU against the oracle and (b) the
+kernel has a line-by-line model.  It is never imported by lsqfit_b200.
+"""
+import numpy as np
+
+EPS = np.finfo(float).eps
+
+
+def _chol_solve(A, alpha, g):
+    """Factor A + alpha I = L L^T; return (ok, L, p = -(A+alpha I)^-1 g)."""
+    n = A.shape[0]
+    M = A + alpha * np.eye(n)
+    L = np.zeros_like(M)
+    for j in range(n):
+        s = M[j, j] - L[j, :j] @ L[j, :j]
+        if not (s > 0.0) or not np.isfinite(s):
+            return False, None, None
+        L[j, j] = np.sqrt(s)
+        L[j + 1:, j] = (M[j + 1:, j] - L[j + 1:, :j] @ L[j, :j]) / L[j, j]
+    y = np.linalg.solve(L, -g)
+    p = np.linalg.solve(L.T, y)
+    return True, L, p
+
+
+def solve_tr(A, g, Delta, alpha0, rtol=0.01, max_iter=10):
+    """min 1/2 p^T A p + g^T p, |p| <= Delta  (cf. common.py: solve_lsq_trust_region).
+
+    Returns (p, alpha, n_factorizations)."""
+    nfac = 1
+    ok0, L0, p0 = _chol_solve(A, 0.0, g)
+    full_rank = ok0
+    if full_rank:
+        pn = np.linalg.norm(p0)
+        if pn <= Delta:
+            return p0, 0.0, nfac
+    alpha_upper = np.linalg.norm(g) / Delta
+    if full_rank:
+        phi = pn - Delta
+        w = np.linalg.solve(L0, p0)
+        phi_prime = -(w @ w) / pn
+        alpha_lower = -phi / phi_prime
+    else:
+        alpha_lower = 0.0
+    if alpha0 is None or (not full_rank and alpha0 == 0):
+        alpha = max(0.001 * alpha_upper, (alpha_lower * alpha_upper) ** 0.5)
+    else:
+        alpha = alpha0
+    p = None
+    for it in range(max_iter):
+        if alpha < alpha_lower or alpha > alpha_upper:
+            alpha = max(0.001 * alpha_upper, (alpha_lower * alpha_upper) ** 0.5)
+        ok, L, p = _chol_solve(A, alpha, g)
+        nfac += 1
+        if not ok:                       # numerically indefinite: push alpha up
+            alpha_lower = max(alpha_lower, alpha)
+            alpha = max(2 * alpha, 0.001 * alpha_upper)
+            p = None
+            continue
+        pn = np.linalg.norm(p)
+        phi = pn - Delta
+        w = np.linalg.solve(L, p)
+        phi_prime = -(w @ w) / pn
+        if phi < 0:
+            alpha_upper = alpha
+        ratio = phi / phi_prime
+        alpha_lower = max(alpha_lower, alpha - ratio)
+        alpha -= (phi + Delta) * ratio / Delta
+        if abs(phi) < rtol * Delta:
+            break
+    # scipy recomputes p at the updated alpha; one more factorisation
+    ok, L, p2 = _chol_solve(A, alpha, g)
+    nfac += 1
+    if ok:
+        p = p2
+    p = p * (Delta / np.linalg.norm(p))
+    return p, alpha, nfac
+
+
+def lm_fit(fun, jac, x0, xtol=1e-8, gtol=1e-10, ftol=1e-10, maxit=1000, scaler="more"):
+    """Device algorithm model.  Returns dict(x, f, J, nfev, status, nfac)."""
+    x = np.array(x0, dtype=float)
+    f = fun(x)
+    nfev = 1
+    J = jac(x)
+    m, n = J.shape
+    cost = 0.5 * f @ f
+    g = J.T @ f
+    if scaler == "more":
+        scale_inv = np.sqrt(np.sum(J ** 2, axis=0))
+        scale_inv[scale_inv == 0] = 1
+    else:
+        scale_inv = np.ones(n)
+    Delta = np.linalg.norm(x * scale_inv)
+    if Delta == 0:
+        Delta = 1.0
+    alpha = 0.0
+    status = None
+    nfac = 0
+    while True:
+        g_norm = np.max(np.abs(g))
+        if g_norm < gtol:
+            status = 1
+        if status is not None or nfev >= maxit:
+            break
+        d = 1.0 / scale_inv
+        A = (J.T @ J) * d[:, None] * d[None, :]
+        g_h = d * g
+        actual_reduction = -1.0
+        while actual_reduction <= 0 and nfev < maxit:
+            step_h, alpha, k = solve_tr(A, g_h, Delta, alpha)
+            nfac += k
+            predicted_reduction = -(0.5 * step_h @ A @ step_h + g_h @ step_h)
+            step = d * step_h
+            x_new = x + step
+            f_new = fun(x_new)
+            nfev += 1
+            step_h_norm = np.linalg.norm(step_h)
+            if not np.all(np.isfinite(f_new)):
+                Delta = 0.25 * step_h_norm
+                continue
+            cost_new = 0.5 * f_new @ f_new
+            actual_reduction = cost - cost_new
+            # update_tr_radius
+            if predicted_reduction > 0:
+                ratio = actual_reduction / predicted_reduction
+            elif predicted_reduction == actual_reduction == 0:
+                ratio = 1
+            else:
+                ratio = 0
+            Delta_new = Delta
+            if ratio < 0.25:
+                Delta_new = 0.25 * step_h_norm
+            elif ratio > 0.75 and step_h_norm > 0.95 * Delta:
+                Delta_new = Delta * 2.0
+            # check_termination
+            step_norm = np.linalg.norm(step)
+            ft = actual_reduction < ftol * cost and ratio > 0.25
+            xt = step_norm < xtol * (xtol + np.linalg.norm(x))
+            if ft and xt:
+                status = 4
+            elif ft:
+                status = 2
+            elif xt:
+                status = 3
+            if status is not None:
+                break
+            alpha *= Delta / Delta_new
+            Delta = Delta_new
+        if actual_reduction > 0:
+            x, f, cost = x_new, f_new, cost_new
+            J = jac(x)
+            g = J.T @ f
+            if scaler == "more":
+                scale_inv = np.maximum(scale_inv, np.sqrt(np.sum(J ** 2, axis=0)))
+    if status is None:
+        status = 0
+    return dict(x=x, f=f, J=J, nfev=nfev, status=status, nfac=nfac)

@@ -1,0 +1,429 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the committed
+golden fixtures.  Needs a GPU: run with ``pytest -m gpu`` on the B200 box.
+
+Tolerances (BASELINE.json north_star): best-fit p within 1e-8 * sdev, chi2 to 1e-9
+relative, covariance to 1e-8 relative -- with both sides run to tight tolerance on
+identical inputs.  "Relative" for a covariance entry means relative to
+sqrt(cov_ii cov_jj).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TIGHT = (1e-13, 1e-13, 1e-13)
+
+
+def _need_gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (no CPU fallback)")
+
+
+def _rel_cov(cov, ref):
+    s = np.sqrt(np.diag(ref))
+    return np.max(np.abs(cov - ref) / (s[:, None] * s[None, :]))
+
+
+def _oracle_nist(pr, tol, **kw):
+    from oracle.fit import nonlinear_fit
+    return nonlinear_fit(pr["form"], np.array(pr["x"]), pr["y"], pr["ysdev"], prior_mean=pr["prior_mean"],
+                         prior_cov=pr["prior_sdev"], p0=pr["p0"], tol=tol, x_scale="jac", **kw)
+
+
+def _device_nist(pr, tol, **kw):
+    import lsqfit_b200 as lb
+    return lb.nonlinear_fit(data=(np.array(pr["x"]), pr["y"], pr["ysdev"]), fcn=pr["form"],
+                            prior=(pr["prior_mean"], pr["prior_sdev"]), p0=pr["p0"], tol=tol, **kw)
+
+
+# ------------------------------------------------------------------------------------------
+def test_residual_jacobian_vs_oracle(nist_problems):
+    """chiv(p) and J = d chiv / dp at the NIST start and certified points
+    (reference src/lsqfit/_utilities.pyx:65-94, src/lsqfit/_scipy.py:146-154)."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from oracle import dual as D
+    from oracle.whiten import PDF as OPDF
+    from oracle.chiv import Chiv
+    from oracle import models as M
+    for pr in nist_problems:
+        x = np.array(pr["x"])
+        ny, npar = len(pr["y"]), len(pr["p0"])
+        mean = np.concatenate([pr["y"], pr["prior_mean"]])
+        sd = np.concatenate([pr["ysdev"], pr["prior_sdev"]])
+        opdf = OPDF(mean, sd)
+        chiv = Chiv(opdf, lambda p: M.MODELS[pr["form"]](x, p), False)
+        plan = lb.Plan(pr["form"], npar, ny, x, opdf.i_invwgts)
+        P = np.array([pr["p0"], pr["certified"]])
+        f, J, chi2 = plan.residual_jacobian(P, mean)
+        f, J, chi2 = f.cpu().numpy(), J.cpu().numpy(), chi2.cpu().numpy()
+        for b in range(2):
+            fo = np.asarray(chiv(P[b]))
+            Jo = D.deriv(chiv(D.Dual.variables(P[b])), npar)
+            scale = np.max(np.abs(fo)) + 1e-300
+            assert np.max(np.abs(f[b] - fo)) <= 1e-11 * scale, pr["name"]
+            cs = np.max(np.abs(Jo), axis=0) + 1e-300
+            assert np.max(np.abs(J[b] - Jo) / cs) <= 1e-11, pr["name"]
+            np.testing.assert_allclose(chi2[b], fo @ fo, rtol=1e-11)
+        plan.close()
+
+
+def test_nist_fits_vs_oracle(nist_problems):
+    """All 27 NIST problems, both sides at tight tolerance."""
+    _need_gpu()
+    worst = {}
+    for pr in nist_problems:
+        fo = _oracle_nist(pr, TIGHT)
+        fd = _device_nist(pr, TIGHT)
+        assert fd.error is None, (pr["name"], fd.error)
+        dp = np.max(np.abs(fd.pmean - fo.pmean) / fo.psdev)
+        dchi = abs(fd.chi2 - fo.chi2) / fo.chi2
+        dcov = _rel_cov(fd.cov, fo.cov)
+        worst[pr["name"]] = (dp, dchi, dcov)
+        # lanczos1 has sigma_y ~ 1e-13: chi2 is pure roundoff there (examples/nist.py:18-20)
+        ptol, ctol, vtol = (1e-8, 1e-9, 1e-8) if pr["name"] != "lanczos1" else (1e-3, 1.0, 1e-6)
+        assert dp <= ptol, (pr["name"], worst[pr["name"]])
+        assert dchi <= ctol, (pr["name"], worst[pr["name"]])
+        assert dcov <= vtol, (pr["name"], worst[pr["name"]])
+        assert abs(fd.logGBF - fo.logGBF) <= 1e-7 * max(1.0, abs(fo.logGBF)), pr["name"]
+    print("worst deviations", max(v[0] for v in worst.values()), max(v[1] for k, v in worst.items() if k != "lanczos1"),
+          max(v[2] for v in worst.values()))
+
+
+def test_nist_goldens_default_tol(nist_problems):
+    """Device results printed like examples/nist.out: expected strings, chi2/dof, Q, logGBF."""
+    _need_gpu()
+    from oracle import gvfmt
+    for pr in nist_problems:
+        fit = _device_nist(pr, pr["tol"])
+        exp = pr["expected"][1:-1].replace(" +- ", "+-").split()
+        for m, s, e in zip(fit.pmean, fit.p_sdev, exp):
+            assert gvfmt.agrees(m, s, e), (pr["name"], m, s, e)
+        o = pr["out"]
+        assert fit.dof == o["dof"]
+        assert gvfmt.agrees_g(fit.chi2 / fit.dof, o["chi2_dof"], 2), pr["name"]
+        assert gvfmt.agrees_g(fit.Q, o["Q"], 2), pr["name"]
+        assert gvfmt.agrees_g(fit.logGBF, o["logGBF"], 5), pr["name"]
+
+
+def test_nist_nfev_matches_reference_solver(nist_problems):
+    """Same trust-region decisions as the reference's scipy solver with More' scaling: the
+    number of function evaluations agrees on the well-conditioned problems."""
+    _need_gpu()
+    same = 0
+    for pr in nist_problems:
+        fo = _oracle_nist(pr, 1e-10)
+        fd = _device_nist(pr, 1e-10)
+        same += int(fo.nit == fd.nit)
+    assert same >= 20, same
+
+
+def test_simple_golden(golden_examples):
+    """examples/simple.out through device whitening (two 2x2 blocks) + fit + propagation."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from oracle import gvfmt
+    ex = golden_examples["simple"]
+    ny = len(ex["ymean"])
+    ycov = np.zeros((ny, ny))
+    i = 0
+    for b in ex["ycov_blocks"]:
+        b = np.array(b)
+        ycov[i:i + len(b), i:i + len(b)] = b
+        i += len(b)
+    fit = lb.nonlinear_fit(data=(np.array(ex["x"]), ex["ymean"], ycov), fcn="simple",
+                           prior=(ex["prior_mean"], ex["prior_sdev"]))
+    o = ex["out"]
+    for m, s, e in zip(fit.pmean, fit.p_sdev, o["p"]):
+        assert gvfmt.agrees(m, s, e)
+    assert fit.dof == o["dof"] and fit.svdn == o["svdn"]
+    assert gvfmt.agrees_g(fit.chi2 / fit.dof, o["chi2_dof"], 2)
+    assert gvfmt.agrees_g(fit.Q, o["Q"], 2)
+    assert gvfmt.agrees_g(fit.logGBF, o["logGBF"], 5)
+    assert fit.nblocks == {1: 3, 2: 2}
+    # error budget (simple.out:26-31) pins D
+    D, C = fit.D, fit.yp_pdf.cov
+    a, b = fit.pmean
+    T = np.array([[1, 0], [-b / a ** 2, 1 / a], [0, 1]])
+    vals = np.array([a, b / a, b])
+    Dy, Dp = T @ D[:, :ny], T @ D[:, ny:]
+    ey = np.sqrt(np.diag(Dy @ C[:ny, :ny] @ Dy.T)) / np.abs(vals) * 100
+    ep = np.sqrt(np.diag(Dp @ C[ny:, ny:] @ Dp.T)) / np.abs(vals) * 100
+    np.testing.assert_allclose(ey, o["budget"]["y"], atol=0.006)
+    np.testing.assert_allclose(ep, o["budget"]["prior"], atol=0.006)
+
+
+def test_y_vs_x_golden(golden_examples):
+    """examples/y-vs-x.out: 8x8 covariance with condition number > 1e12; the device svdcut
+    must modify exactly one mode (svdcut/n = 1e-12/1)."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from oracle import gvfmt
+    ex = golden_examples["y-vs-x"]
+    for nexp in (1, 2, 3, 4):
+        pm = np.concatenate([np.full(nexp, 0.5), np.arange(1, nexp + 1.)])
+        fit = lb.nonlinear_fit(data=(np.array(ex["x"]), ex["ymean"], np.array(ex["ycov"])), fcn="multiexp",
+                               prior=(pm, np.full(2 * nexp, 0.4)))
+        o = ex["out"][str(nexp)]
+        assert fit.svdn == o["svdn"] and fit.dof == o["dof"]
+        assert gvfmt.agrees_g(fit.chi2 / fit.dof, o["chi2_dof"], 2)
+        assert gvfmt.agrees_g(fit.Q, o["Q"], 2)
+        assert gvfmt.agrees_g(fit.logGBF, o["logGBF"], 5)
+        for m, s, e in zip(fit.pmean, fit.p_sdev, o["p"]):
+            assert gvfmt.agrees(m, s, e), (nexp, m, s, e)
+
+
+def test_p_corr_and_x_err_goldens(golden_examples):
+    """examples/p-corr.out (correlated 2x2 prior block) and examples/x-err.out (19 params)."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from oracle import gvfmt
+    ex = golden_examples["p-corr"]
+    y = np.array([gvfmt.parse(s)[:2] for s in ex["y"]])
+    fit = lb.nonlinear_fit(data=(np.array(ex["x"]), y[:, 0], y[:, 1]), fcn="mgh09",
+                           prior=(ex["prior_mean"], np.array(ex["prior_cov"])))
+    o = ex["out"]
+    assert fit.dof == o["dof"] and fit.svdn == o["svdn"]
+    assert gvfmt.agrees_g(fit.chi2 / fit.dof, o["chi2_dof"], 2)
+    assert gvfmt.agrees_g(fit.logGBF, o["logGBF"], 5)
+    for m, s, e in zip(fit.pmean, fit.p_sdev, o["p"]):
+        assert gvfmt.agrees(m, s, e)
+    C = fit.p[1]
+    assert "%.4f" % (C[0, 1] / np.sqrt(C[0, 0] * C[1, 1])) == o["corr_p0_p1"]
+
+    ex = golden_examples["x-err"]
+    y = np.array([gvfmt.parse(s)[:2] for s in ex["y"]])
+    xp = np.array([gvfmt.parse(s)[:2] for s in ex["xprior"]])
+    bp = np.array([gvfmt.parse(s)[:2] for s in ex["bprior"]])
+    pm, ps = np.concatenate([bp[:, 0], xp[:, 0]]), np.concatenate([bp[:, 1], xp[:, 1]])
+    fit = lb.nonlinear_fit(data=(y[:, 0], y[:, 1]), fcn="xerr_logistic", prior=(pm, ps))
+    o = ex["out"]
+    assert fit.dof == o["dof"]
+    assert gvfmt.agrees_g(fit.chi2 / fit.dof, o["chi2_dof"], 2)
+    assert gvfmt.agrees_g(fit.logGBF, o["logGBF"], 5)
+    for m, s, e in zip(fit.pmean, fit.p_sdev, o["p"]):
+        assert gvfmt.agrees(m, s, e), (m, s, e)
+
+
+def test_whitening_vs_oracle():
+    """Device Jacobi whitening vs oracle/whiten.py: inverse covariance, logdet, nmod, corrected
+    covariance.  W itself is basis dependent inside degenerate subspaces, so W^T W is compared."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from oracle.whiten import PDF as OPDF
+    rng = np.random.default_rng(7)
+    cases = []
+    for n, cut in [(2, 1e-12), (5, 1e-12), (8, 1e-6), (33, 1e-4), (64, 1e-12), (64, 1e-3), (100, 1e-5),
+                   (130, 1e-6), (12, 0.0), (16, None), (24, -1e-4)]:
+        A = rng.normal(size=(n, max(2, n // 2 + 3)))
+        cov = A @ A.T
+        cov = cov + 1e-9 * np.trace(cov) / n * np.eye(n)
+        s = rng.uniform(1e-3, 1e3, size=n)
+        cov = cov * s[:, None] * s[None, :]
+        cases.append((cov, cut))
+    for cov, cut in cases:
+        n = cov.shape[0]
+        big = np.zeros((n + 3, n + 3))
+        big[:n, :n] = cov
+        big[n:, n:] = np.diag([0.25, 4.0, 9.0])
+        mean = np.zeros(n + 3)
+        o = OPDF(mean, big, svdcut=cut)
+        d = lb.PDF(mean, big, svdcut=cut)
+        assert d.nmod == o.nmod and d.nchiv == o.nchiv, (n, cut, d.nmod, o.nmod)
+        np.testing.assert_allclose(d.logdet, o.logdet, rtol=1e-9, atol=1e-9)
+        np.testing.assert_array_equal(d.i_invwgts[0][0], o.i_invwgts[0][0])
+        np.testing.assert_allclose(d.i_invwgts[0][1], o.i_invwgts[0][1], rtol=1e-15)
+        Wd, Wo = d.i_invwgts[1][1], o.i_invwgts[1][1]
+        icd, ico = Wd.T @ Wd, Wo.T @ Wo
+        sc = np.sqrt(np.diag(ico))
+        assert np.max(np.abs(icd - ico) / (sc[:, None] * sc[None, :])) < 1e-7, (n, cut)
+        sc = np.sqrt(np.diag(o.cov))
+        assert np.max(np.abs(d.cov - o.cov) / (sc[:, None] * sc[None, :])) < 1e-12, (n, cut)
+    # eps regulator (parity unpinned in the reference; checked against the oracle restatement)
+    cov = cases[3][0]
+    o = OPDF(np.zeros(len(cov)), cov, svdcut=None, eps=1e-6)
+    d = lb.PDF(np.zeros(len(cov)), cov, svdcut=None, eps=1e-6)
+    np.testing.assert_allclose(d.logdet, o.logdet, rtol=1e-10)
+    Wd, Wo = d.i_invwgts[1][1], o.i_invwgts[1][1]
+    np.testing.assert_allclose(Wd.T @ Wd, Wo.T @ Wo, rtol=1e-8, atol=0)
+    # known answers of the reference tests (tests/test_lsqfit.py:581-589)
+    cov = np.array([[0.5, 0.25, 0.5], [0.25, 0.5, 0.5], [0.5, 0.5, 1.0]])
+    one = np.ones(3)
+    d = lb.PDF(one, cov, svdcut=1 - 1e-16)
+    W = d.i_invwgts[1][1]
+    np.testing.assert_allclose(1 / (one @ W.T @ W @ one), 0.4561552812808828, rtol=1e-7)
+    d = lb.PDF(one, cov, svdcut=1e-18)
+    W = d.i_invwgts[1][1]
+    np.testing.assert_allclose(1 / (one @ W.T @ W @ one), 1. / 3., rtol=1e-7)
+
+
+def _c3_oracle(cfg, pdf, mean, tol):
+    from oracle.fit import nonlinear_fit
+    ny = cfg["ny"]
+    return nonlinear_fit("multiexp", cfg["x"], mean[:ny], prior_mean=mean[ny:], _yp_pdf=pdf,
+                         p0=cfg["p0"], tol=tol, x_scale="jac")
+
+
+@pytest.mark.parametrize("K", [3, 8])
+def test_correlator_batch_vs_oracle(K):
+    """Config C3/C4 shape (dense 64x64 block + diagonal priors): a bootstrap batch fitted in one
+    launch vs the oracle fitting the same copies one by one, both at tight tolerance."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from lsqfit_b200 import configs
+    from oracle.whiten import PDF as OPDF
+    cfg = configs.correlator(K)
+    cfg["p0"] = cfg["prior_mean"].copy()
+    ny, npar = cfg["ny"], cfg["np"]
+    B = 48
+    N = ny + npar
+    full = np.zeros((N, N))
+    full[:ny, :ny] = cfg["ycov"]
+    full[ny:, ny:] = np.diag(cfg["prior_sdev"] ** 2)
+    mean0 = np.concatenate([cfg["f"], cfg["prior_mean"]])
+    opdf = OPDF(mean0, full, svdcut=1e-12)
+    dpdf = lb.PDF(mean0, full, svdcut=1e-12)
+    assert dpdf.nmod == opdf.nmod
+    means = configs.bootstrap_means(cfg, B, seed=99, cov=opdf.cov[:ny, :ny])
+    # the device fits use the ORACLE's whitening so that inputs are identical
+    plan = lb.Plan("multiexp", npar, ny, cfg["x"], opdf.i_invwgts)
+    out = plan.fit_batch(means, cfg["p0"], tol=TIGHT, maxit=2000).numpy()
+    nbad = 0
+    for b in range(B):
+        fo = _c3_oracle(cfg, opdf, means[b], TIGHT)
+        if fo.stopping_criterion == 0 or out["status"][b] <= 0:
+            nbad += 1
+            continue
+        dp = np.max(np.abs(out["x"][b] - fo.pmean) / fo.psdev)
+        assert dp <= 1e-8, (b, dp)
+        assert abs(out["chi2"][b] - fo.chi2) <= 1e-9 * fo.chi2, b
+        assert _rel_cov(out["cov"][b], fo.cov) <= 1e-8, (b, _rel_cov(out["cov"][b], fo.cov))
+        sign, ld = np.linalg.slogdet(fo.J.T @ fo.J)
+        assert abs(out["logdet"][b] - ld) <= 1e-8 * abs(ld), b
+    assert nbad <= B // 10
+    # device whitening gives the same fits (chi2 is basis independent)
+    plan2 = lb.Plan("multiexp", npar, ny, cfg["x"], dpdf.i_invwgts)
+    out2 = plan2.fit_batch(means, cfg["p0"], tol=TIGHT, maxit=2000).numpy()
+    ok = (out["status"] > 0) & (out2["status"] > 0)
+    np.testing.assert_allclose(out2["chi2"][ok], out["chi2"][ok], rtol=1e-7)
+    np.testing.assert_allclose(out2["x"][ok], out["x"][ok], rtol=1e-6, atol=1e-9)
+
+
+def test_batch_properties_full_size():
+    """Size-independent properties at the BASELINE C3 size (10^4 fits): stationarity
+    (J^T f = 0), cov . J^T J = 1, chi2 = sum f^2, permutation invariance, host == device API."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from lsqfit_b200 import configs
+    cfg = configs.c3(B=10000)
+    ny, npar = cfg["ny"], cfg["np"]
+    N = ny + npar
+    full = np.zeros((N, N))
+    full[:ny, :ny] = cfg["ycov"]
+    full[ny:, ny:] = np.diag(cfg["prior_sdev"] ** 2)
+    mean0 = np.concatenate([cfg["f"], cfg["prior_mean"]])
+    pdf = lb.PDF(mean0, full, svdcut=cfg["svdcut"])
+    means = configs.bootstrap_means(cfg, cfg["B"], cfg["seed"], cov=pdf.cov[:ny, :ny])
+    plan = lb.Plan("multiexp", npar, ny, cfg["x"], pdf.i_invwgts)
+    out = plan.fit_batch(means, cfg["p0"], tol=cfg["tol"], maxit=cfg["maxit"], want_fJ=True).numpy()
+    conv = out["status"] > 0
+    assert conv.mean() > 0.99
+    f, J = out["f"][conv], out["J"][conv]
+    np.testing.assert_allclose(out["chi2"][conv], (f ** 2).sum(axis=1), rtol=1e-12)
+    JtJ = np.einsum("bij,bik->bjk", J, J)
+    eye = np.einsum("bij,bjk->bik", out["cov"][conv], JtJ)
+    assert np.max(np.abs(eye - np.eye(npar)[None])) < 1e-6
+    g = np.einsum("bij,bi->bj", J, f)
+    gscale = np.sqrt(np.einsum("bjj->bj", JtJ)) * np.sqrt(out["chi2"][conv])[:, None] + 1e-300
+    assert np.quantile(np.max(np.abs(g) / gscale, axis=1), 0.99) < 1e-5
+    sign, ld = np.linalg.slogdet(JtJ)
+    np.testing.assert_allclose(out["logdet"][conv], ld, rtol=1e-9)
+    # permutation invariance: every fit is independent of its position in the batch
+    perm = np.random.default_rng(0).permutation(cfg["B"])
+    outp = plan.fit_batch(means[perm], cfg["p0"], tol=cfg["tol"], maxit=cfg["maxit"]).numpy()
+    np.testing.assert_array_equal(outp["x"], out["x"][perm])
+    np.testing.assert_array_equal(outp["nit"], out["nit"][perm])
+    # host-buffer entry point gives bit-identical results
+    outh = plan.fit_batch_host(means[:512], cfg["p0"], tol=cfg["tol"], maxit=cfg["maxit"])
+    np.testing.assert_array_equal(outh["x"], out["x"][:512])
+    np.testing.assert_array_equal(outh["chi2"], out["chi2"][:512])
+    nfev, njev, nfac = plan.last_stats()
+    assert nfev == int(outh["nit"].sum())
+
+
+def test_propagate_vs_oracle(golden_examples):
+    """D = cov G^T C^-1 and cov(p) = D C D^T vs the oracle restatement of _getp
+    (reference src/lsqfit/__init__.py:897-922) on y-vs-x (svd-corrected covariance)."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from oracle.fit import nonlinear_fit as ofit
+    ex = golden_examples["y-vs-x"]
+    nexp = 2
+    pm = np.concatenate([np.full(nexp, 0.5), np.arange(1, nexp + 1.)])
+    x = np.array(ex["x"])
+    fo = ofit("multiexp", x[:, None], ex["ymean"], np.array(ex["ycov"]), prior_mean=pm,
+              prior_cov=np.full(2 * nexp, 0.4), tol=TIGHT, x_scale="jac")
+    plan = lb.Plan("multiexp", 2 * nexp, len(x), x, fo.yp_pdf.i_invwgts)
+    D, covp = plan.propagate(fo.pmean.reshape(1, -1), fo.cov.reshape(1, -1), fo.yp_pdf.cov)
+    D, covp = D[0].cpu().numpy(), covp[0].cpu().numpy()
+    sD = np.max(np.abs(fo.D), axis=0) + 1e-300
+    assert np.max(np.abs(D - fo.D) / sD) < 1e-8
+    assert _rel_cov(covp, fo.p_cov) < 1e-8
+
+
+def test_stopping_criteria_and_errors():
+    """Plugin contract: tolerance normalisation, stopping codes, maxit, errors as data
+    (reference tests/test_lsqfit.py:1754-1777 and src/lsqfit/_scipy.py:124-132, 177-181)."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    x = np.linspace(0.1, 2.0, 12)
+    ptrue = np.array([0.7, 1.3, 0.4])
+    y = ptrue[0] + ptrue[1] * np.exp(-ptrue[2] * x)
+    kw = dict(data=(x, y * (1 + 1e-3 * np.cos(7 * x)), 1e-3 * np.ones(12)), fcn="offset_exp",
+              prior=([0.5, 1.0, 0.5], [1.0, 1.0, 1.0]))
+    fit = lb.nonlinear_fit(tol=(1e-10, 0.0, 0.0), **kw)
+    assert fit.stopping_criterion == 1 and fit.error is None and fit.tol == (1e-10, 0.0, 0.0)
+    fit = lb.nonlinear_fit(tol=(0.0, 1e-6, 0.0), **kw)
+    assert fit.stopping_criterion == 2
+    fit = lb.nonlinear_fit(tol=(0.0, 0.0, 1e-10), **kw)
+    assert fit.stopping_criterion == 3
+    fit = lb.nonlinear_fit(tol=1e-9, **kw)
+    assert fit.tol == (1e-9, 1e-10, 1e-10)
+    fit = lb.nonlinear_fit(tol=(1e-14, 0.0, 0.0), maxit=3, **kw)
+    assert fit.stopping_criterion == 0 and fit.error is not None and fit.nit == 3
+    with pytest.raises(ValueError):
+        lb.nonlinear_fit(fitter="no_such_fitter", **kw)
+    with pytest.raises(lb.B200LMError):
+        lb.Plan("multiexp", 40, 8, np.arange(8.), [(np.arange(48), np.ones(48))])     # K=20 not compiled
+
+
+def test_iterators():
+    """bootstrapped_fit_iter / simulated_fit_iter semantics (reference
+    tests/test_lsqfit.py:714-770, 1551-1577): the spread of bootstrap results reproduces fit.p's
+    covariance; simulated fits recover pexact within errors."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from lsqfit_b200 import configs
+    cfg = configs.correlator(2, ny=24)
+    fit = lb.nonlinear_fit(data=(cfg["x"], cfg["f"], cfg["ycov"]), fcn="multiexp",
+                           prior=(cfg["prior_mean"], cfg["prior_sdev"]))
+    assert fit.error is None
+    bs = fit.bootstrapped_fits(4000, seed=1)
+    m, c = bs.pmean_stats()
+    assert np.all(np.abs(m - fit.pmean) < 5 * fit.psdev / np.sqrt(4000) + 1e-3 * fit.psdev)
+    np.testing.assert_allclose(np.sqrt(np.diag(c)), fit.psdev, rtol=0.1)
+    n = 0
+    for bf in fit.bootstrapped_fit_iter(5, seed=3):
+        assert bf.error is None and bf.pmean.shape == (4,)
+        n += 1
+    assert n == 5
+    sims = fit.simulated_fits(2000, seed=2)
+    a = sims.arrays()
+    ok = a["status"] > 0
+    pull = (a["x"][ok] - sims.pexact[None, :]) / np.sqrt(np.einsum("bii->bi", a["cov"][ok]))
+    assert np.all(np.abs(pull.mean(axis=0)) < 0.2)
+    chi2_dof = a["chi2"][ok].mean() / fit.dof
+    assert chi2_dof < 1.2          # without prior noise chi2/dof < 1 (reference __init__.py:1427-1430)
+    for sf in fit.simulated_fit_iter(3, seed=5):
+        assert sf.error is None
