@@ -87,6 +87,8 @@ int b200lm_nchiv(b200lm_handle h);
  *   d_p0     [B][np] starting points (p0_stride = np) or one shared start (p0_stride = 0)
  *   xtol, gtol, ftol, maxit   as normalised at src/lsqfit/_scipy.py:124-132
  *   scaler   1 = More' column scaling (GSL scaler='more', scipy x_scale='jac'); 0 = none
+ *   polish   max number of undamped Gauss-Newton refinement steps taken after the trust-region
+ *            loop has stopped (0 = none; they count in d_nit)
  * Outputs (device): d_x [B][np], d_chi2 [B] (= sum f^2, __init__.py:667),
  *   d_cov [B][np][np] (= inv(J^T J), __init__.py:668), d_logdet [B] (= log det J^T J,
  *   __init__.py:712-719), d_nit [B] (function evaluations, _scipy.py:167),
@@ -96,7 +98,7 @@ int b200lm_nchiv(b200lm_handle h);
 int b200lm_fit_batch(b200lm_handle h, int B,
                      const double* d_mean, long long mean_stride,
                      const double* d_p0, long long p0_stride,
-                     double xtol, double gtol, double ftol, int maxit, int scaler,
+                     double xtol, double gtol, double ftol, int maxit, int scaler, int polish,
                      double* d_x, double* d_chi2, double* d_cov, double* d_logdet,
                      int* d_nit, int* d_status, double* d_f, double* d_J, void* stream);
 
@@ -106,7 +108,7 @@ int b200lm_fit_batch(b200lm_handle h, int B,
 int b200lm_fit_batch_host(b200lm_handle h, int B,
                           const double* h_mean, long long mean_stride,
                           const double* h_p0, long long p0_stride,
-                          double xtol, double gtol, double ftol, int maxit, int scaler,
+                          double xtol, double gtol, double ftol, int maxit, int scaler, int polish,
                           double* h_x, double* h_chi2, double* h_cov, double* h_logdet,
                           int* h_nit, int* h_status, double* h_f, double* h_J);
 

@@ -44,11 +44,11 @@ SIGNATURES = {
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200lm_nchiv": (C.c_int, [handle_t]),
     "b200lm_fit_batch": (C.c_int, [handle_t, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
-                                   C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                   C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200lm_fit_batch_host": (C.c_int, [handle_t, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
-                                        C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                        C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200lm_last_stats": (C.c_int, [handle_t, C.POINTER(C.c_ulonglong)]),

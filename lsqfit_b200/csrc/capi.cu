@@ -224,7 +224,7 @@ static int check_ready(b200lm_handle h) {
 int b200lm_fit_batch(b200lm_handle h, int B,
                      const double* d_mean, long long mean_stride,
                      const double* d_p0, long long p0_stride,
-                     double xtol, double gtol, double ftol, int maxit, int scaler,
+                     double xtol, double gtol, double ftol, int maxit, int scaler, int polish,
                      double* d_x, double* d_chi2, double* d_cov, double* d_logdet,
                      int* d_nit, int* d_status, double* d_f, double* d_J, void* stream) {
     int rc = check_ready(h);
@@ -241,7 +241,7 @@ int b200lm_fit_batch(b200lm_handle h, int B,
     FitParams P;
     fill_params(h, P);
     P.B = B; P.mean = d_mean; P.mean_stride = mean_stride; P.p0 = d_p0; P.p0_stride = p0_stride;
-    P.xtol = xtol; P.gtol = gtol; P.ftol = ftol; P.maxit = maxit; P.scaler = scaler;
+    P.xtol = xtol; P.gtol = gtol; P.ftol = ftol; P.maxit = maxit; P.scaler = scaler; P.polish = polish < 0 ? 0 : polish;
     P.x_out = d_x; P.chi2 = d_chi2; P.cov = d_cov; P.logdet = d_logdet; P.nit = d_nit; P.status = d_status;
     P.f_out = d_f; P.J_out = d_J;
     CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s), "reset work queue");
@@ -302,7 +302,7 @@ static int ensure_stage(b200lm_handle h, size_t dev_bytes, size_t pin_bytes) {
 int b200lm_fit_batch_host(b200lm_handle h, int B,
                           const double* h_mean, long long mean_stride,
                           const double* h_p0, long long p0_stride,
-                          double xtol, double gtol, double ftol, int maxit, int scaler,
+                          double xtol, double gtol, double ftol, int maxit, int scaler, int polish,
                           double* h_x, double* h_chi2, double* h_cov, double* h_logdet,
                           int* h_nit, int* h_status, double* h_f, double* h_J) {
     int rc = check_ready(h);
@@ -328,7 +328,7 @@ int b200lm_fit_batch_host(b200lm_handle h, int B,
     CUDA_TRY(h, cudaMemcpyAsync(d + o_p0, h_p0, n_p0 * sizeof(double), cudaMemcpyHostToDevice, s), "H2D p0");
     int* d_nit = (int*)(d + o_int);
     int* d_status = d_nit + B;
-    rc = b200lm_fit_batch(h, B, d + o_mean, mean_stride, d + o_p0, p0_stride, xtol, gtol, ftol, maxit, scaler,
+    rc = b200lm_fit_batch(h, B, d + o_mean, mean_stride, d + o_p0, p0_stride, xtol, gtol, ftol, maxit, scaler, polish,
                           d + o_x, d + o_chi2, h_cov ? d + o_cov : nullptr, d + o_ld, d_nit, d_status,
                           h_f ? d + o_f : nullptr, h_J ? d + o_J : nullptr, (void*)s);
     if (rc) return rc;

@@ -157,14 +157,64 @@ __device__ __forceinline__ void emit_rows(const double* S, int nrows, int slot0,
 // residual + Jacobian + normal equations at pv: fills c.A (J^T J), c.g (J^T r),
 // returns cost.  Optionally writes the residual vector and J to global memory.
 // ---------------------------------------------------------------------------
+// Householder update of the triangular factor Rt (in c.A) with `nrows` rows of S, columns
+// scaled by c.dsc:  Rt <- R of qr([Rt ; S.diag(dsc)]).  Rows are owned by lanes (i mod 32);
+// S is destroyed.  Used for the final covariance: (J^T J)^-1 = dsc Rt^-1 Rt^-T dsc has a
+// relative error ~kappa(J)*eps instead of kappa^2*eps for the normal equations.
 template <class F>
+__device__ void qr_update(WarpCtx<F>& c, double* S, int nrows) {
+    typedef FitLayout<F> Lay;
+    constexpr int NP = Lay::NP, LDR = Lay::LDR, LDA = Lay::LDA;
+    const int lane = c.lane;
+    for (int i = lane; i < nrows; i += 32) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) S[i * LDR + j] *= c.dsc[j];
+    }
+    __syncwarp();
+    for (int j = 0; j < NP; ++j) {
+        double ss = 0.0;
+        for (int i = lane; i < nrows; i += 32) { const double v = S[i * LDR + j]; ss = fma(v, v, ss); }
+        ss = warp_sum(ss);
+        if (ss == 0.0) continue;                             // uniform across the warp
+        const double rjj = c.A[j * LDA + j];
+        const double nrm = sqrt(fma(rjj, rjj, ss));
+        const double alpha = rjj > 0.0 ? -nrm : nrm;
+        const double v0 = rjj - alpha;
+        const double beta = 1.0 / (nrm * fabs(v0));
+        double t[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) t[q] = 0.0;
+        for (int i = lane; i < nrows; i += 32) {
+            const double sj = S[i * LDR + j];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) if (q > j) t[q] = fma(sj, S[i * LDR + q], t[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < NP; ++q) if (q > j) t[q] = (fma(v0, c.A[j * LDA + q], warp_sum(t[q]))) * beta;
+        __syncwarp();
+        for (int i = lane; i < nrows; i += 32) {
+            const double sj = S[i * LDR + j];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) if (q > j) S[i * LDR + q] = fma(-t[q], sj, S[i * LDR + q]);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < NP; ++q) if (q > j) c.A[j * LDA + q] = fma(-t[q], v0, c.A[j * LDA + q]);
+            c.A[j * LDA + j] = alpha;
+        }
+        __syncwarp();
+    }
+}
+
+// MODE 0: normal equations (A = J^T J, g = J^T r).  MODE 1: QR factor of J.diag(dsc) in c.A.
+template <class F, int MODE = 0>
 __device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, double* Jout) {
     typedef FitLayout<F> Lay;
     constexpr int NP = Lay::NP, LDR = Lay::LDR, LDA = Lay::LDA;
     const FitParams& P = c.P;
     const int lane = c.lane;
     for (int e = lane; e < NP * LDA; e += 32) c.A[e] = 0.0;
-    if (lane < NP) c.g[lane] = 0.0;
+    if (MODE == 0 && lane < NP) c.g[lane] = 0.0;
     __syncwarp();
     double acc = 0.0;
     // 1x1 prior rows: J row = w e_j, analytic contribution
@@ -173,8 +223,12 @@ __device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, doubl
         const int j = idx - P.ny;
         const double w = P.dpr_w[i];
         const double r = w * (pv[j] - c.mean[idx]);
-        c.A[j * LDA + j] += w * w;
-        c.g[j] += w * r;
+        if (MODE == 0) {
+            c.A[j * LDA + j] += w * w;
+            c.g[j] += w * r;
+        } else {
+            c.A[j * LDA + j] = w * c.dsc[j];                 // a diagonal matrix is triangular
+        }
         acc = fma(r, r, acc);
         if (fout) fout[P.nd_fn + i] = r;
         if (Jout) {
@@ -195,8 +249,9 @@ __device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, doubl
             c.R[i * LDR + NP] = w * (f - c.mean[row]);
         }
         __syncwarp();
-        accumulate<F>(c, c.R, nrows, acc);
         if (fout || Jout) emit_rows<F>(c.R, nrows, c0, lane, fout, Jout);
+        if (MODE == 0) accumulate<F>(c, c.R, nrows, acc);
+        else { __syncwarp(); qr_update<F>(c, c.R, nrows); }
         __syncwarp();
     }
     // correlated blocks: rows of [G | delta], then W.[G | delta]
@@ -247,8 +302,9 @@ __device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, doubl
             }
             __syncwarp();
             const int nrows = min(64, bd.n_out - g0);
-            accumulate<F>(c, S, nrows, acc);
             if (fout || Jout) emit_rows<F>(S, nrows, bd.chiv_off + g0, lane, fout, Jout);
+            if (MODE == 0) accumulate<F>(c, S, nrows, acc);
+            else { __syncwarp(); qr_update<F>(c, S, nrows); }
             __syncwarp();
         }
     }
@@ -260,12 +316,13 @@ __device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, doubl
 // ---------------------------------------------------------------------------
 // L L^T = d_i A_ij d_j + alpha delta_ij ; false if not numerically positive definite
 template <class F>
-__device__ bool chol_factor(WarpCtx<F>& c, double alpha) {
+__device__ bool chol_factor(WarpCtx<F>& c, double alpha, double* min_pivot_ratio = nullptr) {
     typedef FitLayout<F> Lay;
     constexpr int NP = Lay::NP, LDA = Lay::LDA;
     const int i = c.lane;
     const double di = i < NP ? c.dsc[i] : 0.0;
     bool ok = true;
+    double minr = 1.0;
     for (int j = 0; j < NP; ++j) {
         double s = 0.0, m = 0.0;
         if (i >= j && i < NP) {
@@ -276,12 +333,14 @@ __device__ bool chol_factor(WarpCtx<F>& c, double alpha) {
         const double sjj = __shfl_sync(B200LM_FULL, s, j);
         const double mjj = __shfl_sync(B200LM_FULL, m, j);
         if (!(sjj > 8.0 * NP * 2.220446049250313e-16 * mjj) || !isfinite(sjj)) { ok = false; break; }
+        minr = fmin(minr, sjj / mjj);
         const double inv = rsqrt(sjj);
         if (i == j) { c.L[j * LDA + j] = sjj * inv; c.idg[j] = inv; }
         else if (i > j && i < NP) c.L[i * LDA + j] = s * inv;
         __syncwarp();
     }
     __syncwarp();
+    if (min_pivot_ratio) *min_pivot_ratio = minr;
     return ok;
 }
 // y = L^-1 b (lane i holds b_i, returns y_i)
@@ -398,6 +457,38 @@ __device__ double covariance_from_chol(WarpCtx<F>& c, double* cov_out) {
             double s = 0.0;
             const int k0 = a > b ? a : b;
             for (int k = k0; k < NP; ++k) s = fma(c.A[k * LDA + a], c.A[k * LDA + b], s);
+            cov_out[a * NP + b] = s * c.dsc[a] * c.dsc[b];
+        }
+    }
+    __syncwarp();
+    return ld;
+}
+
+// covariance from the triangular factor Rt (c.A) of J.diag(dsc): (J^T J)^-1 =
+// dsc Rt^-1 Rt^-T dsc.  Uses c.L as scratch for Rt^-1.  Returns log det(J^T J) (nan if singular).
+template <class F>
+__device__ double covariance_from_qr(WarpCtx<F>& c, double* cov_out) {
+    typedef FitLayout<F> Lay;
+    constexpr int NP = Lay::NP, LDA = Lay::LDA;
+    const int a = c.lane;
+    double ld = 0.0;
+    if (a < NP) ld = 2.0 * (log(fabs(c.A[a * LDA + a])) - log(c.dsc[a]));
+    ld = warp_sum(ld);
+    if (a < NP) {
+        // column a of Rt^-1 (upper triangular): back substitution from row a up to row 0
+        for (int j = NP - 1; j > a; --j) c.L[j * LDA + a] = 0.0;
+        for (int j = a; j >= 0; --j) {
+            double s = (j == a) ? 1.0 : 0.0;
+            for (int k = j + 1; k <= a; ++k) s = fma(-c.A[j * LDA + k], c.L[k * LDA + a], s);
+            c.L[j * LDA + a] = s / c.A[j * LDA + j];
+        }
+    }
+    __syncwarp();
+    if (a < NP && cov_out) {
+        for (int b = 0; b < NP; ++b) {
+            double s = 0.0;
+            const int k0 = a > b ? a : b;
+            for (int k = k0; k < NP; ++k) s = fma(c.L[a * LDA + k], c.L[b * LDA + k], s);
             cov_out[a * NP + b] = s * c.dsc[a] * c.dsc[b];
         }
     }
@@ -529,6 +620,52 @@ __global__ void __launch_bounds__(512, 1) fit_kernel(const __grid_constant__ Fit
             }
         }
 
+        // ---- optional Gauss-Newton polish (P.polish > 0; off by default) ----------------
+        // The trust-region loop accepts a step only if the cost decreases, and cost differences
+        // below eps*cost cannot be resolved in fp64: it stalls ~sqrt(eps*chi2) standard deviations
+        // from the stationary point (so does the reference's solver).  Undamped Gauss-Newton
+        // steps, accepted on the decrease of the Newton decrement instead of the cost, take the
+        // solution on to the gradient's rounding level.
+        if (status >= 1 && P.polish > 0) {
+            // Newton decrement dec = g^T (J^T J)^-1 g = predicted decrease of chi2; sqrt(dec) is
+            // the distance to the stationary point in standard deviations.
+            const double d = 1.0 / sinv;
+            if (act) c.dsc[lane] = d;
+            __syncwarp();
+            double dec_prev = 1e300;
+            for (int it = 0; it <= P.polish; ++it) {
+                ++nfac;
+                if (!chol_factor<F>(c, 0.0)) break;
+                const double gh = act ? d * c.g[lane] : 0.0;
+                const double sh = solve_upper<F>(c, solve_lower<F>(c, act ? -gh : 0.0));
+                const double dec = -warp_sum(act ? gh * sh : 0.0);
+                if (it > 0) {
+                    if (!(dec < dec_prev)) {                        // the last step did not help: undo it
+                        if (act) { const double t = c.p[lane]; c.p[lane] = c.pn[lane]; c.pn[lane] = t; }
+                        __syncwarp();
+                        cost = eval_full<F>(c, c.p, nullptr, nullptr);
+                        ++njev;
+                        break;
+                    }
+                }
+                if (!(dec > 1e-22) || it == P.polish) break;        // < 1e-11 sdev from stationarity
+                dec_prev = dec;
+                // keep the old point in pn, step to the new one
+                if (act) { const double t = c.p[lane]; c.pn[lane] = t; c.p[lane] = t + d * sh; }
+                __syncwarp();
+                const double cost_try = eval_full<F>(c, c.p, nullptr, nullptr);
+                ++nfev; ++njev;
+                if (!isfinite(cost_try)) {
+                    if (act) c.p[lane] = c.pn[lane];
+                    __syncwarp();
+                    cost = eval_full<F>(c, c.p, nullptr, nullptr);
+                    ++njev;
+                    break;
+                }
+                cost = cost_try;
+            }
+        }
+
         // ---- results -----------------------------------------------------------
         if (P.f_out || P.J_out) {
             cost = eval_full<F>(c, c.p, P.f_out ? P.f_out + (size_t)b * P.nchiv : nullptr,
@@ -543,11 +680,18 @@ __global__ void __launch_bounds__(512, 1) fit_kernel(const __grid_constant__ Fit
         }
         __syncwarp();
         ++nfac;
-        const bool okc = chol_factor<F>(c, 0.0);
+        double pivr = 0.0;
+        const bool okc = chol_factor<F>(c, 0.0, &pivr);
         double* cov_out = P.cov ? P.cov + (size_t)b * NP * NP : nullptr;
         double ld = nan("");
-        if (okc) {
+        if (okc && pivr > 1e-6) {
+            // well conditioned: kappa^2 * eps < ~2e-10, the normal-equation factor is accurate enough
             ld = covariance_from_chol<F>(c, cov_out);
+        } else if (isfinite(cost)) {
+            // ill conditioned: one more pass over the rows, Householder QR of J.diag(dsc)
+            eval_full<F, 1>(c, c.p, nullptr, nullptr);
+            ++njev;
+            ld = covariance_from_qr<F>(c, cov_out);
         } else if (cov_out && act) {
             for (int j = 0; j < NP; ++j) cov_out[lane * NP + j] = nan("");
         }

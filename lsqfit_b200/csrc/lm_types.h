@@ -42,6 +42,7 @@ struct FitParams {
     double xtol, gtol, ftol;
     int maxit;
     int scaler;                 // 0: none (scipy x_scale=1), 1: More' (scipy 'jac', GSL 'more')
+    int polish;                 // max Gauss-Newton refinement steps after the trust-region loop stops
     // ---- outputs (any of f_out, J_out, cov, logdet may be null) ----------------
     double* x_out;              // [B][np]
     double* chi2;               // [B]

@@ -41,7 +41,8 @@ class BatchResult(object):
         self.nit, self.status, self.f, self.J = nit, status, f, J
 
     def numpy(self):
-        return dict((k, v.cpu().numpy()) for k, v in self.__dict__.items() if v is not None)
+        return dict((k, getattr(self, k).cpu().numpy()) for k in
+                    ("x", "chi2", "cov", "logdet", "nit", "status", "f", "J") if getattr(self, k) is not None)
 
 
 class Plan(object):
@@ -109,7 +110,7 @@ class Plan(object):
 
     # ---- the batch fit -------------------------------------------------------------
     def fit_batch(self, mean, p0, tol=1e-8, maxit=1000, scaler="more", B=None,
-                  want_cov=True, want_fJ=False, out=None):
+                  want_cov=True, want_fJ=False, out=None, polish=0):
         """Fit B problems on the device; inputs may be numpy arrays or device tensors.
 
         mean: [B, N] or [N] (shared);  p0: [B, np] or [np] (shared).
@@ -134,14 +135,14 @@ class Plan(object):
         sc = {"more": 1, "jac": 1, 1: 1, "none": 0, "levenberg": 0, None: 0, 0: 0}[scaler]
         ptr = lambda t: t.data_ptr() if t is not None else None
         _cabi.check(_cabi.lib.b200lm_fit_batch(
-            self._h, B, tm.data_ptr(), sm, tp.data_ptr(), sp, xtol, gtol, ftol, int(maxit), sc,
+            self._h, B, tm.data_ptr(), sm, tp.data_ptr(), sp, xtol, gtol, ftol, int(maxit), sc, int(polish),
             out.x.data_ptr(), out.chi2.data_ptr(), ptr(out.cov), out.logdet.data_ptr(),
             out.nit.data_ptr(), out.status.data_ptr(), ptr(out.f), ptr(out.J), self._stream()), self._h)
         out._keep = (tm, tp)        # keep inputs alive until the stream has consumed them
         return out
 
     def fit_batch_host(self, mean, p0, tol=1e-8, maxit=1000, scaler="more", want_cov=True,
-                       want_fJ=False, out=None):
+                       want_fJ=False, out=None, polish=0):
         """Same fit through the host-buffer C entry point: numpy in, numpy out.
         ``out`` may hold preallocated arrays (dict with keys x, chi2, cov, logdet, nit, status)."""
         xtol, gtol, ftol = normalize_tol(tol)
@@ -160,7 +161,7 @@ class Plan(object):
         sc = {"more": 1, "jac": 1, 1: 1, "none": 0, "levenberg": 0, None: 0, 0: 0}[scaler]
         ptr = lambda a: a.ctypes.data if a is not None else None
         _cabi.check(_cabi.lib.b200lm_fit_batch_host(
-            self._h, B, mean.ctypes.data, sm, p0.ctypes.data, sp, xtol, gtol, ftol, int(maxit), sc,
+            self._h, B, mean.ctypes.data, sm, p0.ctypes.data, sp, xtol, gtol, ftol, int(maxit), sc, int(polish),
             ptr(out["x"]), ptr(out["chi2"]), ptr(out.get("cov")), ptr(out["logdet"]),
             ptr(out["nit"]), ptr(out["status"]), ptr(out.get("f")), ptr(out.get("J"))), self._h)
         return out

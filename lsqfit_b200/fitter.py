@@ -61,11 +61,13 @@ class b200_lm(object):
 
     Args mirror the reference plugins: ``x0`` start, ``n`` number of residuals, ``f`` the chiv
     callable, ``tol`` = xtol or (xtol, gtol, ftol), ``maxit`` = max function evaluations.
-    Extra ``fitterargs``: ``scaler`` ('more' default | 'levenberg'), ``device`` (CUDA index).
+    Extra ``fitterargs``: ``scaler`` ('more' default | 'levenberg'), ``device`` (CUDA index), ``polish`` (max
+    Gauss-Newton refinement steps after the trust-region loop; default 0 = stop where the
+    reference's solver stops).
     """
 
     def __init__(self, x0, n, f, tol=(1e-8, 1e-10, 1e-10), maxit=1000, scaler="more", device=0,
-                 **extra_args):
+                 polish=0, **extra_args):
         if extra_args:
             raise ValueError("b200_lm: unknown fitter arguments: " + ", ".join(sorted(extra_args)))
         spec = getattr(f, "b200", None)
@@ -82,7 +84,7 @@ class b200_lm(object):
         if n != plan.nchiv:
             raise ValueError("b200_lm: n=%d does not match the whitening (%d residuals)" % (n, plan.nchiv))
         out = plan.fit_batch_host(spec.mean, self.x0.reshape(1, -1), tol=self.tol, maxit=maxit,
-                                  scaler=scaler, want_cov=True, want_fJ=True)
+                                  scaler=scaler, want_cov=True, want_fJ=True, polish=polish)
         self.x = out["x"][0].copy()
         self.cov = out["cov"][0].copy()
         self.f = out["f"][0].copy()

@@ -19,7 +19,7 @@ for _ in range(5):
 print(json.dumps(dict(dgemm_8192_tflops=2 * n ** 3 / (best * 1e-3) / 1e12, ms=best)))
 PY
 cat gpurun_out/dgemm.json
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
+timeout 1500 python -m pytest tests -m gpu -q --tb=short -s > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -40 gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
