@@ -172,7 +172,7 @@ int b200lm_set_weights(b200lm_handle h, int ndiag, const int* diag_idx, const do
     }
     std::vector<BlockDesc> blk(nblk);
     std::vector<double> wt;
-    int idx_off = 0, chiv_off = ndiag, w_off = 0, rb = 64;
+    int idx_off = 0, chiv_off = ndiag, w_off = 0, rb = 32, max_nin = 0;
     for (int k = 0; k < nblk; ++k) {
         const int nin = blk_nin[k], nout = blk_nout[k];
         if (nin <= 0 || nout < 0 || nout > nin) return set_error(h, B200LM_EINVAL, "bad block shape");
@@ -188,11 +188,16 @@ int b200lm_set_weights(b200lm_handle h, int ndiag, const int* diag_idx, const do
         for (int r = 0; r < nout; ++r)
             for (int j = 0; j < nin; ++j)
                 wt[b.wt_off + (size_t)j * b.ldw + r] = blk_w[w_off + (size_t)r * nin + j];
-        rb = std::max(rb, nout <= 64 ? nin : nin + 64);
+        max_nin = std::max(max_nin, nin);
         idx_off += nin; w_off += nin * nout; chiv_off += nout;
     }
     for (int i = 0; i < N; ++i)
         if (!seen[i]) return set_error(h, B200LM_EINVAL, "every y(+)prior entry must appear in exactly one block");
+    // the row buffer doubles as the scratch vector of the residual-only pass: rb*LDR >= max n_in
+    {
+        const int ldr = (h->np + 1) | 1;
+        rb = std::max(rb, (max_nin + ldr - 1) / ldr);
+    }
     // does at least one warp fit?
     if (h->fe->per_warp_bytes(rb) > h->smem_budget)
         return set_error(h, B200LM_ESIZE, "correlated block too large for the per-warp shared-memory plan");

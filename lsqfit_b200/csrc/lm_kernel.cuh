@@ -47,6 +47,8 @@ struct FitLayout {
     static constexpr int LDR = NP1 | 1;      // odd: lane-per-row accesses are conflict free
     static constexpr int LDA = NP | 1;
     static constexpr int NVEC = 6;
+    // register budget: 16 warps/CTA leave 128 registers per thread, 12 warps leave 168
+    static constexpr int MAX_WARPS = NP > 10 ? 12 : 16;
     __host__ __device__ static int per_warp_doubles(int rb) {
         int n = rb * LDR + 2 * NP * LDA + NVEC * NP;
         return (n + 1) & ~1;
@@ -254,176 +256,256 @@ __device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, doubl
         else { __syncwarp(); qr_update<F>(c, c.R, nrows); }
         __syncwarp();
     }
-    // correlated blocks: rows of [G | delta], then W.[G | delta]
+    // correlated blocks: J_blk = W.[G | delta].  Output rows are owned by lanes (two per lane per
+    // 64-row group) and stay in registers while the input rows [G | delta] stream through the
+    // row buffer in chunks of P.rb rows; the finished rows then pass through the same buffer,
+    // 32 at a time, into the normal equations (or the QR update).
     for (int b = 0; b < P.nblk; ++b) {
         const BlockDesc bd = P.blk[b];
-        for (int k = lane; k < bd.n_in; k += 32) {
-            const int idx = P.blk_idx[bd.idx_off + k];
-            if (idx < P.ny) {
-                double gr[NP];
-                const double f = F::value_grad(P.x + (size_t)idx * P.nx, idx, pv, gr);
-#pragma unroll
-                for (int j = 0; j < NP; ++j) c.R[k * LDR + j] = gr[j];
-                c.R[k * LDR + NP] = f - c.mean[idx];
-            } else {
-                const int j0 = idx - P.ny;
-#pragma unroll
-                for (int j = 0; j < NP; ++j) c.R[k * LDR + j] = (j == j0) ? 1.0 : 0.0;
-                c.R[k * LDR + NP] = pv[j0] - c.mean[idx];
-            }
-        }
-        __syncwarp();
         const double* wt = c.wt + bd.wt_off;
-        const bool inplace = bd.n_out <= 64;
-        double* S = inplace ? c.R : c.R + (size_t)bd.n_in * LDR;
         for (int g0 = 0; g0 < bd.n_out; g0 += 64) {
             const int r0 = g0 + lane, r1 = g0 + lane + 32;
+            const bool h0 = r0 < bd.n_out, h1 = r1 < bd.n_out;
             double a0[NP + 1], a1[NP + 1];
 #pragma unroll
             for (int j = 0; j <= NP; ++j) { a0[j] = 0.0; a1[j] = 0.0; }
-            for (int k = 0; k < bd.n_in; ++k) {
-                const double w0 = r0 < bd.n_out ? wt[(size_t)k * bd.ldw + r0] : 0.0;
-                const double w1 = r1 < bd.n_out ? wt[(size_t)k * bd.ldw + r1] : 0.0;
+            for (int k0 = 0; k0 < bd.n_in; k0 += P.rb) {
+                const int nk = min(P.rb, bd.n_in - k0);
+                for (int k = lane; k < nk; k += 32) {
+                    const int idx = P.blk_idx[bd.idx_off + k0 + k];
+                    if (idx < P.ny) {
+                        double gr[NP];
+                        const double f = F::value_grad(P.x + (size_t)idx * P.nx, idx, pv, gr);
 #pragma unroll
-                for (int j = 0; j <= NP; ++j) {
-                    const double v = c.R[k * LDR + j];
-                    a0[j] = fma(w0, v, a0[j]);
-                    a1[j] = fma(w1, v, a1[j]);
+                        for (int j = 0; j < NP; ++j) c.R[k * LDR + j] = gr[j];
+                        c.R[k * LDR + NP] = f - c.mean[idx];
+                    } else {
+                        const int j0 = idx - P.ny;
+#pragma unroll
+                        for (int j = 0; j < NP; ++j) c.R[k * LDR + j] = (j == j0) ? 1.0 : 0.0;
+                        c.R[k * LDR + NP] = pv[j0] - c.mean[idx];
+                    }
                 }
-            }
-            if (inplace) __syncwarp();          // everyone has finished reading R
-            if (r0 < bd.n_out) {
+                __syncwarp();
+                const double* wk = wt + (size_t)k0 * bd.ldw;
+#pragma unroll 2
+                for (int k = 0; k < nk; ++k) {
+                    const double w0 = h0 ? wk[(size_t)k * bd.ldw + r0] : 0.0;
+                    const double w1 = h1 ? wk[(size_t)k * bd.ldw + r1] : 0.0;
 #pragma unroll
-                for (int j = 0; j <= NP; ++j) S[lane * LDR + j] = a0[j];
+                    for (int j = 0; j <= NP; ++j) {
+                        const double v = c.R[k * LDR + j];
+                        a0[j] = fma(w0, v, a0[j]);
+                        a1[j] = fma(w1, v, a1[j]);
+                    }
+                }
+                __syncwarp();                      // everyone has finished reading this chunk
             }
-            if (r1 < bd.n_out) {
+            // rows g0 .. g0+31
+            if (h0) {
 #pragma unroll
-                for (int j = 0; j <= NP; ++j) S[(lane + 32) * LDR + j] = a1[j];
+                for (int j = 0; j <= NP; ++j) c.R[lane * LDR + j] = a0[j];
             }
             __syncwarp();
-            const int nrows = min(64, bd.n_out - g0);
-            if (fout || Jout) emit_rows<F>(S, nrows, bd.chiv_off + g0, lane, fout, Jout);
-            if (MODE == 0) accumulate<F>(c, S, nrows, acc);
-            else { __syncwarp(); qr_update<F>(c, S, nrows); }
+            int nrows = min(32, bd.n_out - g0);
+            if (fout || Jout) emit_rows<F>(c.R, nrows, bd.chiv_off + g0, lane, fout, Jout);
+            if (MODE == 0) accumulate<F>(c, c.R, nrows, acc);
+            else { __syncwarp(); qr_update<F>(c, c.R, nrows); }
             __syncwarp();
+            // rows g0+32 .. g0+63
+            nrows = min(32, bd.n_out - g0 - 32);
+            if (nrows > 0) {
+                if (h1) {
+#pragma unroll
+                    for (int j = 0; j <= NP; ++j) c.R[lane * LDR + j] = a1[j];
+                }
+                __syncwarp();
+                if (fout || Jout) emit_rows<F>(c.R, nrows, bd.chiv_off + g0 + 32, lane, fout, Jout);
+                if (MODE == 0) accumulate<F>(c, c.R, nrows, acc);
+                else { __syncwarp(); qr_update<F>(c, c.R, nrows); }
+                __syncwarp();
+            }
         }
     }
     return 0.5 * warp_sum(acc);
 }
 
 // ---------------------------------------------------------------------------
-// small dense kernels on the warp: lane i owns row/element i
+// small dense kernels on the warp: lane i owns row i, everything in registers
 // ---------------------------------------------------------------------------
-// L L^T = d_i A_ij d_j + alpha delta_ij ; false if not numerically positive definite
-template <class F>
-__device__ bool chol_factor(WarpCtx<F>& c, double alpha, double* min_pivot_ratio = nullptr) {
-    typedef FitLayout<F> Lay;
-    constexpr int NP = Lay::NP, LDA = Lay::LDA;
-    const int i = c.lane;
-    const double di = i < NP ? c.dsc[i] : 0.0;
-    bool ok = true;
-    double minr = 1.0;
-    for (int j = 0; j < NP; ++j) {
-        double s = 0.0, m = 0.0;
-        if (i >= j && i < NP) {
-            s = c.A[i * LDA + j] * di * c.dsc[j];
-            if (i == j) { s += alpha; m = s; }
-            for (int k = 0; k < j; ++k) s = fma(-c.L[i * LDA + k], c.L[j * LDA + k], s);
-        }
-        const double sjj = __shfl_sync(B200LM_FULL, s, j);
-        const double mjj = __shfl_sync(B200LM_FULL, m, j);
-        if (!(sjj > 8.0 * NP * 2.220446049250313e-16 * mjj) || !isfinite(sjj)) { ok = false; break; }
-        minr = fmin(minr, sjj / mjj);
-        const double inv = rsqrt(sjj);
-        if (i == j) { c.L[j * LDA + j] = sjj * inv; c.idg[j] = inv; }
-        else if (i > j && i < NP) c.L[i * LDA + j] = s * inv;
-        __syncwarp();
+// Factor of the scaled, shifted normal matrix held in registers: lane i keeps row i of L in
+// l[] (entries k <= i), column i of L in u[] (entries k >= i) and 1/L_ii in inv.
+template <int NP>
+struct CholReg {
+    double l[NP];
+    double u[NP];
+    double inv;
+};
+
+// L L^T = d_i A_ij d_j + alpha delta_ij, right-looking, fully unrolled: the column of the
+// current step is broadcast with warp shuffles.  false if not numerically positive definite.
+template <int NP, int LDA>
+__device__ __forceinline__ bool chol_factor(const double* A, const double* dsc, int lane, double alpha,
+                                            CholReg<NP>& f, double& minr) {
+    const int i = lane;
+    const bool act = i < NP;
+    const double di = act ? dsc[i] : 0.0;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        double v = act ? A[i * LDA + k] * di * dsc[k] : 0.0;
+        if (k == i) v = act ? v + alpha : 1.0;
+        f.l[k] = v;
+        f.u[k] = 0.0;
     }
-    __syncwarp();
-    if (min_pivot_ratio) *min_pivot_ratio = minr;
+    double mdiag = 1.0;                 // original diagonal entry of this lane's row
+#pragma unroll
+    for (int k = 0; k < NP; ++k) if (k == i) mdiag = f.l[k];
+    minr = 1.0;
+    bool ok = true;
+    f.inv = 1.0;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        const double piv = __shfl_sync(B200LM_FULL, f.l[j], j);
+        const double mjj = __shfl_sync(B200LM_FULL, mdiag, j);
+        // no early exit: a `break` would keep the loop from unrolling
+        if (!(piv > 8.0 * NP * 2.220446049250313e-16 * mjj) || !isfinite(piv)) ok = false;
+        minr = fmin(minr, piv / mjj);
+        const double inv = rsqrt(piv);
+        if (i == j) f.inv = inv;
+        const double lij = (i == j) ? piv * inv : f.l[j] * inv;      // L[i][j]
+        f.l[j] = lij;
+        if (i == j) f.u[j] = lij;
+#pragma unroll
+        for (int k = j + 1; k < NP; ++k) {
+            const double lkj = __shfl_sync(B200LM_FULL, lij, k);      // L[k][j]
+            f.l[k] = fma(-lij, lkj, f.l[k]);                          // row i, column k (used for k <= i)
+            if (i == j) f.u[k] = lkj;                                 // column j of L kept by lane j
+        }
+    }
     return ok;
 }
 // y = L^-1 b (lane i holds b_i, returns y_i)
-template <class F>
-__device__ __forceinline__ double solve_lower(WarpCtx<F>& c, double b) {
-    typedef FitLayout<F> Lay;
-    constexpr int NP = Lay::NP, LDA = Lay::LDA;
-    const int i = c.lane;
-#pragma unroll 4
+template <int NP>
+__device__ __forceinline__ double solve_lower(const CholReg<NP>& f, int lane, double b) {
+#pragma unroll
     for (int j = 0; j < NP; ++j) {
-        const double yj = __shfl_sync(B200LM_FULL, b, j) * c.idg[j];
-        if (i == j) b = yj;
-        else if (i > j && i < NP) b = fma(-c.L[i * LDA + j], yj, b);
+        const double yj = __shfl_sync(B200LM_FULL, b * f.inv, j);
+        if (lane == j) b = yj;
+        else if (lane > j) b = fma(-f.l[j], yj, b);
     }
     return b;
 }
 // x = L^-T b
-template <class F>
-__device__ __forceinline__ double solve_upper(WarpCtx<F>& c, double b) {
-    typedef FitLayout<F> Lay;
-    constexpr int NP = Lay::NP, LDA = Lay::LDA;
-    const int i = c.lane;
-#pragma unroll 4
+template <int NP>
+__device__ __forceinline__ double solve_upper(const CholReg<NP>& f, int lane, double b) {
+#pragma unroll
     for (int j = NP - 1; j >= 0; --j) {
-        const double xj = __shfl_sync(B200LM_FULL, b, j) * c.idg[j];
-        if (i == j) b = xj;
-        else if (i < j) b = fma(-c.L[j * LDA + i], xj, b);
+        const double xj = __shfl_sync(B200LM_FULL, b * f.inv, j);
+        if (lane == j) b = xj;
+        else if (lane < j) b = fma(-f.u[j], xj, b);
     }
     return b;
 }
 
+// One factorisation + the solves every caller needs, as ONE out-of-line function (the
+// unrolled factor is ~1.5k instructions; five inlined copies would thrash the i-cache and
+// the register allocator).  With the lane-distributed scaled gradient gh:
+//     p = -(Ah + alpha I)^-1 gh ,  res[0] = |p| ,  res[1] = |L^-1 p|^2 ,  res[2] = min pivot ratio
+// Optionally leaves L (rows) and 1/L_ii in shared memory for the covariance routine.
+template <int NP, int LDA>
+__device__ __noinline__ bool factor_solve(const double* A, const double* dsc, double* Lsm, double* idg,
+                                          int lane, double alpha, double gh, bool store,
+                                          double* p_out, double* res) {
+    CholReg<NP> f;
+    double minr;
+    const bool ok = chol_factor<NP, LDA>(A, dsc, lane, alpha, f, minr);
+    const bool act = lane < NP;
+    double p = 0.0, pn = 0.0, w2 = 0.0;
+    if (ok) {
+        p = solve_upper<NP>(f, lane, solve_lower<NP>(f, lane, act ? -gh : 0.0));
+        pn = sqrt(warp_sum(act ? p * p : 0.0));
+        const double w = solve_lower<NP>(f, lane, act ? p : 0.0);
+        w2 = warp_sum(act ? w * w : 0.0);
+        if (store) {
+            if (act) {
+#pragma unroll
+                for (int k = 0; k < NP; ++k) Lsm[lane * LDA + k] = (k <= lane) ? f.l[k] : 0.0;
+                idg[lane] = f.inv;
+            }
+            __syncwarp();
+        }
+    }
+    *p_out = p;
+    res[0] = pn; res[1] = w2; res[2] = minr;
+    return ok;
+}
+
+// Gauss-Newton step of the current outer iteration (alpha = 0), cached across rejected trials
+struct GNCache {
+    bool valid, full_rank;
+    double p, pn, w2;
+};
+
 // Trust-region sub-problem in scaled variables: min 1/2 s^T Ah s + gh^T s, |s| <= Delta.
 // gh: lane-distributed scaled gradient.  Returns lane-distributed step; updates alpha.
+// (cf. scipy/optimize/_lsq/common.py: solve_lsq_trust_region, with the secular equation
+// evaluated through Cholesky factors instead of singular values.)
 template <class F>
-__device__ double solve_tr(WarpCtx<F>& c, double gh, double Delta, double& alpha, int& nfac) {
+__device__ double solve_tr(WarpCtx<F>& c, double gh, double Delta, double& alpha, int& nfac, GNCache& gn) {
     typedef FitLayout<F> Lay;
-    constexpr int NP = Lay::NP;
-    const bool act = c.lane < NP;
-    ++nfac;
-    const bool full_rank = chol_factor<F>(c, 0.0);
-    double p = 0.0, pn = 0.0;
-    if (full_rank) {
-        p = solve_upper<F>(c, solve_lower<F>(c, act ? -gh : 0.0));
-        pn = sqrt(warp_sum(act ? p * p : 0.0));
-        if (pn <= Delta) { alpha = 0.0; return p; }
+    constexpr int NP = Lay::NP, LDA = Lay::LDA;
+    const int lane = c.lane;
+    const bool act = lane < NP;
+    double res[3];
+    double p = 0.0;
+    if (!gn.valid) {
+        ++nfac;
+        gn.full_rank = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, 0.0, gh, false, &p, res);
+        gn.p = p; gn.pn = res[0]; gn.w2 = res[1];
+        gn.valid = true;
     }
+    const bool full_rank = gn.full_rank;
+    if (full_rank && gn.pn <= Delta) { alpha = 0.0; return gn.p; }
+    p = gn.p;
+    double pn = gn.pn;
     double alpha_upper = sqrt(warp_sum(act ? gh * gh : 0.0)) / Delta;
     double alpha_lower = 0.0;
     if (full_rank) {
-        const double w = solve_lower<F>(c, act ? p : 0.0);
         const double phi = pn - Delta;
-        const double phi_prime = -warp_sum(act ? w * w : 0.0) / pn;
+        const double phi_prime = -gn.w2 / pn;
         alpha_lower = -phi / phi_prime;
     }
     if (!full_rank && alpha == 0.0)
         alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
-    bool have_p = false;
-    for (int it = 0; it < 10; ++it) {
-        if (alpha < alpha_lower || alpha > alpha_upper)
+    bool have_p = false, converged = false;
+    // iterations 0..9: Newton on the secular equation; iteration 10: the step at the final alpha
+    for (int it = 0; it <= 10; ++it) {
+        const bool last = converged || it == 10;
+        if (!last && (alpha < alpha_lower || alpha > alpha_upper))
             alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
         ++nfac;
-        if (!chol_factor<F>(c, alpha)) {
+        double pt;
+        const bool ok = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, alpha, gh, false, &pt, res);
+        if (last) {
+            if (ok) { p = pt; have_p = true; }
+            break;
+        }
+        if (!ok) {
             alpha_lower = fmax(alpha_lower, alpha);
             alpha = fmax(2.0 * alpha, 0.001 * alpha_upper);
             if (alpha > alpha_upper) alpha_upper = 2.0 * alpha;
             continue;
         }
-        p = solve_upper<F>(c, solve_lower<F>(c, act ? -gh : 0.0));
+        p = pt;
         have_p = true;
-        pn = sqrt(warp_sum(act ? p * p : 0.0));
+        pn = res[0];
         const double phi = pn - Delta;
-        const double w = solve_lower<F>(c, act ? p : 0.0);
-        const double phi_prime = -warp_sum(act ? w * w : 0.0) / pn;
+        const double phi_prime = -res[1] / pn;
         if (phi < 0.0) alpha_upper = alpha;
         const double ratio = phi / phi_prime;
         alpha_lower = fmax(alpha_lower, alpha - ratio);
         alpha -= (phi + Delta) * ratio / Delta;
-        if (fabs(phi) < 0.01 * Delta) break;
-    }
-    ++nfac;
-    if (chol_factor<F>(c, alpha)) {
-        p = solve_upper<F>(c, solve_lower<F>(c, act ? -gh : 0.0));
-        have_p = true;
+        if (fabs(phi) < 0.01 * Delta) converged = true;
     }
     if (!have_p) p = act ? -gh : 0.0;             // steepest descent fallback
     pn = sqrt(warp_sum(act ? p * p : 0.0));
@@ -525,7 +607,7 @@ __device__ __forceinline__ void setup_ctx(WarpCtx<F>& c, double* smem, const Fit
 }
 
 template <class F>
-__global__ void __launch_bounds__(512, 1) fit_kernel(const __grid_constant__ FitParams P) {
+__global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(const __grid_constant__ FitParams P) {
     typedef FitLayout<F> Lay;
     constexpr int NP = Lay::NP, LDA = Lay::LDA;
     static_assert(NP <= 32, "one lane per parameter");
@@ -572,8 +654,10 @@ __global__ void __launch_bounds__(512, 1) fit_kernel(const __grid_constant__ Fit
             const double gh = d * gi;
             double actual_reduction = -1.0, cost_new = cost;
             int term = -2;
+            GNCache gn;
+            gn.valid = false;
             while (actual_reduction <= 0.0 && nfev < P.maxit) {
-                const double sh = solve_tr<F>(c, gh, Delta, alpha, nfac);
+                const double sh = solve_tr<F>(c, gh, Delta, alpha, nfac, gn);
                 const double step = act ? d * sh : 0.0;
                 if (act) { c.pn[lane] = c.p[lane] + step; c.idg[lane] = step; }
                 __syncwarp();
@@ -635,9 +719,9 @@ __global__ void __launch_bounds__(512, 1) fit_kernel(const __grid_constant__ Fit
             double dec_prev = 1e300;
             for (int it = 0; it <= P.polish; ++it) {
                 ++nfac;
-                if (!chol_factor<F>(c, 0.0)) break;
                 const double gh = act ? d * c.g[lane] : 0.0;
-                const double sh = solve_upper<F>(c, solve_lower<F>(c, act ? -gh : 0.0));
+                double sh, pres[3];
+                if (!factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, 0.0, gh, false, &sh, pres)) break;
                 const double dec = -warp_sum(act ? gh * sh : 0.0);
                 if (it > 0) {
                     if (!(dec < dec_prev)) {                        // the last step did not help: undo it
@@ -680,8 +764,9 @@ __global__ void __launch_bounds__(512, 1) fit_kernel(const __grid_constant__ Fit
         }
         __syncwarp();
         ++nfac;
-        double pivr = 0.0;
-        const bool okc = chol_factor<F>(c, 0.0, &pivr);
+        double pdummy, fres[3];
+        const bool okc = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, 0.0, 0.0, true, &pdummy, fres);
+        const double pivr = fres[2];
         double* cov_out = P.cov ? P.cov + (size_t)b * NP * NP : nullptr;
         double ld = nan("");
         if (okc && pivr > 1e-6) {
@@ -715,7 +800,7 @@ __global__ void __launch_bounds__(512, 1) fit_kernel(const __grid_constant__ Fit
 // residual + Jacobian at given parameter vectors (test hook for the chiv parity of
 // reference src/lsqfit/_utilities.pyx:65-94); P.p0 holds the B parameter vectors.
 template <class F>
-__global__ void __launch_bounds__(512, 1) resjac_kernel(const __grid_constant__ FitParams P) {
+__global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) resjac_kernel(const __grid_constant__ FitParams P) {
     typedef FitLayout<F> Lay;
     constexpr int NP = Lay::NP;
     extern __shared__ double smem[];
@@ -753,7 +838,7 @@ inline cudaError_t plan_launch(FitParams& P, int sm_count, size_t smem_budget, L
     const size_t avail = smem_budget - (P.wt_in_smem ? wt_bytes : 0);
     int warps = (int)(avail / per_warp);
     if (warps < 1) return cudaErrorInvalidConfiguration;
-    if (warps > 16) warps = 16;
+    if (warps > Lay::MAX_WARPS) warps = Lay::MAX_WARPS;
     P.warps = warps;
     li.block = warps * 32;
     li.smem = (P.wt_in_smem ? wt_bytes : 0) + warps * per_warp;

@@ -1,17 +1,35 @@
-import json, numpy as np, sys, warnings
-warnings.simplefilter('ignore')
-sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+import numpy as np, sys, time, torch
+sys.path.insert(0, '.')
 import lsqfit_b200 as lb
-from oracle.fit import nonlinear_fit
-from parity_util import TIGHT, exact_minimum
-d = json.load(open('tests/golden/nist.json'))
-for name in ['lanczos3', 'gauss1', 'mgh10']:
-    pr = [p for p in d['problems'] if p['name']==name][0]
-    x = np.array(pr['x'])
-    fo = nonlinear_fit(pr['form'], x, pr['y'], pr['ysdev'], prior_mean=pr['prior_mean'], prior_cov=pr['prior_sdev'], p0=pr['p0'], tol=TIGHT, x_scale='jac')
-    xe, fe, Je, cove = exact_minimum(fo); sd=np.sqrt(np.diag(cove))
-    print(name, 'oracle nit', fo.nit, 'gap', np.max(np.abs(fo.pmean-xe)/sd))
-    for pol in [0, 1, 4, 10]:
-        fd = lb.nonlinear_fit(data=(x, pr['y'], pr['ysdev']), fcn=pr['form'], prior=(pr['prior_mean'], pr['prior_sdev']), p0=pr['p0'], tol=TIGHT, polish=pol)
-        g = fd.J.T @ fd.residuals
-        print('   polish', pol, 'nit', fd.nit, fd.fitter_results['status'], 'gap', np.max(np.abs(fd.pmean-xe)/sd), 'g*sd', np.max(np.abs(g)*sd))
+from lsqfit_b200 import configs
+cfg = configs.c3(B=10000)
+ny, npar = cfg["ny"], cfg["np"]; N = ny + npar
+full = np.zeros((N, N)); full[:ny, :ny] = cfg["ycov"]; full[ny:, ny:] = np.diag(cfg["prior_sdev"] ** 2)
+mean0 = np.concatenate([cfg["f"], cfg["prior_mean"]])
+pdf = lb.PDF(mean0, full, svdcut=cfg["svdcut"])
+means = configs.bootstrap_means(cfg, cfg["B"], cfg["seed"], cov=pdf.cov[:ny, :ny])
+plan = lb.Plan("multiexp", npar, ny, cfg["x"], pdf.i_invwgts)
+md = torch.as_tensor(means).cuda(); p0 = torch.as_tensor(cfg["p0"]).cuda()
+def timeit(m, reps=5):
+    out = plan.fit_batch(m, p0, tol=cfg["tol"], maxit=cfg["maxit"])
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): plan.fit_batch(m, p0, tol=cfg["tol"], maxit=cfg["maxit"], out=out)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1)/reps, out
+t, out = timeit(md)
+nit = out.nit.cpu().numpy()
+print("all: %.3f ms; nit mean %.1f median %d p90 %d p99 %d max %d" % (t, nit.mean(), np.median(nit), np.percentile(nit,90), np.percentile(nit,99), nit.max()))
+print("nit histogram:", np.histogram(nit, bins=[0,10,20,30,50,100,200,400,1001])[0])
+order = np.argsort(nit)
+for frac in [0.5, 0.9, 0.99, 0.999]:
+    sel = order[:int(frac*len(nit))]
+    ms = md[torch.as_tensor(sel).cuda()].contiguous()
+    t2, o2 = timeit(ms)
+    print("fastest %.1f%%: B=%d max nit %d total nit %d: %.3f ms  -> %.0f fits/s" % (100*frac, len(sel), nit[sel].max(), nit[sel].sum(), t2, len(sel)/t2*1e3))
+# replicate to larger batches
+for rep in [4, 16]:
+    ms = md.repeat(rep, 1).contiguous()
+    t2, o2 = timeit(ms, reps=2)
+    print("B=%d: %.3f ms -> %.0f fits/s" % (ms.shape[0], t2, ms.shape[0]/t2*1e3))
