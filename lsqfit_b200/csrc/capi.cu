@@ -172,7 +172,8 @@ int b200lm_set_weights(b200lm_handle h, int ndiag, const int* diag_idx, const do
     }
     std::vector<BlockDesc> blk(nblk);
     std::vector<double> wt;
-    int idx_off = 0, chiv_off = ndiag, w_off = 0, rb = 32, max_nin = 0;
+    int idx_off = 0, chiv_off = ndiag, w_off = 0;
+    const int rb = 32;
     for (int k = 0; k < nblk; ++k) {
         const int nin = blk_nin[k], nout = blk_nout[k];
         if (nin <= 0 || nout < 0 || nout > nin) return set_error(h, B200LM_EINVAL, "bad block shape");
@@ -182,22 +183,22 @@ int b200lm_set_weights(b200lm_handle h, int ndiag, const int* diag_idx, const do
             seen[idx] = 1;
         }
         BlockDesc& b = blk[k];
-        b.n_in = nin; b.n_out = nout; b.ldw = (nout + 7) & ~7; if (b.ldw == 0) b.ldw = 8;
+        b.n_in = nin; b.n_out = nout;
+        // row-major [n_out padded to 8][ldw], zero padded; ldw == 4 (mod 16) >= n_in rounded to 4
+        // keeps the DMMA A-fragment loads at the minimum of two shared-memory wavefronts
+        int ldw = (nin + 3) & ~3;
+        while ((ldw & 15) != 4) ldw += 4;
+        b.ldw = ldw;
+        const int nout8 = ((nout + 7) & ~7) > 0 ? ((nout + 7) & ~7) : 8;
         b.idx_off = idx_off; b.wt_off = (int)wt.size(); b.chiv_off = chiv_off;
-        wt.resize(wt.size() + (size_t)nin * b.ldw, 0.0);
+        wt.resize(wt.size() + (size_t)nout8 * ldw, 0.0);
         for (int r = 0; r < nout; ++r)
             for (int j = 0; j < nin; ++j)
-                wt[b.wt_off + (size_t)j * b.ldw + r] = blk_w[w_off + (size_t)r * nin + j];
-        max_nin = std::max(max_nin, nin);
+                wt[b.wt_off + (size_t)r * ldw + j] = blk_w[w_off + (size_t)r * nin + j];
         idx_off += nin; w_off += nin * nout; chiv_off += nout;
     }
     for (int i = 0; i < N; ++i)
         if (!seen[i]) return set_error(h, B200LM_EINVAL, "every y(+)prior entry must appear in exactly one block");
-    // the row buffer doubles as the scratch vector of the residual-only pass: rb*LDR >= max n_in
-    {
-        const int ldr = (h->np + 1) | 1;
-        rb = std::max(rb, (max_nin + ldr - 1) / ldr);
-    }
     // does at least one warp fit?
     if (h->fe->per_warp_bytes(rb) > h->smem_budget)
         return set_error(h, B200LM_ESIZE, "correlated block too large for the per-warp shared-memory plan");

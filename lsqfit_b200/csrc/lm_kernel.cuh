@@ -44,13 +44,26 @@ template <class F>
 struct FitLayout {
     static constexpr int NP = F::NP;
     static constexpr int NP1 = NP + 1;
-    static constexpr int LDR = NP1 | 1;      // odd: lane-per-row accesses are conflict free
+    // Row buffer columns: [ G or J (NP) | delta or r (1) | zero padding ].  The FP64 tensor
+    // instruction (DMMA m8n8k4) consumes 8-column tiles:
+    //   NTA tiles cover the NP Jacobian columns (J^T J),
+    //   if NP is not a multiple of 8 the residual column rides in the padding of the last tile
+    //   (DELTA_IN_TILE) and J^T r / r^T r fall out of the same tiles; otherwise the residual
+    //   column is handled by plain DFMA (a ninth column would cost a whole extra tile).
+    static constexpr int NTA = (NP + 7) / 8;
+    static constexpr bool DELTA_IN_TILE = (NP % 8) != 0;
+    static constexpr int NT = NTA;                         // tiles in the W.[G|delta] product
+    static constexpr int NCOL = 8 * NT > NP1 ? 8 * NT : NP1;
+    // leading dimension == 4 (mod 8): fragment loads (row = 4s + lane%4, col = 8t + lane/4)
+    // then hit every shared-memory bank pair exactly twice (the minimum for 256 B)
+    static constexpr int LDR = ((NCOL + 3) / 8) * 8 + 4;
     static constexpr int LDA = NP | 1;
     static constexpr int NVEC = 6;
+    static constexpr int NTRI = NT * (NT + 1) / 2;         // upper-triangular tile pairs
     // register budget: 16 warps/CTA leave 128 registers per thread, 12 warps leave 168
     static constexpr int MAX_WARPS = NP > 10 ? 12 : 16;
     __host__ __device__ static int per_warp_doubles(int rb) {
-        int n = rb * LDR + 2 * NP * LDA + NVEC * NP;
+        int n = rb * LDR + rb + 2 * NP * LDA + NVEC * NP;  // R | dvec | A | L | vectors
         return (n + 1) & ~1;
     }
 };
@@ -61,17 +74,36 @@ struct WarpCtx {
     const FitParams& P;
     const double* wt;       // whitening matrices (shared or global)
     const double* mean;     // this fit's y(+)prior means
-    double *R, *A, *L, *p, *pn, *g, *sinv, *dsc, *idg;
+    double *R, *dvec, *A, *L, *p, *pn, *g, *sinv, *dsc, *idg;
     int lane;
     __device__ WarpCtx(const FitParams& P_) : P(P_) {}
 };
+
+// D(8x8) += A(8x4) . B(4x8) on the FP64 tensor path.  Fragment ownership (PTX m8n8k4):
+//   a = A[lane/4][lane%4]      b = B[lane%4][lane/4]      c0,c1 = C[lane/4][2*(lane%4) + {0,1}]
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// y_r = sum_k W[r][k] v[k] for the two rows owned by this lane, plain DFMA.  k is rotated by
+// the lane id so that the row-major, padded W and the compact vector are read conflict free.
+__device__ __forceinline__ void matvec2(const double* W, int ldk, int r0, int r1, bool h0, bool h1,
+                                        const double* v, int nk, int lane, double& y0, double& y1) {
+    int k = lane % nk;
+    for (int kk = 0; kk < nk; ++kk) {
+        const double vk = v[k];
+        if (h0) y0 = fma(W[(size_t)r0 * ldk + k], vk, y0);
+        if (h1) y1 = fma(W[(size_t)r1 * ldk + k], vk, y1);
+        k = (k + 1 == nk) ? 0 : k + 1;
+    }
+}
 
 // ---------------------------------------------------------------------------
 // residual only: returns cost = 1/2 sum r^2 (same value in every lane)
 // ---------------------------------------------------------------------------
 template <class F>
 __device__ double eval_cost(WarpCtx<F>& c, const double* pv, double* fout) {
-    typedef FitLayout<F> Lay;
     const FitParams& P = c.P;
     const int lane = c.lane;
     double acc = 0.0;
@@ -88,57 +120,119 @@ __device__ double eval_cost(WarpCtx<F>& c, const double* pv, double* fout) {
         acc = fma(r, r, acc);
         if (fout) fout[P.nd_fn + i] = r;
     }
-    double* dv = c.R;
     for (int b = 0; b < P.nblk; ++b) {
         const BlockDesc bd = P.blk[b];
-        for (int k = lane; k < bd.n_in; k += 32) {
-            const int idx = P.blk_idx[bd.idx_off + k];
-            const double v = idx < P.ny ? F::value(P.x + (size_t)idx * P.nx, idx, pv) : pv[idx - P.ny];
-            dv[k] = v - c.mean[idx];
+        const double* W = c.wt + bd.wt_off;
+        for (int g0 = 0; g0 < bd.n_out; g0 += 64) {
+            const int r0 = g0 + lane, r1 = g0 + lane + 32;
+            const bool h0 = r0 < bd.n_out, h1 = r1 < bd.n_out;
+            double y0 = 0.0, y1 = 0.0;
+            for (int k0 = 0; k0 < bd.n_in; k0 += P.rb) {
+                const int nk = min(P.rb, bd.n_in - k0);
+                for (int k = lane; k < nk; k += 32) {
+                    const int idx = P.blk_idx[bd.idx_off + k0 + k];
+                    const double v = idx < P.ny ? F::value(P.x + (size_t)idx * P.nx, idx, pv) : pv[idx - P.ny];
+                    c.dvec[k] = v - c.mean[idx];
+                }
+                __syncwarp();
+                matvec2(W + k0, bd.ldw, r0, r1, h0, h1, c.dvec, nk, lane, y0, y1);
+                __syncwarp();
+            }
+            if (h0) { acc = fma(y0, y0, acc); if (fout) fout[bd.chiv_off + r0] = y0; }
+            if (h1) { acc = fma(y1, y1, acc); if (fout) fout[bd.chiv_off + r1] = y1; }
         }
-        __syncwarp();
-        const double* wt = c.wt + bd.wt_off;
-        for (int r = lane; r < bd.n_out; r += 32) {
-            double s = 0.0;
-            for (int k = 0; k < bd.n_in; ++k) s = fma(wt[(size_t)k * bd.ldw + r], dv[k], s);
-            acc = fma(s, s, acc);
-            if (fout) fout[bd.chiv_off + r] = s;
-        }
-        __syncwarp();
     }
     return 0.5 * warp_sum(acc);
 }
 
 // ---------------------------------------------------------------------------
-// accumulate A += S^T S, g += S^T r, cost += r^T r over `nrows` rows of S = [J | r]
+// normal-equation accumulators in DMMA C-fragment layout (registers)
 // ---------------------------------------------------------------------------
 template <class F>
-__device__ __forceinline__ void accumulate(WarpCtx<F>& c, const double* S, int nrows, double& acc_cost) {
+struct NormalAcc {
     typedef FitLayout<F> Lay;
-    constexpr int NP = Lay::NP, NP1 = Lay::NP1, LDR = Lay::LDR, LDA = Lay::LDA;
-    constexpr int T = NP1 * (NP1 + 1) / 2;
-    for (int e = c.lane; e < T; e += 32) {
-        int a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-        while ((a + 1) * (a + 2) / 2 <= e) ++a;
-        while (a * (a + 1) / 2 > e) --a;
-        const int b = e - a * (a + 1) / 2;           // b <= a <= NP
-        double s0 = 0.0, s1 = 0.0;
-        int i = 0;
-        for (; i + 1 < nrows; i += 2) {
-            s0 = fma(S[i * LDR + a], S[i * LDR + b], s0);
-            s1 = fma(S[(i + 1) * LDR + a], S[(i + 1) * LDR + b], s1);
-        }
-        if (i < nrows) s0 = fma(S[i * LDR + a], S[i * LDR + b], s0);
-        const double s = s0 + s1;
-        if (a < NP) {
-            c.A[a * LDA + b] += s;
-            if (a != b) c.A[b * LDA + a] += s;
-        } else if (b < NP) {
-            c.g[b] += s;
+    double t[Lay::NTRI][2];     // tiles (ta <= tb) of S^T S
+    double g;                   // partial of J^T r for column (lane % 16 or lane) when !DELTA_IN_TILE
+    double cost;                // partial of r^T r when !DELTA_IN_TILE
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int q = 0; q < Lay::NTRI; ++q) { t[q][0] = 0.0; t[q][1] = 0.0; }
+        g = 0.0; cost = 0.0;
+    }
+};
+
+// acc += S^T S over `nrows4` rows (multiple of 4; rows beyond the data are zero) of the row
+// buffer S = [J | r | 0].  A-operand J^T and B-operand J are the same fragment.
+template <class F>
+__device__ __forceinline__ void mma_accumulate(WarpCtx<F>& c, const double* S, int nrows4, NormalAcc<F>& na) {
+    typedef FitLayout<F> Lay;
+    constexpr int NP = Lay::NP, NT = Lay::NT, LDR = Lay::LDR;
+    const int lane = c.lane;
+    const double* base = S + (lane & 3) * LDR + (lane >> 2);
+    for (int s4 = 0; s4 < nrows4; s4 += 4) {
+        double f[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) f[t] = base[s4 * LDR + 8 * t];
+        int q = 0;
+#pragma unroll
+        for (int ta = 0; ta < NT; ++ta)
+#pragma unroll
+            for (int tb = ta; tb < NT; ++tb) { dmma(na.t[q][0], na.t[q][1], f[ta], f[tb]); ++q; }
+    }
+    if (!Lay::DELTA_IN_TILE) {
+        // J^T r by DFMA: lane (a + 16h) sums rows of half h for column a (NP <= 16), else lane a
+        if (NP <= 16) {
+            const int a = lane & 15, h = lane >> 4;
+            if (a < NP) {
+                const int half = nrows4 >> 1;
+                for (int i = h * half; i < (h + 1) * half; ++i) na.g = fma(S[i * LDR + a], S[i * LDR + NP], na.g);
+            }
         } else {
-            acc_cost += s;
+            if (lane < NP)
+                for (int i = 0; i < nrows4; ++i) na.g = fma(S[i * LDR + lane], S[i * LDR + NP], na.g);
+        }
+        for (int i = lane; i < nrows4; i += 32) { const double r = S[i * LDR + NP]; na.cost = fma(r, r, na.cost); }
+    }
+}
+
+// add the register tiles into shared A (J^T J), g (J^T r); returns this lane's share of r^T r
+template <class F>
+__device__ __forceinline__ double flush_normal(WarpCtx<F>& c, NormalAcc<F>& na) {
+    typedef FitLayout<F> Lay;
+    constexpr int NP = Lay::NP, NT = Lay::NT, LDA = Lay::LDA;
+    const int lane = c.lane;
+    double cost = na.cost;
+    int q = 0;
+#pragma unroll
+    for (int ta = 0; ta < NT; ++ta)
+#pragma unroll
+        for (int tb = ta; tb < NT; ++tb) {
+            const int row = 8 * ta + (lane >> 2);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = 8 * tb + 2 * (lane & 3) + e;
+                const double v = na.t[q][e];
+                if (row < NP && col < NP) {
+                    c.A[row * LDA + col] += v;
+                    if (ta != tb) c.A[col * LDA + row] += v;
+                } else if (Lay::DELTA_IN_TILE && col == NP && row < NP) {
+                    c.g[row] += v;
+                } else if (Lay::DELTA_IN_TILE && col == NP && row == NP) {
+                    cost += v;
+                }
+            }
+            ++q;
+        }
+    if (!Lay::DELTA_IN_TILE) {
+        if (NP <= 16) {
+            const double other = __shfl_xor_sync(B200LM_FULL, na.g, 16);
+            if (lane < NP) c.g[lane] += na.g + other;
+        } else if (lane < NP) {
+            c.g[lane] += na.g;
         }
     }
+    __syncwarp();
+    return cost;
 }
 
 template <class F>
@@ -155,10 +249,6 @@ __device__ __forceinline__ void emit_rows(const double* S, int nrows, int slot0,
     }
 }
 
-// ---------------------------------------------------------------------------
-// residual + Jacobian + normal equations at pv: fills c.A (J^T J), c.g (J^T r),
-// returns cost.  Optionally writes the residual vector and J to global memory.
-// ---------------------------------------------------------------------------
 // Householder update of the triangular factor Rt (in c.A) with `nrows` rows of S, columns
 // scaled by c.dsc:  Rt <- R of qr([Rt ; S.diag(dsc)]).  Rows are owned by lanes (i mod 32);
 // S is destroyed.  Used for the final covariance: (J^T J)^-1 = dsc Rt^-1 Rt^-T dsc has a
@@ -208,17 +298,37 @@ __device__ void qr_update(WarpCtx<F>& c, double* S, int nrows) {
     }
 }
 
+// rows of the buffer are finished [J | r]: emit / fold them into the normal equations or the QR factor
+template <class F, int MODE>
+__device__ __forceinline__ void consume_rows(WarpCtx<F>& c, int nrows, int slot0, double* fout, double* Jout,
+                                             NormalAcc<F>& na) {
+    if (fout || Jout) emit_rows<F>(c.R, nrows, slot0, c.lane, fout, Jout);
+    if (MODE == 0) {
+        mma_accumulate<F>(c, c.R, (nrows + 3) & ~3, na);
+    } else {
+        __syncwarp();
+        qr_update<F>(c, c.R, nrows);
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// residual + Jacobian + normal equations at pv: fills c.A (J^T J), c.g (J^T r),
+// returns cost.  Optionally writes the residual vector and J to global memory.
 // MODE 0: normal equations (A = J^T J, g = J^T r).  MODE 1: QR factor of J.diag(dsc) in c.A.
+// ---------------------------------------------------------------------------
 template <class F, int MODE = 0>
 __device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, double* Jout) {
     typedef FitLayout<F> Lay;
-    constexpr int NP = Lay::NP, LDR = Lay::LDR, LDA = Lay::LDA;
+    constexpr int NP = Lay::NP, NT = Lay::NT, LDR = Lay::LDR, LDA = Lay::LDA, NCOL = Lay::NCOL;
     const FitParams& P = c.P;
     const int lane = c.lane;
     for (int e = lane; e < NP * LDA; e += 32) c.A[e] = 0.0;
     if (MODE == 0 && lane < NP) c.g[lane] = 0.0;
     __syncwarp();
     double acc = 0.0;
+    NormalAcc<F> na;
+    na.clear();
     // 1x1 prior rows: J row = w e_j, analytic contribution
     for (int i = lane; i < P.nd_pr; i += 32) {
         const int idx = P.dpr_idx[i];
@@ -238,201 +348,203 @@ __device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, doubl
         }
     }
     __syncwarp();
-    // 1x1 data rows, staged through the row buffer in chunks
-    for (int c0 = 0; c0 < P.nd_fn; c0 += P.rb) {
-        const int nrows = min(P.rb, P.nd_fn - c0);
-        for (int i = lane; i < nrows; i += 32) {
-            const int row = P.dfn_idx[c0 + i];
-            const double w = P.dfn_w[c0 + i];
+    // 1x1 data rows, staged through the row buffer 32 at a time (one row per lane)
+    for (int c0 = 0; c0 < P.nd_fn; c0 += 32) {
+        const int nrows = min(32, P.nd_fn - c0);
+        double* row_ = c.R + lane * LDR;
+        if (lane < nrows) {
+            const int row = P.dfn_idx[c0 + lane];
+            const double w = P.dfn_w[c0 + lane];
             double gr[NP];
             const double f = F::value_grad(P.x + (size_t)row * P.nx, row, pv, gr);
 #pragma unroll
-            for (int j = 0; j < NP; ++j) c.R[i * LDR + j] = w * gr[j];
-            c.R[i * LDR + NP] = w * (f - c.mean[row]);
+            for (int j = 0; j < NP; ++j) row_[j] = w * gr[j];
+            row_[NP] = w * (f - c.mean[row]);
+#pragma unroll
+            for (int j = NP + 1; j < NCOL; ++j) row_[j] = 0.0;
+        } else {
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) row_[j] = 0.0;
         }
         __syncwarp();
-        if (fout || Jout) emit_rows<F>(c.R, nrows, c0, lane, fout, Jout);
-        if (MODE == 0) accumulate<F>(c, c.R, nrows, acc);
-        else { __syncwarp(); qr_update<F>(c, c.R, nrows); }
-        __syncwarp();
+        consume_rows<F, MODE>(c, nrows, c0, fout, Jout, na);
     }
-    // correlated blocks: J_blk = W.[G | delta].  Output rows are owned by lanes (two per lane per
-    // 64-row group) and stay in registers while the input rows [G | delta] stream through the
-    // row buffer in chunks of P.rb rows; the finished rows then pass through the same buffer,
-    // 32 at a time, into the normal equations (or the QR update).
+    // correlated blocks: J_blk = W.[G | delta] on the FP64 tensor path.  The C fragments of a
+    // 64-row output group stay in registers while the input rows stream through the row buffer
+    // 32 at a time; the finished rows then pass through the same buffer into J^T J.
     for (int b = 0; b < P.nblk; ++b) {
         const BlockDesc bd = P.blk[b];
-        const double* wt = c.wt + bd.wt_off;
+        const double* W = c.wt + bd.wt_off;
         for (int g0 = 0; g0 < bd.n_out; g0 += 64) {
+            const int mtiles = min(8, (bd.n_out - g0 + 7) >> 3);
+            double pc[8][NT][2];
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+#pragma unroll
+                for (int t = 0; t < NT; ++t) { pc[m][t][0] = 0.0; pc[m][t][1] = 0.0; }
             const int r0 = g0 + lane, r1 = g0 + lane + 32;
             const bool h0 = r0 < bd.n_out, h1 = r1 < bd.n_out;
-            double a0[NP + 1], a1[NP + 1];
-#pragma unroll
-            for (int j = 0; j <= NP; ++j) { a0[j] = 0.0; a1[j] = 0.0; }
-            for (int k0 = 0; k0 < bd.n_in; k0 += P.rb) {
-                const int nk = min(P.rb, bd.n_in - k0);
-                for (int k = lane; k < nk; k += 32) {
-                    const int idx = P.blk_idx[bd.idx_off + k0 + k];
+            double y0 = 0.0, y1 = 0.0;                 // residual rows when it is not in a tile
+            for (int k0 = 0; k0 < bd.n_in; k0 += 32) {
+                const int nk = min(32, bd.n_in - k0);
+                const int nk4 = (nk + 3) & ~3;
+                double* row_ = c.R + lane * LDR;
+                if (lane < nk) {
+                    const int idx = P.blk_idx[bd.idx_off + k0 + lane];
+                    double dlt;
                     if (idx < P.ny) {
                         double gr[NP];
                         const double f = F::value_grad(P.x + (size_t)idx * P.nx, idx, pv, gr);
 #pragma unroll
-                        for (int j = 0; j < NP; ++j) c.R[k * LDR + j] = gr[j];
-                        c.R[k * LDR + NP] = f - c.mean[idx];
+                        for (int j = 0; j < NP; ++j) row_[j] = gr[j];
+                        dlt = f - c.mean[idx];
                     } else {
                         const int j0 = idx - P.ny;
 #pragma unroll
-                        for (int j = 0; j < NP; ++j) c.R[k * LDR + j] = (j == j0) ? 1.0 : 0.0;
-                        c.R[k * LDR + NP] = pv[j0] - c.mean[idx];
+                        for (int j = 0; j < NP; ++j) row_[j] = (j == j0) ? 1.0 : 0.0;
+                        dlt = pv[j0] - c.mean[idx];
                     }
+                    row_[NP] = dlt;
+#pragma unroll
+                    for (int j = NP + 1; j < NCOL; ++j) row_[j] = 0.0;
+                    if (!Lay::DELTA_IN_TILE) c.dvec[lane] = dlt;
+                } else if (lane < nk4) {
+#pragma unroll
+                    for (int j = 0; j < NCOL; ++j) row_[j] = 0.0;
                 }
                 __syncwarp();
-                const double* wk = wt + (size_t)k0 * bd.ldw;
+                // A fragment: W[g0 + 8m + lane/4][k0 + 4s + lane%4];  B fragment: R[4s + lane%4][8t + lane/4]
+                const double* wa = W + (size_t)(g0 + (lane >> 2)) * bd.ldw + k0 + (lane & 3);
+                const double* rb_ = c.R + (lane & 3) * LDR + (lane >> 2);
 #pragma unroll 2
-                for (int k = 0; k < nk; ++k) {
-                    const double w0 = h0 ? wk[(size_t)k * bd.ldw + r0] : 0.0;
-                    const double w1 = h1 ? wk[(size_t)k * bd.ldw + r1] : 0.0;
+                for (int s4 = 0; s4 < nk4; s4 += 4) {
+                    double bf[NT];
 #pragma unroll
-                    for (int j = 0; j <= NP; ++j) {
-                        const double v = c.R[k * LDR + j];
-                        a0[j] = fma(w0, v, a0[j]);
-                        a1[j] = fma(w1, v, a1[j]);
+                    for (int t = 0; t < NT; ++t) bf[t] = rb_[s4 * LDR + 8 * t];
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        if (m < mtiles) {
+                            const double af = wa[(size_t)(8 * m) * bd.ldw + s4];
+#pragma unroll
+                            for (int t = 0; t < NT; ++t) dmma(pc[m][t][0], pc[m][t][1], af, bf[t]);
+                        }
                     }
                 }
+                if (!Lay::DELTA_IN_TILE) matvec2(W + k0, bd.ldw, r0, r1, h0, h1, c.dvec, nk, lane, y0, y1);
                 __syncwarp();                      // everyone has finished reading this chunk
             }
-            // rows g0 .. g0+31
-            if (h0) {
+            // finished rows: two passes of (up to) 32 rows = 4 m-tiles each
 #pragma unroll
-                for (int j = 0; j <= NP; ++j) c.R[lane * LDR + j] = a0[j];
-            }
-            __syncwarp();
-            int nrows = min(32, bd.n_out - g0);
-            if (fout || Jout) emit_rows<F>(c.R, nrows, bd.chiv_off + g0, lane, fout, Jout);
-            if (MODE == 0) accumulate<F>(c, c.R, nrows, acc);
-            else { __syncwarp(); qr_update<F>(c, c.R, nrows); }
-            __syncwarp();
-            // rows g0+32 .. g0+63
-            nrows = min(32, bd.n_out - g0 - 32);
-            if (nrows > 0) {
-                if (h1) {
+            for (int half = 0; half < 2; ++half) {
+                const int nrows = min(32, bd.n_out - g0 - 32 * half);
+                if (nrows > 0) {
+                    const int mt_here = min(4, mtiles - 4 * half);
 #pragma unroll
-                    for (int j = 0; j <= NP; ++j) c.R[lane * LDR + j] = a1[j];
+                    for (int m4 = 0; m4 < 4; ++m4) {
+                        if (m4 < mt_here) {
+                            double* dst = c.R + (8 * m4 + (lane >> 2)) * LDR + 2 * (lane & 3);
+#pragma unroll
+                            for (int t = 0; t < NT; ++t) {
+                                dst[8 * t] = pc[4 * half + m4][t][0];
+                                dst[8 * t + 1] = pc[4 * half + m4][t][1];
+                            }
+                        }
+                    }
+                    if (!Lay::DELTA_IN_TILE) {
+                        const bool hh = half == 0 ? h0 : h1;
+                        if (lane < 8 * mt_here) c.R[lane * LDR + NP] = hh ? (half == 0 ? y0 : y1) : 0.0;
+                    }
+                    __syncwarp();
+                    consume_rows<F, MODE>(c, nrows, bd.chiv_off + g0 + 32 * half, fout, Jout, na);
                 }
-                __syncwarp();
-                if (fout || Jout) emit_rows<F>(c.R, nrows, bd.chiv_off + g0 + 32, lane, fout, Jout);
-                if (MODE == 0) accumulate<F>(c, c.R, nrows, acc);
-                else { __syncwarp(); qr_update<F>(c, c.R, nrows); }
-                __syncwarp();
             }
         }
     }
+    if (MODE == 0) acc += flush_normal<F>(c, na);
     return 0.5 * warp_sum(acc);
 }
 
 // ---------------------------------------------------------------------------
 // small dense kernels on the warp: lane i owns row i, everything in registers
 // ---------------------------------------------------------------------------
-// Factor of the scaled, shifted normal matrix held in registers: lane i keeps row i of L in
-// l[] (entries k <= i), column i of L in u[] (entries k >= i) and 1/L_ii in inv.
-template <int NP>
-struct CholReg {
-    double l[NP];
-    double u[NP];
-    double inv;
-};
-
-// L L^T = d_i A_ij d_j + alpha delta_ij, right-looking, fully unrolled: the column of the
-// current step is broadcast with warp shuffles.  false if not numerically positive definite.
+// One Cholesky factorisation + the solves every caller needs, as ONE out-of-line function (one
+// copy of the unrolled code per functor).  Lane i keeps row i of L in registers; each finished
+// column is also written to shared memory as a row of L^T (LT[j][i] = L[i][j]), from where the
+// trailing update reads it back by broadcast and the backward substitution reads its columns.
+//     L L^T = d_i A_ij d_j + alpha delta_ij
+//     p = -(L L^T)^-1 gh ,  res[0] = |p| ,  res[1] = |L^-1 p|^2 ,  res[2] = min_j pivot_j / diag_j
+// Returns false if the matrix is not numerically positive definite.  LT (NP x LDA) and the
+// reciprocal diagonal idg stay valid in shared memory for the covariance routine.
 template <int NP, int LDA>
-__device__ __forceinline__ bool chol_factor(const double* A, const double* dsc, int lane, double alpha,
-                                            CholReg<NP>& f, double& minr) {
+__device__ __noinline__ bool factor_solve(const double* A, const double* dsc, double* LT, double* idg,
+                                          int lane, double alpha, double gh, bool want_ratio,
+                                          double* p_out, double* res) {
     const int i = lane;
     const bool act = i < NP;
+    double l[NP];
     const double di = act ? dsc[i] : 0.0;
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
         double v = act ? A[i * LDA + k] * di * dsc[k] : 0.0;
         if (k == i) v = act ? v + alpha : 1.0;
-        f.l[k] = v;
-        f.u[k] = 0.0;
+        l[k] = v;
     }
     double mdiag = 1.0;                 // original diagonal entry of this lane's row
 #pragma unroll
-    for (int k = 0; k < NP; ++k) if (k == i) mdiag = f.l[k];
-    minr = 1.0;
+    for (int k = 0; k < NP; ++k) if (k == i) mdiag = l[k];
+    double myinv = 1.0, mypiv = 1.0;
     bool ok = true;
-    f.inv = 1.0;
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-        const double piv = __shfl_sync(B200LM_FULL, f.l[j], j);
-        const double mjj = __shfl_sync(B200LM_FULL, mdiag, j);
-        // no early exit: a `break` would keep the loop from unrolling
-        if (!(piv > 8.0 * NP * 2.220446049250313e-16 * mjj) || !isfinite(piv)) ok = false;
-        minr = fmin(minr, piv / mjj);
+        const double piv = __shfl_sync(B200LM_FULL, l[j], j);
         const double inv = rsqrt(piv);
-        if (i == j) f.inv = inv;
-        const double lij = (i == j) ? piv * inv : f.l[j] * inv;      // L[i][j]
-        f.l[j] = lij;
-        if (i == j) f.u[j] = lij;
-#pragma unroll
-        for (int k = j + 1; k < NP; ++k) {
-            const double lkj = __shfl_sync(B200LM_FULL, lij, k);      // L[k][j]
-            f.l[k] = fma(-lij, lkj, f.l[k]);                          // row i, column k (used for k <= i)
-            if (i == j) f.u[k] = lkj;                                 // column j of L kept by lane j
+        const double lij = (i == j) ? piv * inv : l[j] * inv;        // L[i][j]
+        if (i == j) {
+            myinv = inv; mypiv = piv;
+            if (!(piv > 8.0 * NP * 2.220446049250313e-16 * mdiag) || !isfinite(piv)) ok = false;
         }
-    }
-    return ok;
-}
-// y = L^-1 b (lane i holds b_i, returns y_i)
-template <int NP>
-__device__ __forceinline__ double solve_lower(const CholReg<NP>& f, int lane, double b) {
+        l[j] = lij;
+        if (act) LT[j * LDA + i] = lij;
+        __syncwarp();
 #pragma unroll
-    for (int j = 0; j < NP; ++j) {
-        const double yj = __shfl_sync(B200LM_FULL, b * f.inv, j);
-        if (lane == j) b = yj;
-        else if (lane > j) b = fma(-f.l[j], yj, b);
+        for (int k = j + 1; k < NP; ++k) l[k] = fma(-lij, LT[j * LDA + k], l[k]);   // row i, col k (k <= i used)
     }
-    return b;
-}
-// x = L^-T b
-template <int NP>
-__device__ __forceinline__ double solve_upper(const CholReg<NP>& f, int lane, double b) {
-#pragma unroll
-    for (int j = NP - 1; j >= 0; --j) {
-        const double xj = __shfl_sync(B200LM_FULL, b * f.inv, j);
-        if (lane == j) b = xj;
-        else if (lane < j) b = fma(-f.u[j], xj, b);
-    }
-    return b;
-}
-
-// One factorisation + the solves every caller needs, as ONE out-of-line function (the
-// unrolled factor is ~1.5k instructions; five inlined copies would thrash the i-cache and
-// the register allocator).  With the lane-distributed scaled gradient gh:
-//     p = -(Ah + alpha I)^-1 gh ,  res[0] = |p| ,  res[1] = |L^-1 p|^2 ,  res[2] = min pivot ratio
-// Optionally leaves L (rows) and 1/L_ii in shared memory for the covariance routine.
-template <int NP, int LDA>
-__device__ __noinline__ bool factor_solve(const double* A, const double* dsc, double* Lsm, double* idg,
-                                          int lane, double alpha, double gh, bool store,
-                                          double* p_out, double* res) {
-    CholReg<NP> f;
-    double minr;
-    const bool ok = chol_factor<NP, LDA>(A, dsc, lane, alpha, f, minr);
-    const bool act = lane < NP;
-    double p = 0.0, pn = 0.0, w2 = 0.0;
+    ok = __all_sync(B200LM_FULL, ok);
+    if (act) idg[i] = myinv;
+    double p = 0.0, pn = 0.0, w2 = 0.0, minr = 0.0;
     if (ok) {
-        p = solve_upper<NP>(f, lane, solve_lower<NP>(f, lane, act ? -gh : 0.0));
-        pn = sqrt(warp_sum(act ? p * p : 0.0));
-        const double w = solve_lower<NP>(f, lane, act ? p : 0.0);
-        w2 = warp_sum(act ? w * w : 0.0);
-        if (store) {
-            if (act) {
+        // y = L^-1 (-gh)
+        double b = act ? -gh : 0.0;
 #pragma unroll
-                for (int k = 0; k < NP; ++k) Lsm[lane * LDA + k] = (k <= lane) ? f.l[k] : 0.0;
-                idg[lane] = f.inv;
-            }
-            __syncwarp();
+        for (int j = 0; j < NP; ++j) {
+            const double yj = __shfl_sync(B200LM_FULL, b * myinv, j);
+            if (i == j) b = yj;
+            else if (i > j) b = fma(-l[j], yj, b);
+        }
+        // p = L^-T y : lane i needs column i of L^T, i.e. LT[j][i] ... stored as LT[j*LDA + i]
+#pragma unroll
+        for (int j = NP - 1; j >= 0; --j) {
+            const double xj = __shfl_sync(B200LM_FULL, b * myinv, j);
+            if (i == j) b = xj;
+            else if (i < j && act) b = fma(-LT[i * LDA + j], xj, b);
+        }
+        p = act ? b : 0.0;
+        pn = sqrt(warp_sum(p * p));
+        // w = L^-1 p
+        double w = p;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const double yj = __shfl_sync(B200LM_FULL, w * myinv, j);
+            if (i == j) w = yj;
+            else if (i > j) w = fma(-l[j], yj, w);
+        }
+        w2 = warp_sum(act ? w * w : 0.0);
+        if (want_ratio) {
+            double r = act ? mypiv / mdiag : 1.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r = fmin(r, __shfl_xor_sync(B200LM_FULL, r, o));
+            minr = r;
         }
     }
     *p_out = p;
@@ -477,19 +589,17 @@ __device__ double solve_tr(WarpCtx<F>& c, double gh, double Delta, double& alpha
     }
     if (!full_rank && alpha == 0.0)
         alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
-    bool have_p = false, converged = false;
-    // iterations 0..9: Newton on the secular equation; iteration 10: the step at the final alpha
-    for (int it = 0; it <= 10; ++it) {
-        const bool last = converged || it == 10;
-        if (!last && (alpha < alpha_lower || alpha > alpha_upper))
+    bool have_p = false;
+    // Newton iteration on the secular equation.  Unlike the reference's solver the step of the
+    // last iterate (|phi| < 0.01 Delta) is kept instead of being recomputed at the updated
+    // alpha: it is rescaled to the trust-region boundary below anyway, and one factorisation
+    // per trial is saved.
+    for (int it = 0; it < 10; ++it) {
+        if (alpha < alpha_lower || alpha > alpha_upper)
             alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
         ++nfac;
         double pt;
         const bool ok = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, alpha, gh, false, &pt, res);
-        if (last) {
-            if (ok) { p = pt; have_p = true; }
-            break;
-        }
         if (!ok) {
             alpha_lower = fmax(alpha_lower, alpha);
             alpha = fmax(2.0 * alpha, 0.001 * alpha_upper);
@@ -505,7 +615,7 @@ __device__ double solve_tr(WarpCtx<F>& c, double gh, double Delta, double& alpha
         const double ratio = phi / phi_prime;
         alpha_lower = fmax(alpha_lower, alpha - ratio);
         alpha -= (phi + Delta) * ratio / Delta;
-        if (fabs(phi) < 0.01 * Delta) converged = true;
+        if (fabs(phi) < 0.01 * Delta) break;
     }
     if (!have_p) p = act ? -gh : 0.0;             // steepest descent fallback
     pn = sqrt(warp_sum(act ? p * p : 0.0));
@@ -513,8 +623,9 @@ __device__ double solve_tr(WarpCtx<F>& c, double gh, double Delta, double& alpha
     return p;
 }
 
-// covariance (J^T J)^-1 = d (L L^T)^-1 d from the factor of the scaled matrix at alpha=0.
-// Uses c.A as scratch for L^-1 (column a computed by lane a).  Returns log det(J^T J).
+// covariance (J^T J)^-1 = d (L L^T)^-1 d from the factor of the scaled matrix at alpha=0
+// (c.L holds L^T: c.L[k*LDA + j] = L[j][k]).  Uses c.A as scratch for L^-1 (column a computed by
+// lane a).  Returns log det(J^T J).
 template <class F>
 __device__ double covariance_from_chol(WarpCtx<F>& c, double* cov_out) {
     typedef FitLayout<F> Lay;
@@ -529,7 +640,7 @@ __device__ double covariance_from_chol(WarpCtx<F>& c, double* cov_out) {
         for (int j = 0; j < NP; ++j) {
             double s = (j == a) ? 1.0 : 0.0;
             if (j < a) { c.A[j * LDA + a] = 0.0; continue; }
-            for (int k = a; k < j; ++k) s = fma(-c.L[j * LDA + k], c.A[k * LDA + a], s);
+            for (int k = a; k < j; ++k) s = fma(-c.L[k * LDA + j], c.A[k * LDA + a], s);
             c.A[j * LDA + a] = s * c.idg[j];
         }
     }
@@ -595,7 +706,8 @@ __device__ __forceinline__ void setup_ctx(WarpCtx<F>& c, double* smem, const Fit
     }
     double* base = smem + wt_region + (size_t)warp * Lay::per_warp_doubles(P.rb);
     c.R = base;
-    c.A = c.R + (size_t)P.rb * Lay::LDR;
+    c.dvec = c.R + (size_t)P.rb * Lay::LDR;
+    c.A = c.dvec + P.rb;
     c.L = c.A + Lay::NP * Lay::LDA;
     c.p = c.L + Lay::NP * Lay::LDA;
     c.pn = c.p + Lay::NP;

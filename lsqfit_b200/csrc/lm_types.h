@@ -9,9 +9,9 @@ namespace b200lm {
 struct BlockDesc {
     int n_in;        // number of y(+)prior entries in the block
     int n_out;       // number of residuals it produces (rows of W_k; < n_in if svdcut<0 dropped modes)
-    int ldw;         // leading dimension of the transposed weight matrix (>= n_out)
+    int ldw;         // row stride of the zero-padded, row-major weight matrix (== 4 mod 16, >= n_in)
     int idx_off;     // offset into blk_idx[]  (n_in entries: index into y(+)prior)
-    int wt_off;      // offset into blk_wt[]   (Wt[k*ldw + r] = W[r][k], n_in x ldw doubles)
+    int wt_off;      // offset into blk_wt[]   (W[r*ldw + k], n_out rounded up to 8 rows)
     int chiv_off;    // first residual slot of this block in chiv
 };
 

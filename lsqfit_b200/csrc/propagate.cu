@@ -105,7 +105,7 @@ extern "C" int b200lm_propagate(b200lm_handle h, int B, const double* d_x, const
         for (auto& b : h->h_blk)
             for (int r = 0; r < b.n_out; ++r)
                 for (int j = 0; j < b.n_in; ++j)
-                    W[(size_t)(b.chiv_off + r) * N + h->h_blk_idx[b.idx_off + j]] = wt[b.wt_off + (size_t)j * b.ldw + r];
+                    W[(size_t)(b.chiv_off + r) * N + h->h_blk_idx[b.idx_off + j]] = wt[b.wt_off + (size_t)r * b.ldw + j];
         e = cudaMalloc((void**)&h->d_wfull, W.size() * sizeof(double));
         if (e == cudaSuccess) e = cudaMemcpy(h->d_wfull, W.data(), W.size() * sizeof(double), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return cuda_fail(h, e, "upload dense whitening operator");
@@ -124,8 +124,9 @@ extern "C" int b200lm_propagate(b200lm_handle h, int B, const double* d_x, const
     double* dM = dJ + nJ;
     double* dT = dM + nM;
     // J at the solution.  The residual/Jacobian kernel needs a mean vector only for the
-    // residuals, which are not used here: pass x itself as a dummy mean when shapes allow,
-    // otherwise the (unused) D buffer, which has at least N entries per fit.
+    // residuals, which are not used here: the zeroed head of the D buffer serves as a dummy.
+    e = cudaMemsetAsync(d_D, 0, (size_t)N * sizeof(double), s);
+    if (e != cudaSuccess) return cuda_fail(h, e, "memset");
     int rc = b200lm_residual_jacobian(h, B, d_x, np, d_D, 0, nullptr, dJ, nullptr, stream);
     if (rc) return rc;
     // M = cov . J^T      (np x nchiv)
