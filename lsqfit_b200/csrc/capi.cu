@@ -31,6 +31,7 @@ void fill_params(b200lm_handle_s* h, FitParams& P) {
     P.nblk = h->nblk; P.blk = h->d_blk; P.blk_idx = h->d_blk_idx; P.blk_wt = h->d_blk_wt;
     P.wt_total = h->wt_total;
     P.rb = h->rb;
+    P.nblkrows = h->nchiv - h->nd_fn - h->nd_pr;
     P.counter = h->d_counter;
     P.stats = h->d_stats;
 }
@@ -200,7 +201,7 @@ int b200lm_set_weights(b200lm_handle h, int ndiag, const int* diag_idx, const do
     for (int i = 0; i < N; ++i)
         if (!seen[i]) return set_error(h, B200LM_EINVAL, "every y(+)prior entry must appear in exactly one block");
     // does at least one warp fit?
-    if (h->fe->per_warp_bytes(rb) > h->smem_budget)
+    if (h->fe->per_warp_bytes(rb) + (size_t)(chiv_off - ndiag + 2) * sizeof(double) > h->smem_budget)
         return set_error(h, B200LM_ESIZE, "correlated block too large for the per-warp shared-memory plan");
     h->nd_fn = (int)fn_idx.size(); h->nd_pr = (int)pr_idx.size();
     CUDA_TRY(h, upload(&h->d_dfn_idx, fn_idx.data(), fn_idx.size()), "upload weights");

@@ -84,19 +84,25 @@ template <int N> __device__ __forceinline__ Dual<N> operator*(const Dual<N>& a, 
     return r;
 }
 template <int N> __device__ __forceinline__ Dual<N> operator*(double b, const Dual<N>& a) { return a * b; }
+// NOTE: every .v below is computed exactly like the plain-double expression would be, so that
+// Body::eval<double> and Body::eval<Dual<N>>().v agree bit for bit.
 template <int N> __device__ __forceinline__ Dual<N> operator/(const Dual<N>& a, const Dual<N>& b) {
     const double ib = 1.0 / b.v;
-    Dual<N> r; r.v = a.v * ib;
+    Dual<N> r; r.v = a.v / b.v;
 #pragma unroll
     for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
     return r;
 }
 template <int N> __device__ __forceinline__ Dual<N> operator/(const Dual<N>& a, double b) {
-    return a * (1.0 / b);
+    const double ib = 1.0 / b;
+    Dual<N> r; r.v = a.v / b;
+#pragma unroll
+    for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * ib;
+    return r;
 }
 template <int N> __device__ __forceinline__ Dual<N> operator/(double a, const Dual<N>& b) {
     const double ib = 1.0 / b.v;
-    const double v = a * ib;
+    const double v = a / b.v;
     return chain(b, v, -v * ib);
 }
 
@@ -110,18 +116,18 @@ template <int N> __device__ __forceinline__ Dual<N> sqrt(const Dual<N>& a) {
     const double s = ::sqrt(a.v); return chain(a, s, 0.5 / s);
 }
 template <int N> __device__ __forceinline__ Dual<N> sin(const Dual<N>& a) {
-    double s, c; ::sincos(a.v, &s, &c); return chain(a, s, c);
+    return chain(a, ::sin(a.v), ::cos(a.v));
 }
 template <int N> __device__ __forceinline__ Dual<N> cos(const Dual<N>& a) {
-    double s, c; ::sincos(a.v, &s, &c); return chain(a, c, -s);
+    return chain(a, ::cos(a.v), -::sin(a.v));
 }
 template <int N> __device__ __forceinline__ Dual<N> atan(const Dual<N>& a) {
     return chain(a, ::atan(a.v), 1.0 / (1.0 + a.v * a.v));
 }
 // a ** c, constant exponent
 template <int N> __device__ __forceinline__ Dual<N> pow(const Dual<N>& a, double c) {
-    const double pm1 = ::pow(a.v, c - 1.0);
-    return chain(a, pm1 * a.v, c * pm1);
+    const double v = ::pow(a.v, c);
+    return chain(a, v, a.v != 0.0 ? c * v / a.v : c * ::pow(a.v, c - 1.0));
 }
 // a ** b, both dual (a > 0)
 template <int N> __device__ __forceinline__ Dual<N> pow(const Dual<N>& a, const Dual<N>& b) {

@@ -5,9 +5,13 @@
 //     static constexpr int NP;   number of fit parameters (compile time)
 //     static constexpr int NX;   number of x columns the row reads
 //     double value     (const double* xrow, int row, const double* p)
-//     double value_grad(const double* xrow, int row, const double* p, double* g /*[NP]*/)
-// x is row-major [ny][NX] in global memory; p points to the warp's parameter
-// vector in shared memory.
+//     double value_grad(const double* xrow, int row, const double* p, double w, double* out /*[NP]*/)
+//            returns f and writes out[j] = w * df/dp_j (straight into the warp's row buffer)
+// x is row-major [ny][NX] in global memory; p points to the warp's parameter vector in shared
+// memory.  value() and value_grad() return bit-identical f (same operation order), so that
+// results do not depend on which of the two evaluated the final residuals.  Loops over
+// exponentials / powers are deliberately NOT unrolled: the fit kernel is instruction-fetch
+// bound and a double-precision exp is ~50 instructions.
 //
 // Reference definitions (paths relative to the reference tree):
 //   multiexp       examples/y-vs-x.py:58-61, examples/y-noerr.py:70-73
@@ -47,13 +51,13 @@ struct ADFunctor {
         return Body::template eval<double>(x, q);
     }
     __device__ __forceinline__ static double value_grad(const double* __restrict__ x, int,
-                                                        const double* p, double* g) {
+                                                        const double* p, double w, double* g) {
         Dual<NP> q[NP];
 #pragma unroll
         for (int j = 0; j < NP; ++j) q[j] = Dual<NP>::variable(p[j], j);
         const Dual<NP> r = Body::template eval<Dual<NP>>(x, q);
 #pragma unroll
-        for (int j = 0; j < NP; ++j) g[j] = r.d[j];
+        for (int j = 0; j < NP; ++j) g[j] = w * r.d[j];
         return r.v;
     }
 };
@@ -69,21 +73,22 @@ struct MultiExp {
     __device__ __forceinline__ static double value(const double* __restrict__ x, int, const double* p) {
         const double t = x[0];
         double f = 0.0;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < K; ++k) f = fma(p[k], ::exp(-p[K + k] * t), f);
         return f;
     }
     __device__ __forceinline__ static double value_grad(const double* __restrict__ x, int,
-                                                        const double* p, double* g) {
+                                                        const double* p, double w, double* g) {
         const double t = x[0];
+        const double wt = -w * t;
         double f = 0.0;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < K; ++k) {
             const double e = ::exp(-p[K + k] * t);
-            const double ae = p[k] * e;
-            g[k] = e;
-            g[K + k] = -t * ae;
-            f += ae;
+            const double a = p[k];
+            g[k] = w * e;
+            g[K + k] = wt * (a * e);
+            f = fma(a, e, f);
         }
         return f;
     }
@@ -97,27 +102,28 @@ struct MultiExpDE {
     __device__ __forceinline__ static double value(const double* __restrict__ x, int, const double* p) {
         const double t = x[0];
         double f = 0.0, E = 0.0;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < K; ++k) { E += p[K + k]; f = fma(p[k], ::exp(-E * t), f); }
         return f;
     }
     __device__ __forceinline__ static double value_grad(const double* __restrict__ x, int,
-                                                        const double* p, double* g) {
+                                                        const double* p, double w, double* g) {
         const double t = x[0];
+        const double wt = -w * t;
         double f = 0.0, E = 0.0;
-        double ae[K];
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < K; ++k) {
             E += p[K + k];
             const double e = ::exp(-E * t);
-            ae[k] = p[k] * e;
-            g[k] = e;
-            f += ae[k];
+            const double a = p[k];
+            g[k] = w * e;
+            g[K + k] = a * e;                 // a_k e_k for now
+            f = fma(a, e, f);
         }
         // df/d(dE_j) = -t sum_{k>=j} a_k e_k
         double tail = 0.0;
-#pragma unroll
-        for (int k = K - 1; k >= 0; --k) { tail += ae[k]; g[K + k] = -t * tail; }
+#pragma unroll 1
+        for (int k = K - 1; k >= 0; --k) { tail += g[K + k]; g[K + k] = wt * tail; }
         return f;
     }
 };
@@ -129,17 +135,17 @@ struct Poly {
     static constexpr int NX = 1;
     __device__ __forceinline__ static double value(const double* __restrict__ x, int, const double* p) {
         const double t = x[0];
-        double f = p[NP - 1];
-#pragma unroll
-        for (int n = NP - 2; n >= 0; --n) f = fma(f, t, p[n]);
+        double tn = 1.0, f = 0.0;
+#pragma unroll 1
+        for (int n = 0; n < NP; ++n) { f = fma(p[n], tn, f); tn *= t; }
         return f;
     }
     __device__ __forceinline__ static double value_grad(const double* __restrict__ x, int,
-                                                        const double* p, double* g) {
+                                                        const double* p, double w, double* g) {
         const double t = x[0];
         double tn = 1.0, f = 0.0;
-#pragma unroll
-        for (int n = 0; n < NP; ++n) { g[n] = tn; f = fma(p[n], tn, f); tn *= t; }
+#pragma unroll 1
+        for (int n = 0; n < NP; ++n) { g[n] = w * tn; f = fma(p[n], tn, f); tn *= t; }
         return f;
     }
 };
@@ -153,10 +159,11 @@ struct ExpPoly {
         return ::exp(-Poly<NP>::value(x, r, p));
     }
     __device__ __forceinline__ static double value_grad(const double* __restrict__ x, int r,
-                                                        const double* p, double* g) {
-        const double f = ::exp(-Poly<NP>::value_grad(x, r, p, g));
-#pragma unroll
-        for (int n = 0; n < NP; ++n) g[n] *= -f;
+                                                        const double* p, double w, double* g) {
+        const double f = ::exp(-Poly<NP>::value_grad(x, r, p, 1.0, g));
+        const double wf = -w * f;
+#pragma unroll 1
+        for (int n = 0; n < NP; ++n) g[n] *= wf;
         return f;
     }
 };
@@ -174,17 +181,15 @@ struct XerrLogistic {
         return body<double>(p[0], p[1], p[2], p[3], p[4 + row]);
     }
     __device__ __forceinline__ static double value_grad(const double* __restrict__, int row,
-                                                        const double* p, double* g) {
+                                                        const double* p, double w, double* g) {
         typedef Dual<5> D5;
         const D5 r = body<D5>(D5::variable(p[0], 0), D5::variable(p[1], 1), D5::variable(p[2], 2),
                               D5::variable(p[3], 3), D5::variable(p[4 + row], 4));
+#pragma unroll 1
+        for (int j = 4; j < NP; ++j) g[j] = 0.0;
 #pragma unroll
-        for (int j = 0; j < NP; ++j) g[j] = 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) g[j] = r.d[j];
-        // runtime index: written through a loop so g[] stays in registers
-#pragma unroll
-        for (int j = 0; j < NY; ++j) if (j == row) g[4 + j] = r.d[4];
+        for (int j = 0; j < 4; ++j) g[j] = w * r.d[j];
+        g[4 + row] = w * r.d[4];
         return r.v;
     }
 };

@@ -66,6 +66,10 @@ struct FitLayout {
         int n = rb * LDR + rb + 2 * NP * LDA + NVEC * NP;  // R | dvec | A | L | vectors
         return (n + 1) & ~1;
     }
+    // + rvec: whitened residuals of the correlated blocks, kept from the trial evaluation
+    __host__ __device__ static int per_warp_doubles(int rb, int nblkrows) {
+        return (per_warp_doubles(rb) + nblkrows + 1) & ~1;
+    }
 };
 
 template <class F>
@@ -74,7 +78,7 @@ struct WarpCtx {
     const FitParams& P;
     const double* wt;       // whitening matrices (shared or global)
     const double* mean;     // this fit's y(+)prior means
-    double *R, *dvec, *A, *L, *p, *pn, *g, *sinv, *dsc, *idg;
+    double *R, *dvec, *rvec, *A, *L, *p, *pn, *g, *sinv, *dsc, *idg;
     int lane;
     __device__ WarpCtx(const FitParams& P_) : P(P_) {}
 };
@@ -103,7 +107,7 @@ __device__ __forceinline__ void matvec2(const double* W, int ldk, int r0, int r1
 // residual only: returns cost = 1/2 sum r^2 (same value in every lane)
 // ---------------------------------------------------------------------------
 template <class F>
-__device__ double eval_cost(WarpCtx<F>& c, const double* pv, double* fout) {
+__device__ __noinline__ double eval_cost(WarpCtx<F>& c, const double* pv, double* fout) {
     const FitParams& P = c.P;
     const int lane = c.lane;
     double acc = 0.0;
@@ -138,8 +142,8 @@ __device__ double eval_cost(WarpCtx<F>& c, const double* pv, double* fout) {
                 matvec2(W + k0, bd.ldw, r0, r1, h0, h1, c.dvec, nk, lane, y0, y1);
                 __syncwarp();
             }
-            if (h0) { acc = fma(y0, y0, acc); if (fout) fout[bd.chiv_off + r0] = y0; }
-            if (h1) { acc = fma(y1, y1, acc); if (fout) fout[bd.chiv_off + r1] = y1; }
+            if (h0) { acc = fma(y0, y0, acc); c.rvec[bd.chiv_off - P.nd_fn - P.nd_pr + r0] = y0; if (fout) fout[bd.chiv_off + r0] = y0; }
+            if (h1) { acc = fma(y1, y1, acc); c.rvec[bd.chiv_off - P.nd_fn - P.nd_pr + r1] = y1; if (fout) fout[bd.chiv_off + r1] = y1; }
         }
     }
     return 0.5 * warp_sum(acc);
@@ -318,7 +322,8 @@ __device__ __forceinline__ void consume_rows(WarpCtx<F>& c, int nrows, int slot0
 // MODE 0: normal equations (A = J^T J, g = J^T r).  MODE 1: QR factor of J.diag(dsc) in c.A.
 // ---------------------------------------------------------------------------
 template <class F, int MODE = 0>
-__device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, double* Jout) {
+__device__ __noinline__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, double* Jout,
+                                         bool reuse_r = false) {
     typedef FitLayout<F> Lay;
     constexpr int NP = Lay::NP, NT = Lay::NT, LDR = Lay::LDR, LDA = Lay::LDA, NCOL = Lay::NCOL;
     const FitParams& P = c.P;
@@ -355,10 +360,7 @@ __device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, doubl
         if (lane < nrows) {
             const int row = P.dfn_idx[c0 + lane];
             const double w = P.dfn_w[c0 + lane];
-            double gr[NP];
-            const double f = F::value_grad(P.x + (size_t)row * P.nx, row, pv, gr);
-#pragma unroll
-            for (int j = 0; j < NP; ++j) row_[j] = w * gr[j];
+            const double f = F::value_grad(P.x + (size_t)row * P.nx, row, pv, w, row_);
             row_[NP] = w * (f - c.mean[row]);
 #pragma unroll
             for (int j = NP + 1; j < NCOL; ++j) row_[j] = 0.0;
@@ -385,6 +387,12 @@ __device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, doubl
             const int r0 = g0 + lane, r1 = g0 + lane + 32;
             const bool h0 = r0 < bd.n_out, h1 = r1 < bd.n_out;
             double y0 = 0.0, y1 = 0.0;                 // residual rows when it is not in a tile
+            const bool do_mv = !Lay::DELTA_IN_TILE && !reuse_r;
+            if (!Lay::DELTA_IN_TILE && reuse_r) {
+                const double* rv = c.rvec + (bd.chiv_off - P.nd_fn - P.nd_pr);
+                if (h0) y0 = rv[r0];
+                if (h1) y1 = rv[r1];
+            }
             for (int k0 = 0; k0 < bd.n_in; k0 += 32) {
                 const int nk = min(32, bd.n_in - k0);
                 const int nk4 = (nk + 3) & ~3;
@@ -393,10 +401,7 @@ __device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, doubl
                     const int idx = P.blk_idx[bd.idx_off + k0 + lane];
                     double dlt;
                     if (idx < P.ny) {
-                        double gr[NP];
-                        const double f = F::value_grad(P.x + (size_t)idx * P.nx, idx, pv, gr);
-#pragma unroll
-                        for (int j = 0; j < NP; ++j) row_[j] = gr[j];
+                        const double f = F::value_grad(P.x + (size_t)idx * P.nx, idx, pv, 1.0, row_);
                         dlt = f - c.mean[idx];
                     } else {
                         const int j0 = idx - P.ny;
@@ -414,8 +419,9 @@ __device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, doubl
                 }
                 __syncwarp();
                 // A fragment: W[g0 + 8m + lane/4][k0 + 4s + lane%4];  B fragment: R[4s + lane%4][8t + lane/4]
-                const double* wa = W + (size_t)(g0 + (lane >> 2)) * bd.ldw + k0 + (lane & 3);
+                const double* wa = W + (g0 + (lane >> 2)) * bd.ldw + k0 + (lane & 3);
                 const double* rb_ = c.R + (lane & 3) * LDR + (lane >> 2);
+                const int ldw8 = 8 * bd.ldw;
 #pragma unroll 2
                 for (int s4 = 0; s4 < nk4; s4 += 4) {
                     double bf[NT];
@@ -424,39 +430,43 @@ __device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, doubl
 #pragma unroll
                     for (int m = 0; m < 8; ++m) {
                         if (m < mtiles) {
-                            const double af = wa[(size_t)(8 * m) * bd.ldw + s4];
+                            const double af = wa[m * ldw8 + s4];
 #pragma unroll
                             for (int t = 0; t < NT; ++t) dmma(pc[m][t][0], pc[m][t][1], af, bf[t]);
                         }
                     }
                 }
-                if (!Lay::DELTA_IN_TILE) matvec2(W + k0, bd.ldw, r0, r1, h0, h1, c.dvec, nk, lane, y0, y1);
+                if (do_mv) matvec2(W + k0, bd.ldw, r0, r1, h0, h1, c.dvec, nk, lane, y0, y1);
                 __syncwarp();                      // everyone has finished reading this chunk
             }
-            // finished rows: two passes of (up to) 32 rows = 4 m-tiles each
-#pragma unroll
+            // finished rows: two passes of (up to) 32 rows = 4 m-tiles each.  The loop is rolled
+            // (code size); the second pass first moves tiles 4..7 down into registers 0..3.
+#pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 const int nrows = min(32, bd.n_out - g0 - 32 * half);
-                if (nrows > 0) {
-                    const int mt_here = min(4, mtiles - 4 * half);
+                if (nrows <= 0) break;
+                const int mt_here = min(4, mtiles - 4 * half);
 #pragma unroll
-                    for (int m4 = 0; m4 < 4; ++m4) {
-                        if (m4 < mt_here) {
-                            double* dst = c.R + (8 * m4 + (lane >> 2)) * LDR + 2 * (lane & 3);
+                for (int m4 = 0; m4 < 4; ++m4) {
+                    if (m4 < mt_here) {
+                        double* dst = c.R + (8 * m4 + (lane >> 2)) * LDR + 2 * (lane & 3);
 #pragma unroll
-                            for (int t = 0; t < NT; ++t) {
-                                dst[8 * t] = pc[4 * half + m4][t][0];
-                                dst[8 * t + 1] = pc[4 * half + m4][t][1];
-                            }
+                        for (int t = 0; t < NT; ++t) {
+                            dst[8 * t] = pc[m4][t][0];
+                            dst[8 * t + 1] = pc[m4][t][1];
                         }
                     }
-                    if (!Lay::DELTA_IN_TILE) {
-                        const bool hh = half == 0 ? h0 : h1;
-                        if (lane < 8 * mt_here) c.R[lane * LDR + NP] = hh ? (half == 0 ? y0 : y1) : 0.0;
-                    }
-                    __syncwarp();
-                    consume_rows<F, MODE>(c, nrows, bd.chiv_off + g0 + 32 * half, fout, Jout, na);
                 }
+                if (!Lay::DELTA_IN_TILE) {
+                    const bool hh = half == 0 ? h0 : h1;
+                    if (lane < 8 * mt_here) c.R[lane * LDR + NP] = hh ? (half == 0 ? y0 : y1) : 0.0;
+                }
+                __syncwarp();
+                consume_rows<F, MODE>(c, nrows, bd.chiv_off + g0 + 32 * half, fout, Jout, na);
+#pragma unroll
+                for (int m4 = 0; m4 < 4; ++m4)
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) { pc[m4][t][0] = pc[m4 + 4][t][0]; pc[m4][t][1] = pc[m4 + 4][t][1]; }
             }
         }
     }
@@ -467,10 +477,14 @@ __device__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, doubl
 // ---------------------------------------------------------------------------
 // small dense kernels on the warp: lane i owns row i, everything in registers
 // ---------------------------------------------------------------------------
-// One Cholesky factorisation + the solves every caller needs, as ONE out-of-line function (one
-// copy of the unrolled code per functor).  Lane i keeps row i of L in registers; each finished
-// column is also written to shared memory as a row of L^T (LT[j][i] = L[i][j]), from where the
-// trailing update reads it back by broadcast and the backward substitution reads its columns.
+// One Cholesky factorisation + the solves every caller needs, as ONE out-of-line function with
+// ROLLED loops: the kernel is instruction-fetch bound when this code is unrolled (ncu: more than
+// half of the stall samples were "no instruction"), so code size matters more than a few moves.
+// Lane i owns row i.  r[m] holds the live entry (i, j+m) of the trailing matrix at step j: the
+// update writes r[m-1] = r[m] - L_ij L_(j+m)j, which rotates the row so that the pivot column is
+// always r[0] and every register index is static.  Finished columns go to shared memory as rows
+// of L^T (LT[j][i] = L[i][j]); the update reads them back by broadcast, the substitutions read
+// L[i][j] = LT[j][i] and L[j][i] = LT[i][j].
 //     L L^T = d_i A_ij d_j + alpha delta_ij
 //     p = -(L L^T)^-1 gh ,  res[0] = |p| ,  res[1] = |L^-1 p|^2 ,  res[2] = min_j pivot_j / diag_j
 // Returns false if the matrix is not numerically positive definite.  LT (NP x LDA) and the
@@ -481,70 +495,73 @@ __device__ __noinline__ bool factor_solve(const double* A, const double* dsc, do
                                           double* p_out, double* res) {
     const int i = lane;
     const bool act = i < NP;
-    double l[NP];
+    double r[NP];
     const double di = act ? dsc[i] : 0.0;
+    double mdiag = 1.0;                 // original diagonal entry of this lane's row
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
         double v = act ? A[i * LDA + k] * di * dsc[k] : 0.0;
-        if (k == i) v = act ? v + alpha : 1.0;
-        l[k] = v;
+        if (k == i) { v = act ? v + alpha : 1.0; mdiag = v; }
+        r[k] = v;
     }
-    double mdiag = 1.0;                 // original diagonal entry of this lane's row
-#pragma unroll
-    for (int k = 0; k < NP; ++k) if (k == i) mdiag = l[k];
     double myinv = 1.0, mypiv = 1.0;
     bool ok = true;
     __syncwarp();
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < NP; ++j) {
-        const double piv = __shfl_sync(B200LM_FULL, l[j], j);
+        const double piv = __shfl_sync(B200LM_FULL, r[0], j);
         const double inv = rsqrt(piv);
-        const double lij = (i == j) ? piv * inv : l[j] * inv;        // L[i][j]
+        const double lij = (i == j) ? piv * inv : r[0] * inv;        // L[i][j]
         if (i == j) {
             myinv = inv; mypiv = piv;
             if (!(piv > 8.0 * NP * 2.220446049250313e-16 * mdiag) || !isfinite(piv)) ok = false;
         }
-        l[j] = lij;
         if (act) LT[j * LDA + i] = lij;
         __syncwarp();
+        const double* lt = LT + j * LDA + j;                         // lt[m] = L[j+m][j]
 #pragma unroll
-        for (int k = j + 1; k < NP; ++k) l[k] = fma(-lij, LT[j * LDA + k], l[k]);   // row i, col k (k <= i used)
+        for (int m = 1; m < NP; ++m) r[m - 1] = fma(-lij, lt[m], r[m]);   // entries past the row end are junk, never used
+        r[NP - 1] = 0.0;
     }
     ok = __all_sync(B200LM_FULL, ok);
     if (act) idg[i] = myinv;
+    __syncwarp();
     double p = 0.0, pn = 0.0, w2 = 0.0, minr = 0.0;
     if (ok) {
         // y = L^-1 (-gh)
         double b = act ? -gh : 0.0;
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < NP; ++j) {
             const double yj = __shfl_sync(B200LM_FULL, b * myinv, j);
+            const double lij = act ? LT[j * LDA + i] : 0.0;
             if (i == j) b = yj;
-            else if (i > j) b = fma(-l[j], yj, b);
+            else if (i > j) b = fma(-lij, yj, b);
         }
-        // p = L^-T y : lane i needs column i of L^T, i.e. LT[j][i] ... stored as LT[j*LDA + i]
-#pragma unroll
+        // p = L^-T y
+#pragma unroll 1
         for (int j = NP - 1; j >= 0; --j) {
             const double xj = __shfl_sync(B200LM_FULL, b * myinv, j);
+            const double lji = act ? LT[i * LDA + j] : 0.0;
             if (i == j) b = xj;
-            else if (i < j && act) b = fma(-LT[i * LDA + j], xj, b);
+            else if (i < j) b = fma(-lji, xj, b);
         }
         p = act ? b : 0.0;
         pn = sqrt(warp_sum(p * p));
         // w = L^-1 p
         double w = p;
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < NP; ++j) {
             const double yj = __shfl_sync(B200LM_FULL, w * myinv, j);
+            const double lij = act ? LT[j * LDA + i] : 0.0;
             if (i == j) w = yj;
-            else if (i > j) w = fma(-l[j], yj, w);
+            else if (i > j) w = fma(-lij, yj, w);
         }
         w2 = warp_sum(act ? w * w : 0.0);
         if (want_ratio) {
-            double r = act ? mypiv / mdiag : 1.0;
+            double q = act ? mypiv / mdiag : 1.0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) r = fmin(r, __shfl_xor_sync(B200LM_FULL, r, o));
-            minr = r;
+            for (int o = 16; o > 0; o >>= 1) q = fmin(q, __shfl_xor_sync(B200LM_FULL, q, o));
+            minr = q;
         }
     }
     *p_out = p;
@@ -704,10 +721,11 @@ __device__ __forceinline__ void setup_ctx(WarpCtx<F>& c, double* smem, const Fit
     } else {
         c.wt = P.blk_wt;
     }
-    double* base = smem + wt_region + (size_t)warp * Lay::per_warp_doubles(P.rb);
+    double* base = smem + wt_region + (size_t)warp * Lay::per_warp_doubles(P.rb, P.nblkrows);
     c.R = base;
     c.dvec = c.R + (size_t)P.rb * Lay::LDR;
-    c.A = c.dvec + P.rb;
+    c.rvec = c.dvec + P.rb;
+    c.A = c.rvec + ((P.nblkrows + 1) & ~1);
     c.L = c.A + Lay::NP * Lay::LDA;
     c.p = c.L + Lay::NP * Lay::LDA;
     c.pn = c.p + Lay::NP;
@@ -805,7 +823,8 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
             if (actual_reduction > 0.0) {
                 if (act) c.p[lane] = c.pn[lane];
                 __syncwarp();
-                cost = eval_full<F>(c, c.p, nullptr, nullptr);   // J, J^T J, J^T r at the new point
+                cost = eval_full<F>(c, c.p, nullptr, nullptr, true);   // J, J^T J, J^T r at the new point;
+                                                                        // residuals of the blocks kept from the trial
                 ++njev;
                 if (act && P.scaler == 1) sinv = fmax(sinv, sqrt(c.A[lane * LDA + lane]));
             }
@@ -945,7 +964,7 @@ template <class F>
 inline cudaError_t plan_launch(FitParams& P, int sm_count, size_t smem_budget, LaunchInfo& li) {
     typedef FitLayout<F> Lay;
     const size_t wt_bytes = ((size_t)(P.wt_total + 1) & ~(size_t)1) * sizeof(double);
-    const size_t per_warp = (size_t)Lay::per_warp_doubles(P.rb) * sizeof(double);
+    const size_t per_warp = (size_t)Lay::per_warp_doubles(P.rb, P.nblkrows) * sizeof(double);
     P.wt_in_smem = (P.wt_total > 0 && wt_bytes + 4 * per_warp <= smem_budget) ? 1 : 0;
     const size_t avail = smem_budget - (P.wt_in_smem ? wt_bytes : 0);
     int warps = (int)(avail / per_warp);

@@ -32,6 +32,7 @@ struct FitParams {
     int wt_total;               // doubles in blk_wt
     int wt_in_smem;             // stage blk_wt in shared memory
     int rb;                     // rows of the per-warp row buffer
+    int nblkrows;               // total residual rows produced by the correlated blocks
     int warps;                  // warps per CTA
     // ---- batch ------------------------------------------------------------
     int B;
