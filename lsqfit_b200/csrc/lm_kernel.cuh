@@ -23,6 +23,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include "lm_types.h"
 
 namespace b200lm {
@@ -60,7 +61,9 @@ struct FitLayout {
     static constexpr int LDA = NP | 1;
     static constexpr int NVEC = 6;
     static constexpr int NTRI = NT * (NT + 1) / 2;         // upper-triangular tile pairs
-    // register budget: 16 warps/CTA leave 128 registers per thread, 12 warps leave 168
+    // register budget: 16 warps/CTA leave 128 registers per thread, 12 warps leave 168.  Measured on
+    // C3 (NP=16): 12 warps beat 16 (19.1 vs 22.6 ms per 10k fits) -- per-warp latency and
+    // instruction-cache pressure matter more than occupancy for this kernel.
     static constexpr int MAX_WARPS = NP > 10 ? 12 : 16;
     __host__ __device__ static int per_warp_doubles(int rb) {
         int n = rb * LDR + rb + 2 * NP * LDA + NVEC * NP;  // R | dvec | A | L | vectors
@@ -506,17 +509,26 @@ __device__ __noinline__ bool factor_solve(const double* A, const double* dsc, do
     }
     double myinv = 1.0, mypiv = 1.0;
     bool ok = true;
+    double b = act ? -gh : 0.0;          // forward substitution y = L^-1 (-gh) rides along
     __syncwarp();
 #pragma unroll 1
     for (int j = 0; j < NP; ++j) {
         const double piv = __shfl_sync(B200LM_FULL, r[0], j);
-        const double inv = rsqrt(piv);
+        // 1/sqrt(piv): the scaled matrix has diagonal 1 + alpha, so the pivot is far from the
+        // float range limits; fp32 seed + two Newton steps in fp64 (full double accuracy)
+        double inv = (double)rsqrtf((float)piv);
+        const double hp = 0.5 * piv;
+        inv = inv * fma(-hp * inv, inv, 1.5);
+        inv = inv * fma(-hp * inv, inv, 1.5);
         const double lij = (i == j) ? piv * inv : r[0] * inv;        // L[i][j]
         if (i == j) {
             myinv = inv; mypiv = piv;
-            if (!(piv > 8.0 * NP * 2.220446049250313e-16 * mdiag) || !isfinite(piv)) ok = false;
+            if (!(piv > 8.0 * NP * 2.220446049250313e-16 * mdiag) || !(piv < 1e300)) ok = false;
         }
         if (act) LT[j * LDA + i] = lij;
+        const double yj = __shfl_sync(B200LM_FULL, b * inv, j);
+        if (i == j) b = yj;
+        else if (i > j) b = fma(-lij, yj, b);
         __syncwarp();
         const double* lt = LT + j * LDA + j;                         // lt[m] = L[j+m][j]
 #pragma unroll
@@ -528,15 +540,6 @@ __device__ __noinline__ bool factor_solve(const double* A, const double* dsc, do
     __syncwarp();
     double p = 0.0, pn = 0.0, w2 = 0.0, minr = 0.0;
     if (ok) {
-        // y = L^-1 (-gh)
-        double b = act ? -gh : 0.0;
-#pragma unroll 1
-        for (int j = 0; j < NP; ++j) {
-            const double yj = __shfl_sync(B200LM_FULL, b * myinv, j);
-            const double lij = act ? LT[j * LDA + i] : 0.0;
-            if (i == j) b = yj;
-            else if (i > j) b = fma(-lij, yj, b);
-        }
         // p = L^-T y
 #pragma unroll 1
         for (int j = NP - 1; j >= 0; --j) {
@@ -586,37 +589,52 @@ __device__ double solve_tr(WarpCtx<F>& c, double gh, double Delta, double& alpha
     const int lane = c.lane;
     const bool act = lane < NP;
     double res[3];
-    double p = 0.0;
-    if (!gn.valid) {
+    double p = 0.0, pn = 0.0;
+    bool have_p = false;
+    // |p(alpha)| decreases with alpha.  If the warm-started alpha > 0 already gives a step longer
+    // than Delta, the Gauss-Newton step (alpha = 0) is longer still: its factorisation is skipped.
+    bool tried_warm = false, warm_ok = false;
+    double warm_phi = 0.0, warm_w2 = 0.0, warm_pn = 0.0, warm_p = 0.0;
+    if (!gn.valid && alpha > 0.0) {
+        ++nfac;
+        tried_warm = true;
+        warm_ok = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, alpha, gh, false, &warm_p, res);
+        if (warm_ok) { warm_pn = res[0]; warm_w2 = res[1]; warm_phi = warm_pn - Delta; }
+    }
+    const bool need_gn = !(tried_warm && warm_ok && warm_phi > 0.0);
+    if (!gn.valid && need_gn) {
         ++nfac;
         gn.full_rank = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, 0.0, gh, false, &p, res);
         gn.p = p; gn.pn = res[0]; gn.w2 = res[1];
         gn.valid = true;
     }
-    const bool full_rank = gn.full_rank;
+    const bool full_rank = gn.valid && gn.full_rank;
     if (full_rank && gn.pn <= Delta) { alpha = 0.0; return gn.p; }
-    p = gn.p;
-    double pn = gn.pn;
     double alpha_upper = sqrt(warp_sum(act ? gh * gh : 0.0)) / Delta;
     double alpha_lower = 0.0;
     if (full_rank) {
-        const double phi = pn - Delta;
-        const double phi_prime = -gn.w2 / pn;
+        const double phi = gn.pn - Delta;
+        const double phi_prime = -gn.w2 / gn.pn;
         alpha_lower = -phi / phi_prime;
+        p = gn.p; have_p = true;
     }
     if (!full_rank && alpha == 0.0)
         alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
-    bool have_p = false;
-    // Newton iteration on the secular equation.  Unlike the reference's solver the step of the
-    // last iterate (|phi| < 0.01 Delta) is kept instead of being recomputed at the updated
-    // alpha: it is rescaled to the trust-region boundary below anyway, and one factorisation
-    // per trial is saved.
+    // Newton iteration on the secular equation phi(alpha) = |p(alpha)| - Delta (More' 1978; the
+    // same safeguarded update as scipy's solve_lsq_trust_region).  The step of the last iterate is
+    // kept (it is rescaled to the boundary below) instead of being recomputed at the updated
+    // alpha, and the iteration stops at |phi| < 0.1 Delta (MINPACK's lmpar tolerance).
     for (int it = 0; it < 10; ++it) {
-        if (alpha < alpha_lower || alpha > alpha_upper)
-            alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
-        ++nfac;
+        bool ok;
         double pt;
-        const bool ok = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, alpha, gh, false, &pt, res);
+        if (it == 0 && tried_warm) {
+            ok = warm_ok; pt = warm_p; res[0] = warm_pn; res[1] = warm_w2;
+        } else {
+            if (alpha < alpha_lower || alpha > alpha_upper)
+                alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
+            ++nfac;
+            ok = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, alpha, gh, false, &pt, res);
+        }
         if (!ok) {
             alpha_lower = fmax(alpha_lower, alpha);
             alpha = fmax(2.0 * alpha, 0.001 * alpha_upper);
@@ -632,7 +650,7 @@ __device__ double solve_tr(WarpCtx<F>& c, double gh, double Delta, double& alpha
         const double ratio = phi / phi_prime;
         alpha_lower = fmax(alpha_lower, alpha - ratio);
         alpha -= (phi + Delta) * ratio / Delta;
-        if (fabs(phi) < 0.01 * Delta) break;
+        if (fabs(phi) < 0.1 * Delta) break;
     }
     if (!have_p) p = act ? -gh : 0.0;             // steepest descent fallback
     pn = sqrt(warp_sum(act ? p * p : 0.0));
@@ -970,6 +988,10 @@ inline cudaError_t plan_launch(FitParams& P, int sm_count, size_t smem_budget, L
     int warps = (int)(avail / per_warp);
     if (warps < 1) return cudaErrorInvalidConfiguration;
     if (warps > Lay::MAX_WARPS) warps = Lay::MAX_WARPS;
+    if (const char* env = getenv("B200LM_WARPS")) {          // tuning knob (profiling only)
+        const int w = atoi(env);
+        if (w >= 1 && w < warps) warps = w;
+    }
     P.warps = warps;
     li.block = warps * 32;
     li.smem = (P.wt_in_smem ? wt_bytes : 0) + warps * per_warp;

@@ -33,3 +33,12 @@ for rep in [4, 16]:
     ms = md.repeat(rep, 1).contiguous()
     t2, o2 = timeit(ms, reps=2)
     print("B=%d: %.3f ms -> %.0f fits/s" % (ms.shape[0], t2, ms.shape[0]/t2*1e3))
+# --- does the initial chi2 predict the iteration count? (longest-processing-time-first scheduling)
+f0, J0, chi0 = plan.residual_jacobian(p0, md)
+chi0 = chi0.cpu().numpy()
+print("corr(nit, chi2_0) = %.3f, corr(nit, log chi2_0) = %.3f" % (np.corrcoef(nit, chi0)[0,1], np.corrcoef(nit, np.log(chi0))[0,1]))
+for name, key in [("chi2_0 descending", -chi0), ("nit descending (oracle schedule)", -nit.astype(float)), ("nit ascending (worst)", nit.astype(float))]:
+    o = np.argsort(key, kind="stable")
+    ms = md[torch.as_tensor(o).cuda()].contiguous()
+    t2, _ = timeit(ms)
+    print("%-36s %.3f ms" % (name, t2))
