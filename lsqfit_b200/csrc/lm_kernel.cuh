@@ -66,12 +66,11 @@ struct FitLayout {
     // instruction-cache pressure matter more than occupancy for this kernel.
     static constexpr int MAX_WARPS = NP > 10 ? 12 : 16;
     __host__ __device__ static int per_warp_doubles(int rb) {
-        int n = rb * LDR + rb + 2 * NP * LDA + NVEC * NP;  // R | dvec | A | L | vectors
+        // R | dvec | A0 | A1 | L | vectors (+ second gradient).  A0/A1, g0/g1: the Jacobian is
+        // evaluated speculatively at every trial point, so the normal equations of the current
+        // point must survive a rejected trial.
+        int n = rb * LDR + rb + 3 * NP * LDA + (NVEC + 1) * NP;
         return (n + 1) & ~1;
-    }
-    // + rvec: whitened residuals of the correlated blocks, kept from the trial evaluation
-    __host__ __device__ static int per_warp_doubles(int rb, int nblkrows) {
-        return (per_warp_doubles(rb) + nblkrows + 1) & ~1;
     }
 };
 
@@ -81,7 +80,8 @@ struct WarpCtx {
     const FitParams& P;
     const double* wt;       // whitening matrices (shared or global)
     const double* mean;     // this fit's y(+)prior means
-    double *R, *dvec, *rvec, *A, *L, *p, *pn, *g, *sinv, *dsc, *idg;
+    double *R, *dvec, *A, *L, *p, *pn, *g, *sinv, *dsc, *idg;
+    double *Abuf[2], *gbuf[2];      // c.A / c.g point at the buffer the next evaluation writes
     int lane;
     __device__ WarpCtx(const FitParams& P_) : P(P_) {}
 };
@@ -91,65 +91,6 @@ struct WarpCtx {
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-// y_r = sum_k W[r][k] v[k] for the two rows owned by this lane, plain DFMA.  k is rotated by
-// the lane id so that the row-major, padded W and the compact vector are read conflict free.
-__device__ __forceinline__ void matvec2(const double* W, int ldk, int r0, int r1, bool h0, bool h1,
-                                        const double* v, int nk, int lane, double& y0, double& y1) {
-    int k = lane % nk;
-    for (int kk = 0; kk < nk; ++kk) {
-        const double vk = v[k];
-        if (h0) y0 = fma(W[(size_t)r0 * ldk + k], vk, y0);
-        if (h1) y1 = fma(W[(size_t)r1 * ldk + k], vk, y1);
-        k = (k + 1 == nk) ? 0 : k + 1;
-    }
-}
-
-// ---------------------------------------------------------------------------
-// residual only: returns cost = 1/2 sum r^2 (same value in every lane)
-// ---------------------------------------------------------------------------
-template <class F>
-__device__ __noinline__ double eval_cost(WarpCtx<F>& c, const double* pv, double* fout) {
-    const FitParams& P = c.P;
-    const int lane = c.lane;
-    double acc = 0.0;
-    for (int i = lane; i < P.nd_fn; i += 32) {
-        const int row = P.dfn_idx[i];
-        const double f = F::value(P.x + (size_t)row * P.nx, row, pv);
-        const double r = P.dfn_w[i] * (f - c.mean[row]);
-        acc = fma(r, r, acc);
-        if (fout) fout[i] = r;
-    }
-    for (int i = lane; i < P.nd_pr; i += 32) {
-        const int idx = P.dpr_idx[i];
-        const double r = P.dpr_w[i] * (pv[idx - P.ny] - c.mean[idx]);
-        acc = fma(r, r, acc);
-        if (fout) fout[P.nd_fn + i] = r;
-    }
-    for (int b = 0; b < P.nblk; ++b) {
-        const BlockDesc bd = P.blk[b];
-        const double* W = c.wt + bd.wt_off;
-        for (int g0 = 0; g0 < bd.n_out; g0 += 64) {
-            const int r0 = g0 + lane, r1 = g0 + lane + 32;
-            const bool h0 = r0 < bd.n_out, h1 = r1 < bd.n_out;
-            double y0 = 0.0, y1 = 0.0;
-            for (int k0 = 0; k0 < bd.n_in; k0 += P.rb) {
-                const int nk = min(P.rb, bd.n_in - k0);
-                for (int k = lane; k < nk; k += 32) {
-                    const int idx = P.blk_idx[bd.idx_off + k0 + k];
-                    const double v = idx < P.ny ? F::value(P.x + (size_t)idx * P.nx, idx, pv) : pv[idx - P.ny];
-                    c.dvec[k] = v - c.mean[idx];
-                }
-                __syncwarp();
-                matvec2(W + k0, bd.ldw, r0, r1, h0, h1, c.dvec, nk, lane, y0, y1);
-                __syncwarp();
-            }
-            if (h0) { acc = fma(y0, y0, acc); c.rvec[bd.chiv_off - P.nd_fn - P.nd_pr + r0] = y0; if (fout) fout[bd.chiv_off + r0] = y0; }
-            if (h1) { acc = fma(y1, y1, acc); c.rvec[bd.chiv_off - P.nd_fn - P.nd_pr + r1] = y1; if (fout) fout[bd.chiv_off + r1] = y1; }
-        }
-    }
-    return 0.5 * warp_sum(acc);
 }
 
 // ---------------------------------------------------------------------------
@@ -325,8 +266,7 @@ __device__ __forceinline__ void consume_rows(WarpCtx<F>& c, int nrows, int slot0
 // MODE 0: normal equations (A = J^T J, g = J^T r).  MODE 1: QR factor of J.diag(dsc) in c.A.
 // ---------------------------------------------------------------------------
 template <class F, int MODE = 0>
-__device__ __noinline__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, double* Jout,
-                                         bool reuse_r = false) {
+__device__ __noinline__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, double* Jout) {
     typedef FitLayout<F> Lay;
     constexpr int NP = Lay::NP, NT = Lay::NT, LDR = Lay::LDR, LDA = Lay::LDA, NCOL = Lay::NCOL;
     const FitParams& P = c.P;
@@ -387,15 +327,11 @@ __device__ __noinline__ double eval_full(WarpCtx<F>& c, const double* pv, double
             for (int m = 0; m < 8; ++m)
 #pragma unroll
                 for (int t = 0; t < NT; ++t) { pc[m][t][0] = 0.0; pc[m][t][1] = 0.0; }
-            const int r0 = g0 + lane, r1 = g0 + lane + 32;
-            const bool h0 = r0 < bd.n_out, h1 = r1 < bd.n_out;
-            double y0 = 0.0, y1 = 0.0;                 // residual rows when it is not in a tile
-            const bool do_mv = !Lay::DELTA_IN_TILE && !reuse_r;
-            if (!Lay::DELTA_IN_TILE && reuse_r) {
-                const double* rv = c.rvec + (bd.chiv_off - P.nd_fn - P.nd_pr);
-                if (h0) y0 = rv[r0];
-                if (h1) y1 = rv[r1];
-            }
+            // when the residual column does not ride in a tile (np % 8 == 0) it gets a tile of its
+            // own in which only column 0 is populated: r = W.delta as 8 more DMMA per k-step
+            double pr[Lay::DELTA_IN_TILE ? 1 : 8][2];
+#pragma unroll
+            for (int m = 0; m < (Lay::DELTA_IN_TILE ? 1 : 8); ++m) { pr[m][0] = 0.0; pr[m][1] = 0.0; }
             for (int k0 = 0; k0 < bd.n_in; k0 += 32) {
                 const int nk = min(32, bd.n_in - k0);
                 const int nk4 = (nk + 3) & ~3;
@@ -419,6 +355,7 @@ __device__ __noinline__ double eval_full(WarpCtx<F>& c, const double* pv, double
                 } else if (lane < nk4) {
 #pragma unroll
                     for (int j = 0; j < NCOL; ++j) row_[j] = 0.0;
+                    if (!Lay::DELTA_IN_TILE) c.dvec[lane] = 0.0;
                 }
                 __syncwarp();
                 // A fragment: W[g0 + 8m + lane/4][k0 + 4s + lane%4];  B fragment: R[4s + lane%4][8t + lane/4]
@@ -430,16 +367,18 @@ __device__ __noinline__ double eval_full(WarpCtx<F>& c, const double* pv, double
                     double bf[NT];
 #pragma unroll
                     for (int t = 0; t < NT; ++t) bf[t] = rb_[s4 * LDR + 8 * t];
+                    double bd_ = 0.0;
+                    if constexpr (!Lay::DELTA_IN_TILE) bd_ = (lane >> 2) == 0 ? c.dvec[s4 + (lane & 3)] : 0.0;
 #pragma unroll
                     for (int m = 0; m < 8; ++m) {
                         if (m < mtiles) {
                             const double af = wa[m * ldw8 + s4];
 #pragma unroll
                             for (int t = 0; t < NT; ++t) dmma(pc[m][t][0], pc[m][t][1], af, bf[t]);
+                            if constexpr (!Lay::DELTA_IN_TILE) dmma(pr[m][0], pr[m][1], af, bd_);
                         }
                     }
                 }
-                if (do_mv) matvec2(W + k0, bd.ldw, r0, r1, h0, h1, c.dvec, nk, lane, y0, y1);
                 __syncwarp();                      // everyone has finished reading this chunk
             }
             // finished rows: two passes of (up to) 32 rows = 4 m-tiles each.  The loop is rolled
@@ -460,16 +399,20 @@ __device__ __noinline__ double eval_full(WarpCtx<F>& c, const double* pv, double
                         }
                     }
                 }
-                if (!Lay::DELTA_IN_TILE) {
-                    const bool hh = half == 0 ? h0 : h1;
-                    if (lane < 8 * mt_here) c.R[lane * LDR + NP] = hh ? (half == 0 ? y0 : y1) : 0.0;
+                if constexpr (!Lay::DELTA_IN_TILE) {
+                    // column 0 of the residual tile lives in c0 of the lanes with lane % 4 == 0
+#pragma unroll
+                    for (int m4 = 0; m4 < 4; ++m4)
+                        if (m4 < mt_here && (lane & 3) == 0) c.R[(8 * m4 + (lane >> 2)) * LDR + NP] = pr[m4][0];
                 }
                 __syncwarp();
                 consume_rows<F, MODE>(c, nrows, bd.chiv_off + g0 + 32 * half, fout, Jout, na);
 #pragma unroll
-                for (int m4 = 0; m4 < 4; ++m4)
+                for (int m4 = 0; m4 < 4; ++m4) {
 #pragma unroll
                     for (int t = 0; t < NT; ++t) { pc[m4][t][0] = pc[m4 + 4][t][0]; pc[m4][t][1] = pc[m4 + 4][t][1]; }
+                    if constexpr (!Lay::DELTA_IN_TILE) pr[m4][0] = pr[m4 + 4][0];
+                }
             }
         }
     }
@@ -739,18 +682,21 @@ __device__ __forceinline__ void setup_ctx(WarpCtx<F>& c, double* smem, const Fit
     } else {
         c.wt = P.blk_wt;
     }
-    double* base = smem + wt_region + (size_t)warp * Lay::per_warp_doubles(P.rb, P.nblkrows);
+    double* base = smem + wt_region + (size_t)warp * Lay::per_warp_doubles(P.rb);
     c.R = base;
     c.dvec = c.R + (size_t)P.rb * Lay::LDR;
-    c.rvec = c.dvec + P.rb;
-    c.A = c.rvec + ((P.nblkrows + 1) & ~1);
-    c.L = c.A + Lay::NP * Lay::LDA;
+    c.Abuf[0] = c.dvec + P.rb;
+    c.Abuf[1] = c.Abuf[0] + Lay::NP * Lay::LDA;
+    c.A = c.Abuf[0];
+    c.L = c.Abuf[1] + Lay::NP * Lay::LDA;
     c.p = c.L + Lay::NP * Lay::LDA;
     c.pn = c.p + Lay::NP;
     c.g = c.pn + Lay::NP;
     c.sinv = c.g + Lay::NP;
     c.dsc = c.sinv + Lay::NP;
     c.idg = c.dsc + Lay::NP;
+    c.gbuf[0] = c.g;
+    c.gbuf[1] = c.idg + Lay::NP;
     __syncthreads();
 }
 
@@ -776,6 +722,8 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
         if (act) c.p[lane] = p0[lane];
         __syncwarp();
 
+        int cur = 0;                              // buffer holding J^T J, J^T r of the current point
+        c.A = c.Abuf[0]; c.g = c.gbuf[0];
         double cost = eval_full<F>(c, c.p, nullptr, nullptr);
         int nfev = 1, njev = 1, nfac = 0;
         int status = -2;                         // -2: running
@@ -816,8 +764,14 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
                 }
                 const double predicted = -warp_sum(act ? step * (0.5 * As + gi) : 0.0);
                 __syncwarp();
-                cost_new = eval_cost<F>(c, c.pn, nullptr);
-                ++nfev;
+                // Speculative evaluation: residual AND Jacobian / normal equations at the trial
+                // point, into the other buffer.  ~87 % of the trials are accepted, and then no
+                // second pass over the rows is needed; a rejected trial leaves the current
+                // buffers untouched.
+                c.A = c.Abuf[cur ^ 1]; c.g = c.gbuf[cur ^ 1];
+                cost_new = eval_full<F>(c, c.pn, nullptr, nullptr);
+                c.A = c.Abuf[cur]; c.g = c.gbuf[cur];
+                ++nfev; ++njev;
                 const double shn = sqrt(warp_sum(act ? sh * sh : 0.0));
                 if (!isfinite(cost_new)) { Delta = 0.25 * shn; continue; }
                 actual_reduction = cost - cost_new;
@@ -839,11 +793,12 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
                 Delta = Delta_new;
             }
             if (actual_reduction > 0.0) {
+                // accept: the trial buffers become the current ones
                 if (act) c.p[lane] = c.pn[lane];
+                cur ^= 1;
+                c.A = c.Abuf[cur]; c.g = c.gbuf[cur];
+                cost = cost_new;
                 __syncwarp();
-                cost = eval_full<F>(c, c.p, nullptr, nullptr, true);   // J, J^T J, J^T r at the new point;
-                                                                        // residuals of the blocks kept from the trial
-                ++njev;
                 if (act && P.scaler == 1) sinv = fmax(sinv, sqrt(c.A[lane * LDA + lane]));
             }
             if (term != -2) {
@@ -982,7 +937,7 @@ template <class F>
 inline cudaError_t plan_launch(FitParams& P, int sm_count, size_t smem_budget, LaunchInfo& li) {
     typedef FitLayout<F> Lay;
     const size_t wt_bytes = ((size_t)(P.wt_total + 1) & ~(size_t)1) * sizeof(double);
-    const size_t per_warp = (size_t)Lay::per_warp_doubles(P.rb, P.nblkrows) * sizeof(double);
+    const size_t per_warp = (size_t)Lay::per_warp_doubles(P.rb) * sizeof(double);
     P.wt_in_smem = (P.wt_total > 0 && wt_bytes + 4 * per_warp <= smem_budget) ? 1 : 0;
     const size_t avail = smem_budget - (P.wt_in_smem ? wt_bytes : 0);
     int warps = (int)(avail / per_warp);
