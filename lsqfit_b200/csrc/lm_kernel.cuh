@@ -202,7 +202,7 @@ __device__ __forceinline__ void emit_rows(const double* S, int nrows, int slot0,
 // S is destroyed.  Used for the final covariance: (J^T J)^-1 = dsc Rt^-1 Rt^-T dsc has a
 // relative error ~kappa(J)*eps instead of kappa^2*eps for the normal equations.
 template <class F>
-__device__ void qr_update(WarpCtx<F>& c, double* S, int nrows) {
+__device__ __forceinline__ void qr_update(WarpCtx<F>& c, double* S, int nrows) {
     typedef FitLayout<F> Lay;
     constexpr int NP = Lay::NP, LDR = Lay::LDR, LDA = Lay::LDA;
     const int lane = c.lane;
@@ -265,12 +265,20 @@ __device__ __forceinline__ void consume_rows(WarpCtx<F>& c, int nrows, int slot0
 // returns cost.  Optionally writes the residual vector and J to global memory.
 // MODE 0: normal equations (A = J^T J, g = J^T r).  MODE 1: QR factor of J.diag(dsc) in c.A.
 // ---------------------------------------------------------------------------
-template <class F, int MODE = 0>
-__device__ __noinline__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, double* Jout) {
+template <class F, int MODE, bool WSMEM>
+__device__ __noinline__ double eval_full_impl(const WarpCtx<F>& c_in, const double* pv, double* fout, double* Jout) {
+    WarpCtx<F> c = c_in;                // local copy: the address-space assumptions below attach to SSA values
     typedef FitLayout<F> Lay;
     constexpr int NP = Lay::NP, NT = Lay::NT, LDR = Lay::LDR, LDA = Lay::LDA, NCOL = Lay::NCOL;
     const FitParams& P = c.P;
     const int lane = c.lane;
+    // per-warp state lives in shared memory: say so, or the out-of-line code uses generic LD/ST
+    __builtin_assume(__isShared(c.R));
+    __builtin_assume(__isShared(c.dvec));
+    __builtin_assume(__isShared(c.A));
+    __builtin_assume(__isShared(c.g));
+    __builtin_assume(__isShared(c.dsc));
+    __builtin_assume(__isShared(pv));
     for (int e = lane; e < NP * LDA; e += 32) c.A[e] = 0.0;
     if (MODE == 0 && lane < NP) c.g[lane] = 0.0;
     __syncwarp();
@@ -320,6 +328,7 @@ __device__ __noinline__ double eval_full(WarpCtx<F>& c, const double* pv, double
     for (int b = 0; b < P.nblk; ++b) {
         const BlockDesc bd = P.blk[b];
         const double* W = c.wt + bd.wt_off;
+        if constexpr (WSMEM) __builtin_assume(__isShared(W));
         for (int g0 = 0; g0 < bd.n_out; g0 += 64) {
             const int mtiles = min(8, (bd.n_out - g0 + 7) >> 3);
             double pc[8][NT][2];
@@ -420,6 +429,13 @@ __device__ __noinline__ double eval_full(WarpCtx<F>& c, const double* pv, double
     return 0.5 * warp_sum(acc);
 }
 
+// the block weights are staged in shared memory whenever they fit (P.wt_in_smem, uniform)
+template <class F, int MODE = 0>
+__device__ __forceinline__ double eval_full(WarpCtx<F>& c, const double* pv, double* fout, double* Jout) {
+    return c.P.wt_in_smem ? eval_full_impl<F, MODE, true>(c, pv, fout, Jout)
+                          : eval_full_impl<F, MODE, false>(c, pv, fout, Jout);
+}
+
 // ---------------------------------------------------------------------------
 // small dense kernels on the warp: lane i owns row i, everything in registers
 // ---------------------------------------------------------------------------
@@ -439,24 +455,28 @@ template <int NP, int LDA>
 __device__ __noinline__ bool factor_solve(const double* A, const double* dsc, double* LT, double* idg,
                                           int lane, double alpha, double gh, bool want_ratio,
                                           double* p_out, double* res) {
+    // the matrices live in shared memory: tell the compiler, or it emits generic LD/ST
+    __builtin_assume(__isShared(A));
+    __builtin_assume(__isShared(dsc));
+    __builtin_assume(__isShared(LT));
+    __builtin_assume(__isShared(idg));
     const int i = lane;
     const bool act = i < NP;
+    const int ii = act ? i : NP - 1;    // idle lanes shadow the last row (results unused): no selects
     double r[NP];
-    const double di = act ? dsc[i] : 0.0;
-    double mdiag = 1.0;                 // original diagonal entry of this lane's row
+    const double di = dsc[ii];
 #pragma unroll
-    for (int k = 0; k < NP; ++k) {
-        double v = act ? A[i * LDA + k] * di * dsc[k] : 0.0;
-        if (k == i) { v = act ? v + alpha : 1.0; mdiag = v; }
-        r[k] = v;
-    }
+    for (int k = 0; k < NP; ++k) r[k] = A[ii * LDA + k] * di * dsc[k];
+    // alpha is added when an entry becomes the pivot (only diagonal entries ever see it)
+    const double mdiag = fma(A[ii * LDA + ii] * di, di, alpha);     // diagonal entry of this lane's row
     double myinv = 1.0, mypiv = 1.0;
     bool ok = true;
     double b = act ? -gh : 0.0;          // forward substitution y = L^-1 (-gh) rides along
     __syncwarp();
-#pragma unroll 1
+    // unrolled by 4: the row rotation costs register moves only at the loop back-edge
+#pragma unroll 4
     for (int j = 0; j < NP; ++j) {
-        const double piv = __shfl_sync(B200LM_FULL, r[0], j);
+        const double piv = __shfl_sync(B200LM_FULL, r[0], j) + alpha;
         // 1/sqrt(piv): the scaled matrix has diagonal 1 + alpha, so the pivot is far from the
         // float range limits; fp32 seed + two Newton steps in fp64 (full double accuracy)
         double inv = (double)rsqrtf((float)piv);
