@@ -152,6 +152,16 @@ int b200lm_whiten(int device, int nblk, const int* h_n, const double* d_cov,
 int b200lm_propagate(b200lm_handle h, int B, const double* d_x, const double* d_cov,
                      const double* d_C, double* d_D, double* d_covp, void* stream);
 
+/* ---- dense FP64 GEMM on the DMMA path ---------------------------------------------------
+ * C[b] (M x N) = alpha * op(A[b]) . op(B[b]) + beta * C[b], all row-major fp64, batch strides in
+ * elements (0 = operand shared by the batch).  transA: A is stored [K][M]; transB: B is stored
+ * [N][K].  This is the building block of the dense side of the path -- W.[G|delta] and J^T J of
+ * src/lsqfit/_utilities.pyx:20-36, 90-93 at config-5 sizes, and the D / D C D^T products of
+ * nonlinear_fit._getp (src/lsqfit/__init__.py:897-922); exported for tests and for host drivers. */
+int b200lm_dgemm(int device, int transA, int transB, int batch, int M, int N, int K, double alpha,
+                 const double* d_A, long long sA, int lda, const double* d_B, long long sB, int ldb,
+                 double beta, double* d_C, long long sC, int ldc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

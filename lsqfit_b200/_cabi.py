@@ -1,7 +1,7 @@
 """ctypes binding of libb200lm.so (the C ABI declared in include/b200lm.h).
 
 There is no CPU fallback: if the library is missing, importing this module raises.
-Build it with ``python -m lsqfit_b200.build`` (or ``__graft_entry__.build()``).
+Build it with ``python lsqfit_b200/build.py`` (or ``__graft_entry__.build()``).
 """
 import ctypes as C
 import os
@@ -21,7 +21,7 @@ class B200LMError(RuntimeError):
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         "lsqfit_b200: %s not found -- the CUDA extension must be built "
-        "(python -m lsqfit_b200.build); there is no CPU fallback" % LIB_PATH)
+        "(python lsqfit_b200/build.py); there is no CPU fallback" % LIB_PATH)
 
 lib = C.CDLL(LIB_PATH)
 
@@ -57,6 +57,9 @@ SIGNATURES = {
                                            C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200lm_whiten": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200lm_dgemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                               C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong, C.c_int,
+                               C.c_double, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "b200lm_propagate": (C.c_int, [handle_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
 }

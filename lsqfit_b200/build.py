@@ -1,6 +1,6 @@
 """Build libb200lm.so in-tree with nvcc for sm_100a.
 
-    python -m lsqfit_b200.build [--force]
+    python lsqfit_b200/build.py [--force]      (run as a script: importing the package needs the built library)
 
 Every .cu under lsqfit_b200/csrc is compiled to an object file (in parallel) and
 linked into lsqfit_b200/libb200lm.so.  nvcc cross-compiles without a GPU, so this

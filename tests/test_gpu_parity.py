@@ -480,3 +480,47 @@ def test_iterators():
     assert chi2_dof < 1.2          # without prior noise chi2/dof < 1 (reference __init__.py:1427-1430)
     for sf in fit.simulated_fit_iter(3, seed=5):
         assert sf.error is None
+
+
+def test_dgemm_vs_torch():
+    """The DMMA fp64 GEMM against torch.matmul (fp64) for every transpose mode, odd sizes,
+    unaligned leading dimensions, batching with a shared operand, alpha/beta."""
+    _need_gpu()
+    import ctypes as C
+    import torch
+    from lsqfit_b200 import _cabi
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+
+    def run(tA, tB, batch, M, N, K, alpha=1.0, beta=0.0, shareB=False, pad=0):
+        shA = (batch, K, M + pad) if tA else (batch, M, K + pad)
+        shB = (1 if shareB else batch, N, K + pad) if tB else (1 if shareB else batch, K, N + pad)
+        A = torch.randn(shA, generator=g, device=dev, dtype=torch.float64)
+        B = torch.randn(shB, generator=g, device=dev, dtype=torch.float64)
+        Cm = torch.randn((batch, M, N), generator=g, device=dev, dtype=torch.float64)
+        Av = A[:, :, :M] if tA else A[:, :, :K]
+        Bv = B[:, :, :K] if tB else B[:, :, :N]
+        opA = Av.transpose(1, 2) if tA else Av
+        opB = Bv.transpose(1, 2) if tB else Bv
+        ref = alpha * torch.matmul(opA, opB) + beta * Cm
+        out = Cm.clone()
+        _cabi.check(_cabi.lib.b200lm_dgemm(
+            0, int(tA), int(tB), batch, M, N, K, alpha,
+            A.data_ptr(), A.stride(0), A.stride(1), B.data_ptr(), 0 if shareB else B.stride(0), B.stride(1),
+            beta, out.data_ptr(), out.stride(0), out.stride(1),
+            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        torch.cuda.synchronize()
+        scale = float(torch.sqrt(torch.tensor(float(K)))) + 1.0
+        err = float((out - ref).abs().max()) / scale
+        assert err < 1e-13, (tA, tB, batch, M, N, K, err)
+
+    for tA in (False, True):
+        for tB in (False, True):
+            run(tA, tB, 1, 128, 128, 64)
+            run(tA, tB, 1, 257, 131, 77)                 # ragged edges
+            run(tA, tB, 3, 16, 80, 16, shareB=True)      # propagate-like: tiny M, shared B
+            run(tA, tB, 2, 100, 50, 33, pad=1)           # odd leading dimension -> scalar-copy path
+            run(tA, tB, 1, 300, 200, 500, alpha=-0.5, beta=2.0)
+    run(False, False, 1, 1, 1, 1)
+    run(False, True, 1, 512, 512, 1024)
