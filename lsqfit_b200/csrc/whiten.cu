@@ -12,6 +12,7 @@
 #include <string>
 #include "../../include/b200lm.h"
 #include "handle.h"
+#include "jacobi_core.cuh"
 
 namespace b200lm {
 
@@ -34,15 +35,6 @@ struct WhitenArgs {
     int use_eps;
 };
 
-__device__ __forceinline__ void rr_pair(int n2, int r, int k, int& p, int& q) {
-    // round-robin tournament on n2 (even) players, round r in [0, n2-1), pair k in [0, n2/2)
-    const int m = n2 - 1;
-    int a, b;
-    if (k == 0) { a = m; b = r; }
-    else { a = (r + k) % m; b = (r - k + m) % m; }
-    p = min(a, b); q = max(a, b);
-}
-
 __global__ void __launch_bounds__(WH_THREADS) whiten_kernel(const __grid_constant__ WhitenArgs a) {
     extern __shared__ double sm[];
     const int blk = blockIdx.x;
@@ -54,7 +46,8 @@ __global__ void __launch_bounds__(WH_THREADS) whiten_kernel(const __grid_constan
     const int tid = threadIdx.x;
     const int ld = n | 1;
     __shared__ double s_c[WH_NMAX / 2], s_s[WH_NMAX / 2];
-    __shared__ int s_rot, s_cnt;
+    __shared__ int s_flag[2];
+    __shared__ int s_pq[WH_NMAX + 2];
     __shared__ double s_red[WH_THREADS];
     double *A, *V;
     if (n <= WH_SMEM_NMAX) { A = sm; V = sm + (size_t)n * ld; }
@@ -142,69 +135,7 @@ __global__ void __launch_bounds__(WH_THREADS) whiten_kernel(const __grid_constan
     }
 
     // ---- parallel cyclic Jacobi on the correlation matrix ---------------------------
-    const int n2 = (n + 1) & ~1;            // pad to even with a phantom index n
-    const int npair = n2 / 2;
-    for (int sweep = 0; sweep < 60; ++sweep) {
-        if (tid == 0) s_cnt = 0;
-        __syncthreads();
-        for (int r = 0; r < n2 - 1; ++r) {
-            if (tid == 0) s_rot = 0;
-            __syncthreads();
-            for (int k = tid; k < npair; k += WH_THREADS) {
-                int p, q;
-                rr_pair(n2, r, k, p, q);
-                double c = 1.0, s = 0.0;
-                if (q < n) {
-                    const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
-                    // relative threshold: high relative accuracy for the small eigenvalues
-                    if (fabs(apq) > 1.1102230246251565e-16 * sqrt(fabs(app * aqq)) && apq != 0.0) {
-                        const double tau = (aqq - app) / (2.0 * apq);
-                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                        c = rsqrt(1.0 + t * t);
-                        s = t * c;
-                        s_rot = 1;
-                    }
-                }
-                s_c[k] = c; s_s[k] = s;
-            }
-            __syncthreads();
-            if (s_rot) {
-                // columns: A <- A J, V <- V J
-                for (int e = tid; e < npair * n; e += WH_THREADS) {
-                    const int k = e / n, i = e % n;
-                    const double s = s_s[k];
-                    if (s == 0.0) continue;
-                    int p, q;
-                    rr_pair(n2, r, k, p, q);
-                    const double c = s_c[k];
-                    const double aip = A[i * ld + p], aiq = A[i * ld + q];
-                    A[i * ld + p] = c * aip - s * aiq;
-                    A[i * ld + q] = s * aip + c * aiq;
-                    const double vip = V[i * ld + p], viq = V[i * ld + q];
-                    V[i * ld + p] = c * vip - s * viq;
-                    V[i * ld + q] = s * vip + c * viq;
-                }
-                __syncthreads();
-                // rows: A <- J^T A
-                for (int e = tid; e < npair * n; e += WH_THREADS) {
-                    const int k = e / n, j = e % n;
-                    const double s = s_s[k];
-                    if (s == 0.0) continue;
-                    int p, q;
-                    rr_pair(n2, r, k, p, q);
-                    const double c = s_c[k];
-                    const double apj = A[p * ld + j], aqj = A[q * ld + j];
-                    A[p * ld + j] = c * apj - s * aqj;
-                    A[q * ld + j] = s * apj + c * aqj;
-                }
-                if (tid == 0) s_cnt += 1;
-            }
-            __syncthreads();
-        }
-        if (s_cnt == 0) break;
-        __syncthreads();
-    }
-    __syncthreads();
+    jacobi_diagonalize<WH_THREADS>(A, V, n, ld, 60, s_c, s_s, s_pq, s_flag);
     // eigenvalues (signed), descending order by rank sort
     for (int i = tid; i < n; i += WH_THREADS) val[i] = A[i * ld + i];
     __syncthreads();
@@ -291,6 +222,11 @@ __global__ void __launch_bounds__(WH_THREADS) whiten_kernel(const __grid_constan
 
 using namespace b200lm;
 
+namespace b200lm {
+int whiten_large(int device, int n, const double* d_cov, double svdcut, double* d_w, double* d_cov_out,
+                 int* d_nout, int* d_nmod, double* d_logdet, cudaStream_t stream);
+}
+
 extern "C" int b200lm_whiten(int device, int nblk, const int* h_n, const double* d_cov,
                              double svdcut, double eps, int use_eps,
                              double* d_w, double* d_cov_out, int* d_nout, int* d_nmod, double* d_logdet,
@@ -302,16 +238,33 @@ extern "C" int b200lm_whiten(int device, int nblk, const int* h_n, const double*
     if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
     cudaStream_t s = (cudaStream_t)stream;
     int nmax = 0;
+    bool any_large = false;
     std::vector<long long> off(nblk);
     long long o = 0;
     for (int k = 0; k < nblk; ++k) {
         if (h_n[k] < 1) return set_error(nullptr, B200LM_EINVAL, "block size must be positive");
-        if (h_n[k] > WH_NMAX)
-            return set_error(nullptr, B200LM_ESIZE, "correlated block larger than 512 is not supported by the "
-                                                    "single-CTA Jacobi whitening kernel");
+        if (h_n[k] > WH_NMAX) any_large = true;
         nmax = std::max(nmax, h_n[k]);
         off[k] = o;
         o += (long long)h_n[k] * h_n[k];
+    }
+    if (any_large) {
+        // blocks beyond the single-CTA kernel: one at a time through the block-Jacobi solver
+        for (int k = 0; k < nblk; ++k) {
+            int rc;
+            if (h_n[k] > WH_NMAX) {
+                if (use_eps)
+                    return set_error(nullptr, B200LM_ESIZE, "eps (Cholesky) regulator is not implemented for blocks > 512");
+                rc = whiten_large(device, h_n[k], d_cov + off[k], svdcut, d_w + off[k], d_cov_out + off[k],
+                                  d_nout + k, d_nmod + k, d_logdet + k, s);
+            } else {
+                const int one = h_n[k];
+                rc = b200lm_whiten(device, 1, &one, d_cov + off[k], svdcut, eps, use_eps, d_w + off[k],
+                                   d_cov_out + off[k], d_nout + k, d_nmod + k, d_logdet + k, stream);
+            }
+            if (rc) return rc;
+        }
+        return B200LM_OK;
     }
     int* d_n = nullptr; long long* d_off = nullptr; double* d_work = nullptr;
     e = cudaMalloc((void**)&d_n, nblk * sizeof(int));

@@ -524,3 +524,39 @@ def test_dgemm_vs_torch():
             run(tA, tB, 1, 300, 200, 500, alpha=-0.5, beta=2.0)
     run(False, False, 1, 1, 1, 1)
     run(False, True, 1, 512, 512, 1024)
+
+
+@pytest.mark.parametrize("n,cut", [(600, 1e-8), (1100, 1e-6), (777, -1e-6), (640, 0.0)])
+def test_large_block_whitening_vs_oracle(n, cut):
+    """Blocks beyond the single-CTA kernel (n > 512) go through the block-Jacobi solver
+    (csrc/whiten_large.cu); config-5 style input: a rank-deficient sample covariance."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from oracle.whiten import PDF as OPDF
+    rng = np.random.default_rng(n)
+    ns = n // 2 if cut != 0.0 else 2 * n             # fewer samples than dimensions -> singular
+    idx = np.arange(n)
+    base = np.exp(-np.abs(idx[:, None] - idx[None, :]) / 50.0)
+    L = np.linalg.cholesky(base + 1e-10 * np.eye(n))
+    sig = rng.uniform(0.5, 2.0, size=n) * 1e-3
+    samples = (L @ rng.standard_normal((n, ns))).T * sig[None, :]
+    cov = np.cov(samples.T)
+    mean = np.zeros(n)
+    o = OPDF(mean, cov, svdcut=cut)
+    d = lb.PDF(mean, cov, svdcut=cut)
+    assert d.nmod == o.nmod and d.nchiv == o.nchiv, (d.nmod, o.nmod, d.nchiv, o.nchiv)
+    np.testing.assert_allclose(d.logdet, o.logdet, rtol=1e-7, atol=1e-5)
+    Wd, Wo = d.i_invwgts[1][1], o.i_invwgts[1][1]
+    assert Wd.shape == Wo.shape
+    icd, ico = Wd.T @ Wd, Wo.T @ Wo
+    sc = np.sqrt(np.diag(ico))
+    Dn = np.diag(cov) ** -0.5
+    ev = np.linalg.eigvalsh(cov * Dn[:, None] * Dn[None, :])
+    lo = max(abs(cut) * ev[-1], 1e-300) if cut else np.min(np.abs(ev))
+    tol = max(1e-8, 500 * 2.2e-16 * ev[-1] / lo)
+    assert np.max(np.abs(icd - ico) / (sc[:, None] * sc[None, :])) < tol, tol
+    sc = np.sqrt(np.diag(o.cov))
+    assert np.max(np.abs(d.cov - o.cov) / (sc[:, None] * sc[None, :])) < 1e-10
+    # chi2 of a random residual vector is basis independent
+    v = rng.standard_normal(n) * sig
+    np.testing.assert_allclose(np.sum((Wd @ v) ** 2), np.sum((Wo @ v) ** 2), rtol=1e-6)
