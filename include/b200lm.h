@@ -162,6 +162,28 @@ int b200lm_dgemm(int device, int transA, int transB, int batch, int M, int N, in
                  const double* d_A, long long sA, int lda, const double* d_B, long long sB, int ldb,
                  double beta, double* d_C, long long sC, int ldc, void* stream);
 
+/* ---- dense single-fit path (config 5: np in the thousands) ------------------------------
+ * Multi-exponential correlator with K exponentials: un-whitened model rows at parameters
+ * d_p = [a_0..a_K-1, E_0..E_K-1]:  d_G (ny x 2K, leading dimension ld >= 2K; may be NULL for a
+ * residual-only evaluation) = df/dp,  d_delta[ny] = f(p) - y.  Feeds b200lm_dgemm with the
+ * whitening matrix; replaces fcn(x, p) on GVar object arrays + the delta of
+ * src/lsqfit/_utilities.pyx:76-77. */
+int b200lm_multiexp_dense(int device, int ny, int K, const double* d_t, const double* d_p,
+                          const double* d_y, double* d_G, int ld, double* d_delta, void* stream);
+
+/* Blocked Cholesky  L L^T = A + shift*I  (lower, row-major; d_L may equal d_A).  d_linv receives
+ * the inverted 64 x 64 diagonal blocks (ceil(n/64) * 4096 doubles) used by b200lm_trsm.  *d_info
+ * (device int) = 0 or the 1-based index of the first non-positive pivot.  Stands in for the
+ * per-iteration LAPACK SVD of scipy's trf behind src/lsqfit/_scipy.py:156-161. */
+int b200lm_potrf(int device, int n, const double* d_A, int lda, double shift, double* d_L, int ldl,
+                 double* d_linv, int* d_info, void* stream);
+
+/* Triangular solve with the factor of b200lm_potrf: trans = 0: L X = B, trans = 1: L^T X = B.
+ * B (n x nrhs, row-major) is workspace and is destroyed; X must not alias B.  With B = I twice
+ * this gives the parameter covariance (J^T J)^-1 of src/lsqfit/_scipy.py:171-175. */
+int b200lm_trsm(int device, int n, int nrhs, const double* d_L, int ldl, const double* d_linv, int trans,
+                double* d_B, int ldb, double* d_X, int ldx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,3 +67,30 @@ def eval_flops(ny, npar, K, nchiv=None, dense=True):
     first = 2.0 * ny * ny * (npar + 1) if dense else 2.0 * ny * (npar + 1)
     return (first + 2.0 * nchiv * npar ** 2 + 2.0 * nchiv * npar
             + npar ** 3 / 3.0 + 2.0 * npar ** 2 + ny * K * 6.0)
+
+
+def c5(ny=5000, K=1000, Ns=None, seed=5000, corr_len=50.0, rel_err=1e-3):
+    """Config 5: one large dense fit.  Multi-exponential with K terms on
+    t_i = 8 i / ny, priors a_k = 0.5(4)/sqrt(K), E_k = 0.01(k+1) +- 0.004; the data covariance is the
+    SAMPLE covariance of Ns = ny/2 draws (rank deficient => more than ny/2 modes clamped by the svd
+    cut) from sigma_i sigma_j exp(-|i-j|/corr_len), sigma_i = rel_err |f_i|; svdcut = 1e-8; truth
+    drawn from the prior, data mean = f(truth) + noise with that sample covariance, start = prior mean."""
+    rng = np.random.default_rng(seed)
+    Ns = ny // 2 if Ns is None else Ns
+    t = 8.0 * np.arange(1, ny + 1) / ny
+    prior_mean = np.concatenate([np.full(K, 0.5 / np.sqrt(K)), 0.01 * (np.arange(K) + 1.0)])
+    prior_sdev = np.concatenate([np.full(K, 0.4 / np.sqrt(K)), np.full(K, 0.004)])
+    ptrue = prior_mean + prior_sdev * rng.standard_normal(2 * K)
+    f = (ptrue[None, :K] * np.exp(-ptrue[None, K:] * t[:, None])).sum(axis=1)
+    sig = rel_err * np.abs(f)
+    idx = np.arange(ny)
+    base = sig[:, None] * sig[None, :] * np.exp(-np.abs(idx[:, None] - idx[None, :]) / corr_len)
+    L = np.linalg.cholesky(base + 1e-14 * np.diag(sig ** 2))
+    draws = rng.standard_normal((Ns, ny)) @ L.T
+    draws -= draws.mean(axis=0, keepdims=True)
+    ycov = draws.T @ draws / (Ns - 1)
+    # noise of the mean drawn from the sample covariance itself (lies in the span of the draws)
+    ymean = f + draws.T @ rng.standard_normal(Ns) / np.sqrt(Ns - 1)
+    return dict(K=K, ny=ny, np=2 * K, x=t[:, None], t=t, f=f, ymean=ymean, ycov=ycov, ptrue=ptrue,
+                prior_mean=prior_mean, prior_sdev=prior_sdev, p0=prior_mean.copy(), svdcut=1e-8,
+                tol=(1e-8, 1e-10, 1e-10), maxit=1000, name="C5 large dense fit %dx%d" % (2 * K, ny))

@@ -32,11 +32,12 @@ static cudaError_t launch_al(const GemmArgs& g, int batch, bool aligned, cudaStr
 
 cudaError_t dgemm(bool transA, bool transB, int batch, int M, int N, int K, double alpha,
                   const double* A, long long sA, int lda, const double* B, long long sB, int ldb,
-                  double beta, double* C, long long sC, int ldc, cudaStream_t stream) {
+                  double beta, double* C, long long sC, int ldc, cudaStream_t stream, bool lower) {
     if (batch <= 0 || M <= 0 || N <= 0) return cudaSuccess;
     GemmArgs g;
     g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
     g.A = A; g.sA = sA; g.lda = lda; g.B = B; g.sB = sB; g.ldb = ldb; g.C = C; g.sC = sC; g.ldc = ldc;
+    g.lower = lower ? 1 : 0;
     const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && (lda % 2 == 0) && (ldb % 2 == 0) &&
                          (sA % 2 == 0) && (sB % 2 == 0);
     // A_KC: A stored [M][K]  <=> !transA ;  B_KC: B stored [N][K] <=> transB

@@ -35,6 +35,7 @@ struct GemmArgs {
     const double* A; long long sA; int lda;
     const double* B; long long sB; int ldb;
     double* C; long long sC; int ldc;
+    int lower;   // 1: skip CTA tiles strictly above the diagonal (symmetric rank-k updates)
 };
 
 __device__ __forceinline__ void gemm_dmma(double& c0, double& c1, double a, double b) {
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) dgemm_kernel(const __grid_constan
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;              // 2 x 4 warps
     const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+    if (g.lower && n0 > m0 + GM - 1) return;
     const double* A = g.A + (size_t)blockIdx.z * g.sA;
     const double* B = g.B + (size_t)blockIdx.z * g.sB;
     double* C = g.C + (size_t)blockIdx.z * g.sC;
@@ -182,6 +184,6 @@ inline size_t dgemm_smem_bytes() {
 // transA: C = A^T . (...) with A stored [K][M];  transB: C = (...) . B^T with B stored [N][K]
 cudaError_t dgemm(bool transA, bool transB, int batch, int M, int N, int K, double alpha,
                   const double* A, long long sA, int lda, const double* B, long long sB, int ldb,
-                  double beta, double* C, long long sC, int ldc, cudaStream_t stream);
+                  double beta, double* C, long long sC, int ldc, cudaStream_t stream, bool lower = false);
 
 }  // namespace b200lm

@@ -9,8 +9,8 @@
 // (I, J) in nb-1 rounds of nb/2 disjoint pairs (round-robin tournament); per round
 //   bj_diag : one CTA per pair diagonalises the (<=64)^2 sub-matrix [A_II A_IJ; A_JI A_JJ] exactly
 //             with the shared-memory Jacobi of jacobi_core.cuh and leaves the orthogonal Q_p
-//   bj_cols : A[:, IuJ] <- A[:, IuJ] Q_p  and  V[:, IuJ] <- V[:, IuJ] Q_p   (64-row slabs staged in smem)
-//   bj_rows : A[IuJ, :] <- Q_p^T A[IuJ, :]
+//   bj_tile : A[P, R] <- Q_P^T A[P, R] Q_R for all pairs of pairs P < R, mirrored (A read once per round)
+//   bj_cols : V[:, IuJ] <- V[:, IuJ] Q_p                                  (64-row slabs staged in smem)
 // until the off-diagonal mass is at rounding level.  Eigenvalues keep Jacobi's high relative
 // accuracy, which the svdcut count (nmod) depends on.  Post-processing (sorting, clamp/drop, W,
 // corrected covariance via the DMMA GEMM of dgemm.cuh, logdet) follows the small-block kernel.
@@ -38,35 +38,91 @@ struct BJArgs {
     double* Q;              // [nbe/2][BJ_M][BJ_M]
     double* offsq;          // sum of squares of the off-diagonal blocks met in this sweep
     int* rotated;           // number of pairs whose sub-problem was not yet diagonal in this sweep
+    int* ident;             // [nbe/2] 1 if the pair's Q of this round is the identity
+    int inner;              // Jacobi sweeps per sub-problem visit
 };
 
 __device__ __forceinline__ bool bj_pair(const BJArgs& a, int pair, int& I, int& J, int& nI, int& nJ) {
     rr_pair(a.nbe, a.round, pair, I, J);
-    if (J >= a.nb) return false;                      // phantom block: this pair idles
     nI = min(BJ_B, a.n - I * BJ_B);
-    nJ = min(BJ_B, a.n - J * BJ_B);
+    // phantom partner (odd block count): the real block idles this round, i.e. it is a "pair" of
+    // one block with Q = I -- its rows and columns still receive the other pairs' rotations
+    nJ = J >= a.nb ? 0 : min(BJ_B, a.n - J * BJ_B);
     return true;
 }
 // global column/row index of local index l in the (I, J) pair
 __device__ __forceinline__ int bj_gidx(int l, int I, int J, int nI) { return l < nI ? I * BJ_B + l : J * BJ_B + (l - nI); }
 
+// Two-sided cyclic Jacobi on a 64 x 64 symmetric matrix in shared memory (pitch 65), statically
+// mapped: the 32 disjoint pivot pairs of a round go to 8 lanes each (pair = tid/8); every lane
+// recomputes its pair's rotation from the pivots (no broadcast through memory), then updates 8
+// rows of the two pivot columns of S and Q, then 8 columns of the two pivot rows of S.  Two block
+// barriers per round.  Rotation criterion as in jacobi_core.cuh (relative, so small eigenvalues
+// keep their relative accuracy).  Returns the number of sweeps that rotated something.
+__device__ __forceinline__ int bj_jacobi64(double* S, double* Qs, int max_sweeps) {
+    const int tid = threadIdx.x, k = tid >> 3, sub = tid & 7;
+    int sweeps = 0;
+    for (; sweeps < max_sweeps; ++sweeps) {
+        int any = 0;
+        for (int r = 0; r < BJ_M - 1; ++r) {
+            int p, q;
+            rr_pair(BJ_M, r, k, p, q);
+            const double app = S[p * BJ_LD + p], aqq = S[q * BJ_LD + q], apq = S[p * BJ_LD + q];
+            __syncwarp();                       // all 8 lanes of the pair have the pivots before anyone writes
+            const bool rot = fabs(apq) > 1.1102230246251565e-16 * sqrt(fabs(app * aqq)) && apq != 0.0;
+            double c = 1.0, sn = 0.0;
+            if (rot) {
+                const double tau = (aqq - app) / (2.0 * apq);
+                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                c = rsqrt(1.0 + t * t);
+                sn = t * c;
+#pragma unroll
+                for (int ii = 0; ii < 8; ++ii) {
+                    const int i = sub + 8 * ii;
+                    const double aip = S[i * BJ_LD + p], aiq = S[i * BJ_LD + q];
+                    S[i * BJ_LD + p] = c * aip - sn * aiq;
+                    S[i * BJ_LD + q] = sn * aip + c * aiq;
+                    const double vip = Qs[i * BJ_LD + p], viq = Qs[i * BJ_LD + q];
+                    Qs[i * BJ_LD + p] = c * vip - sn * viq;
+                    Qs[i * BJ_LD + q] = sn * vip + c * viq;
+                }
+            }
+            __syncthreads();
+            if (rot) {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int j = sub + 8 * jj;
+                    const double apj = S[p * BJ_LD + j], aqj = S[q * BJ_LD + j];
+                    S[p * BJ_LD + j] = c * apj - sn * aqj;
+                    S[q * BJ_LD + j] = sn * apj + c * aqj;
+                }
+            }
+            any |= __syncthreads_or(rot ? 1 : 0);
+        }
+        if (!any) break;
+    }
+    return sweeps;
+}
+
 __global__ void __launch_bounds__(BJ_THREADS) bj_diag_kernel(const __grid_constant__ BJArgs a) {
     extern __shared__ double bj_sm[];
     double* S = bj_sm;
     double* Qs = bj_sm + BJ_M * BJ_LD;
-    __shared__ double s_c[BJ_M / 2 + 1], s_s[BJ_M / 2 + 1];
-    __shared__ int s_flag[2];
-    __shared__ int s_pq[BJ_M + 2];
     __shared__ double s_red[BJ_THREADS];
     const int tid = threadIdx.x;
     int I, J, nI, nJ;
     double* Qg = a.Q + (size_t)blockIdx.x * BJ_M * BJ_M;
-    if (!bj_pair(a, blockIdx.x, I, J, nI, nJ)) return;
+    bj_pair(a, blockIdx.x, I, J, nI, nJ);
+    if (nJ == 0) {                                         // idle block
+        if (tid == 0) a.ident[blockIdx.x] = 1;
+        return;
+    }
     const int m = nI + nJ;
     double off = 0.0;
-    for (int e = tid; e < m * m; e += BJ_THREADS) {
-        const int r = e / m, c = e % m;
-        const double v = a.A[(size_t)bj_gidx(r, I, J, nI) * a.ld + bj_gidx(c, I, J, nI)];
+    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        double v = 0.0;
+        if (r < m && c < m) v = a.A[(size_t)bj_gidx(r, I, J, nI) * a.ld + bj_gidx(c, I, J, nI)];
         S[r * BJ_LD + c] = v;
         Qs[r * BJ_LD + c] = (r == c) ? 1.0 : 0.0;
         if (r < nI && c >= nI) off = fma(v, v, off);
@@ -79,23 +135,28 @@ __global__ void __launch_bounds__(BJ_THREADS) bj_diag_kernel(const __grid_consta
     }
     if (tid == 0) atomicAdd(a.offsq, 2.0 * s_red[0]);
     // symmetrise the copy (the global matrix is symmetric up to rounding)
-    for (int e = tid; e < m * m; e += BJ_THREADS) {
-        const int r = e / m, c = e % m;
+    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
+        const int r = e >> 6, c = e & 63;
         if (r < c) { const double v = 0.5 * (S[r * BJ_LD + c] + S[c * BJ_LD + r]); S[r * BJ_LD + c] = v; }
     }
     __syncthreads();
-    for (int e = tid; e < m * m; e += BJ_THREADS) {
-        const int r = e / m, c = e % m;
+    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
+        const int r = e >> 6, c = e & 63;
         if (r > c) S[r * BJ_LD + c] = S[c * BJ_LD + r];
     }
     __syncthreads();
-    // a few inner sweeps per visit are enough: the outer iteration finishes the job, and a full
-    // diagonalisation of every sub-problem is what dominated the first version (sync-latency bound)
-    const int nsw = jacobi_diagonalize<BJ_THREADS>(S, Qs, m, BJ_LD, 3, s_c, s_s, s_pq, s_flag);
-    if (tid == 0 && nsw > 0) atomicAdd(a.rotated, 1);      // this pair still needed rotations
-    for (int e = tid; e < m * m; e += BJ_THREADS) {
-        const int r = e / m, c = e % m;
-        Qg[r * BJ_M + c] = Qs[r * BJ_LD + c];
+    // a few inner sweeps per visit are enough: the outer iteration finishes the job
+    const int nsw = bj_jacobi64(S, Qs, a.inner);
+    if (tid == 0) {
+        a.ident[blockIdx.x] = nsw == 0 ? 1 : 0;            // Q == I: the slab kernels skip this pair
+        if (nsw > 0) atomicAdd(a.rotated, 1);              // this pair still needed rotations
+    }
+    if (nsw == 0) return;
+    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        Qg[e] = Qs[r * BJ_LD + c];
+        // the pair's own diagonal tile: Q^T S Q is what the rotations left in S
+        if (r < m && c < m) a.A[(size_t)bj_gidx(r, I, J, nI) * a.ld + bj_gidx(c, I, J, nI)] = S[r * BJ_LD + c];
     }
 }
 
@@ -110,39 +171,42 @@ __device__ __forceinline__ void bj_dmma(double& c0, double& c1, double a, double
         : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// X[rows, IuJ] <- X[rows, IuJ] . Q   (grid: x = row slab of 64, y = pair).  8 warps: warp w owns
-// output rows 8w..8w+7 of the slab and all 8 column tiles (16 k-steps x 8 DMMA).
-__global__ void __launch_bounds__(BJ_THREADS) bj_cols_kernel(const __grid_constant__ BJArgs a, double* X, int nrows) {
-    extern __shared__ double bj_sm[];
-    double* S = bj_sm;                       // [64][BJ_PA]   A operand: S[r][k]
-    double* Qs = bj_sm + 64 * BJ_PA;         // [BJ_M][BJ_PB] B operand: Q[k][c]
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    int I, J, nI, nJ;
-    if (!bj_pair(a, blockIdx.y, I, J, nI, nJ)) return;
-    const int m = nI + nJ;
-    const int r0 = blockIdx.x * 64;
-    const int nr = min(64, nrows - r0);
-    const double* Qg = a.Q + (size_t)blockIdx.y * BJ_M * BJ_M;
-    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
-        const int r = e / BJ_M, c = e % BJ_M;
-        Qs[r * BJ_PB + c] = (r < m && c < m) ? Qg[r * BJ_M + c] : 0.0;
-    }
-    for (int e = tid; e < 64 * BJ_M; e += BJ_THREADS) {
-        const int r = e / BJ_M, c = e % BJ_M;
-        S[r * BJ_PA + c] = (r < nr && c < m) ? X[(size_t)(r0 + r) * a.ld + bj_gidx(c, I, J, nI)] : 0.0;
-    }
-    __syncthreads();
-    double acc[8][2];
+// 64 x 64 x 64 product of an A operand (pitch BJ_PA, [row][k]) and a B operand (pitch BJ_PB, [k][col]):
+// warp w owns output rows 8w..8w+7 and all 8 column tiles (16 k-steps x 8 DMMA).
+__device__ __forceinline__ void bj_mma64(const double* Aop, const double* Bop, int w, int lane, double (&acc)[8][2]) {
 #pragma unroll
     for (int t = 0; t < 8; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
-    const double* sa = S + (8 * w + (lane >> 2)) * BJ_PA + (lane & 3);
-    const double* qb = Qs + (lane & 3) * BJ_PB + (lane >> 2);
+    const double* sa = Aop + (8 * w + (lane >> 2)) * BJ_PA + (lane & 3);
+    const double* qb = Bop + (lane & 3) * BJ_PB + (lane >> 2);
 #pragma unroll 4
     for (int k4 = 0; k4 < BJ_M; k4 += 4) {
         const double af = sa[k4];
 #pragma unroll
         for (int t = 0; t < 8; ++t) bj_dmma(acc[t][0], acc[t][1], af, qb[k4 * BJ_PB + 8 * t]);
     }
+}
+
+// V[rows, IuJ] <- V[rows, IuJ] . Q   (grid: x = row slab of 64, y = pair).
+__global__ void __launch_bounds__(BJ_THREADS) bj_cols_kernel(const __grid_constant__ BJArgs a, double* X, int nrows) {
+    extern __shared__ double bj_sm[];
+    double* S = bj_sm;                       // [64][BJ_PA]   A operand: S[r][k]
+    double* Qs = bj_sm + 64 * BJ_PA;         // [BJ_M][BJ_PB] B operand: Q[k][c]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int I, J, nI, nJ;
+    bj_pair(a, blockIdx.y, I, J, nI, nJ);
+    if (a.ident[blockIdx.y]) return;
+    const int m = nI + nJ;
+    const int r0 = blockIdx.x * 64;
+    const int nr = min(64, nrows - r0);
+    const double* Qg = a.Q + (size_t)blockIdx.y * BJ_M * BJ_M;
+    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        Qs[r * BJ_PB + c] = (r < m && c < m) ? Qg[e] : 0.0;
+        S[r * BJ_PA + c] = (r < nr && c < m) ? X[(size_t)(r0 + r) * a.ld + bj_gidx(c, I, J, nI)] : 0.0;
+    }
+    __syncthreads();
+    double acc[8][2];
+    bj_mma64(S, Qs, w, lane, acc);
     __syncthreads();
     // C fragment -> slab (row 8w + lane/4, cols 8t + 2(lane%4) + {0,1})
 #pragma unroll
@@ -151,55 +215,60 @@ __global__ void __launch_bounds__(BJ_THREADS) bj_cols_kernel(const __grid_consta
         d[0] = acc[t][0]; d[1] = acc[t][1];
     }
     __syncthreads();
-    for (int e = tid; e < nr * m; e += BJ_THREADS) {
-        const int rr = e / m, c = e % m;
-        X[(size_t)(r0 + rr) * a.ld + bj_gidx(c, I, J, nI)] = S[rr * BJ_PA + c];
+    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        if (r < nr && c < m) X[(size_t)(r0 + r) * a.ld + bj_gidx(c, I, J, nI)] = S[r * BJ_PA + c];
     }
 }
 
-// A[IuJ, cols] <- Q^T . A[IuJ, cols]   (grid: x = column slab of 64, y = pair).  Warp w owns output
-// rows 8w..8w+7 (rows of Q^T = columns of Q) and all 8 column tiles.
-__global__ void __launch_bounds__(BJ_THREADS) bj_rows_kernel(const __grid_constant__ BJArgs a) {
+// A[P-rows, R-cols] <- Q_P^T . A[P-rows, R-cols] . Q_R  for every pair of pairs P < R of this round
+// (grid: x = R, y = P), written back together with its mirror image, so A is read once and stays
+// exactly symmetric.  The diagonal tiles P == R are written by bj_diag_kernel.
+__global__ void __launch_bounds__(BJ_THREADS) bj_tile_kernel(const __grid_constant__ BJArgs a) {
     extern __shared__ double bj_sm[];
-    double* Qt = bj_sm;                      // [BJ_M][BJ_PA]  A operand: Qt[r][k] = Q[k][r]
-    double* S = bj_sm + BJ_M * BJ_PA;        // [BJ_M][BJ_PB]  B operand: S[k][c]
+    double* S = bj_sm;                              // [64][BJ_PA]  tile (A operand), later the result
+    double* B2 = bj_sm + BJ_M * BJ_PA;              // [64][BJ_PB]  Q_R (B operand), later T = tile . Q_R
+    double* Qt = B2 + BJ_M * BJ_PB;                 // [64][BJ_PA]  Q_P^T (A operand)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    int I, J, nI, nJ;
-    if (!bj_pair(a, blockIdx.y, I, J, nI, nJ)) return;
-    const int m = nI + nJ;
-    const int c0 = blockIdx.x * 64;
-    const int nc = min(64, a.n - c0);
-    const double* Qg = a.Q + (size_t)blockIdx.y * BJ_M * BJ_M;
+    const int P = blockIdx.y, R = blockIdx.x;
+    if (P >= R) return;
+    int IP, JP, nIP, nJP, IR, JR, nIR, nJR;
+    bj_pair(a, P, IP, JP, nIP, nJP);
+    bj_pair(a, R, IR, JR, nIR, nJR);
+    const bool idP = a.ident[P] != 0, idR = a.ident[R] != 0;
+    if (idP && idR) return;
+    const int mP = nIP + nJP, mR = nIR + nJR;
+    const double* QP = a.Q + (size_t)P * BJ_M * BJ_M;
+    const double* QR = a.Q + (size_t)R * BJ_M * BJ_M;
     for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
-        const int k = e / BJ_M, r = e % BJ_M;          // coalesced read of Q[k][r]
-        Qt[r * BJ_PA + k] = (r < m && k < m) ? Qg[k * BJ_M + r] : 0.0;
-    }
-    for (int e = tid; e < BJ_M * 64; e += BJ_THREADS) {
-        const int r = e / 64, c = e % 64;
-        S[r * BJ_PB + c] = (r < m && c < nc) ? a.A[(size_t)bj_gidx(r, I, J, nI) * a.ld + c0 + c] : 0.0;
+        const int r = e >> 6, c = e & 63;
+        S[r * BJ_PA + c] = (r < mP && c < mR) ? a.A[(size_t)bj_gidx(r, IP, JP, nIP) * a.ld + bj_gidx(c, IR, JR, nIR)] : 0.0;
+        B2[r * BJ_PB + c] = idR ? (r == c ? 1.0 : 0.0) : ((r < mR && c < mR) ? QR[e] : 0.0);
+        // Qt[c][r] = Q_P[r][c]
+        Qt[c * BJ_PA + r] = idP ? (r == c ? 1.0 : 0.0) : ((r < mP && c < mP) ? QP[e] : 0.0);
     }
     __syncthreads();
     double acc[8][2];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
-    const double* qa = Qt + (8 * w + (lane >> 2)) * BJ_PA + (lane & 3);
-    const double* sb = S + (lane & 3) * BJ_PB + (lane >> 2);
-#pragma unroll 4
-    for (int k4 = 0; k4 < BJ_M; k4 += 4) {
-        const double af = qa[k4];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) bj_dmma(acc[t][0], acc[t][1], af, sb[k4 * BJ_PB + 8 * t]);
-    }
+    bj_mma64(S, B2, w, lane, acc);                  // T = tile . Q_R
     __syncthreads();
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-        double* d = S + (8 * w + (lane >> 2)) * BJ_PB + 8 * t + 2 * (lane & 3);
+        double* d = B2 + (8 * w + (lane >> 2)) * BJ_PB + 8 * t + 2 * (lane & 3);
         d[0] = acc[t][0]; d[1] = acc[t][1];
     }
     __syncthreads();
-    for (int e = tid; e < m * nc; e += BJ_THREADS) {
-        const int rr = e / nc, cc = e % nc;
-        a.A[(size_t)bj_gidx(rr, I, J, nI) * a.ld + c0 + cc] = S[rr * BJ_PB + cc];
+    bj_mma64(Qt, B2, w, lane, acc);                 // out = Q_P^T . T
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        double* d = S + (8 * w + (lane >> 2)) * BJ_PA + 8 * t + 2 * (lane & 3);
+        d[0] = acc[t][0]; d[1] = acc[t][1];
+    }
+    __syncthreads();
+    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        if (r < mP && c < mR) a.A[(size_t)bj_gidx(r, IP, JP, nIP) * a.ld + bj_gidx(c, IR, JR, nIR)] = S[r * BJ_PA + c];
+        // mirror: row index from the R pair (e >> 6), column index from the P pair (e & 63)
+        if (c < mP && r < mR) a.A[(size_t)bj_gidx(r, IR, JR, nIR) * a.ld + bj_gidx(c, IP, JP, nIP)] = S[c * BJ_PA + r];
     }
 }
 
@@ -253,11 +322,11 @@ int whiten_large(int device, int n, const double* d_cov, double svdcut, double* 
     const int ld = (n + 1) & ~1;                     // even leading dimension (aligned GEMM path)
     const int nb = (n + BJ_B - 1) / BJ_B, nbe = (nb + 1) & ~1, npairs = nbe / 2;
     double *A = nullptr, *V = nullptr, *Q = nullptr, *Dv = nullptr, *val = nullptr, *offsq = nullptr;
-    int* d_rot = nullptr;
+    int* d_rot = nullptr; int* d_ident = nullptr;
     double *T = nullptr, *U = nullptr, *G = nullptr, *d_used = nullptr, *d_wgt = nullptr;
     int *d_order = nullptr, *d_sel = nullptr;
     auto cleanup = [&]() {
-        cudaFree(A); cudaFree(V); cudaFree(Q); cudaFree(Dv); cudaFree(val); cudaFree(offsq); cudaFree(d_rot);
+        cudaFree(A); cudaFree(V); cudaFree(Q); cudaFree(Dv); cudaFree(val); cudaFree(offsq); cudaFree(d_rot); cudaFree(d_ident);
         cudaFree(T); cudaFree(U); cudaFree(G); cudaFree(d_used); cudaFree(d_wgt); cudaFree(d_order); cudaFree(d_sel);
     };
     WL_TRY(cudaMalloc((void**)&A, (size_t)n * ld * sizeof(double)));
@@ -267,18 +336,21 @@ int whiten_large(int device, int n, const double* d_cov, double svdcut, double* 
     WL_TRY(cudaMalloc((void**)&val, n * sizeof(double)));
     WL_TRY(cudaMalloc((void**)&offsq, sizeof(double)));
     WL_TRY(cudaMalloc((void**)&d_rot, sizeof(int)));
+    WL_TRY(cudaMalloc((void**)&d_ident, npairs * sizeof(int)));
     const size_t sm_diag = 2 * (size_t)BJ_M * BJ_LD * sizeof(double);
     const size_t sm_slab = ((size_t)BJ_M * BJ_PA + (size_t)BJ_M * BJ_PB) * sizeof(double);
     WL_TRY(cudaFuncSetAttribute(bj_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_diag));
     WL_TRY(cudaFuncSetAttribute(bj_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_slab));
-    WL_TRY(cudaFuncSetAttribute(bj_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_slab));
+    const size_t sm_tile = (2 * (size_t)BJ_M * BJ_PA + (size_t)BJ_M * BJ_PB) * sizeof(double);
+    WL_TRY(cudaFuncSetAttribute(bj_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_tile));
     const int tpb = 256;
     const unsigned gnn = (unsigned)(((size_t)n * n + tpb - 1) / tpb);
     wl_init_kernel<<<gnn, tpb, 0, s>>>(d_cov, n, A, V, ld, Dv);
     WL_TRY(cudaGetLastError());
 
     BJArgs a;
-    a.A = A; a.V = V; a.n = n; a.ld = ld; a.nb = nb; a.nbe = nbe; a.Q = Q; a.offsq = offsq; a.rotated = d_rot; a.round = 0;
+    a.A = A; a.V = V; a.n = n; a.ld = ld; a.nb = nb; a.nbe = nbe; a.Q = Q; a.offsq = offsq; a.rotated = d_rot; a.round = 0; a.ident = d_ident;
+    a.inner = getenv("B200LM_BJ_INNER") ? atoi(getenv("B200LM_BJ_INNER")) : 3;
     const dim3 gslab((n + 63) / 64, npairs);
     // ||corr||_F^2 <= n^2 (unit diagonal, |corr_ij| <= 1): convergence relative to n (trace)
     const double tol = (double)n * 1e-30 * n;         // off^2 <= (1e-15)^2 * n * trace-ish
@@ -289,9 +361,8 @@ int whiten_large(int device, int n, const double* d_cov, double svdcut, double* 
         for (int r = 0; r < nbe - 1; ++r) {
             a.round = r;
             bj_diag_kernel<<<npairs, BJ_THREADS, sm_diag, s>>>(a);
-            bj_cols_kernel<<<gslab, BJ_THREADS, sm_slab, s>>>(a, A, n);
+            bj_tile_kernel<<<dim3(npairs, npairs), BJ_THREADS, sm_tile, s>>>(a);
             bj_cols_kernel<<<gslab, BJ_THREADS, sm_slab, s>>>(a, V, n);
-            bj_rows_kernel<<<gslab, BJ_THREADS, sm_slab, s>>>(a);
         }
         WL_TRY(cudaGetLastError());
         double h_off = 0.0;

@@ -1,0 +1,428 @@
+"""One LARGE fit spread over the whole GPU (BASELINE config 5: 2000 params x 5000 correlated data).
+
+The batched engine (engine.py / csrc/lm_kernel.cuh) gives one warp to each fit and keeps J^T J in
+registers; that stops making sense when a single Jacobian is 5000 x 2000.  ``DenseFit`` runs the
+same pipeline -- whiten (reference src/lsqfit/__init__.py:1895-1900) -> residual + Jacobian
+(src/lsqfit/_utilities.pyx:65-94) -> trust-region Levenberg-Marquardt with the decisions of scipy's
+unbounded TRF (the solver behind src/lsqfit/_scipy.py:156-161) -> covariance and fit.p propagation
+(src/lsqfit/_scipy.py:171-175, src/lsqfit/__init__.py:897-922) -- with every O(n^3) / O(n^2) step
+on our own kernels through the C ABI:
+
+    whitening              b200lm_whiten      (block-Jacobi eigensolver, csrc/whiten_large.cu)
+    model rows [G|delta]   b200lm_multiexp_dense
+    W.G, J^T J, J^T f, ... b200lm_dgemm       (FP64 DMMA GEMM)
+    chol(d J^T J d + aI)   b200lm_potrf       (blocked, DMMA trailing updates)
+    secular-equation solves, (J^T J)^-1        b200lm_trsm
+
+The trust-region control flow (a few dozen scalar decisions per iteration) runs on the host; torch
+is used for buffers and for O(n) / O(n^2) element-wise glue only.  There is no CPU fallback.
+"""
+import ctypes as C
+import time
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .engine import STOPPING_CRITERION, normalize_tol
+from .whiten import PDF
+
+
+class _LA(object):
+    """Thin torch-tensor wrappers over the dense C-ABI entry points."""
+
+    def __init__(self, device):
+        if not torch.cuda.is_available():
+            raise RuntimeError("lsqfit_b200.dense: no CUDA device visible; there is no CPU fallback")
+        self.device = int(device)
+        self.tdev = torch.device("cuda", self.device)
+        self.launches = 0
+
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    def empty(self, *shape):
+        return torch.empty(shape, dtype=torch.float64, device=self.tdev)
+
+    def gemm(self, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, Cm, ldc):
+        _cabi.check(_cabi.lib.b200lm_dgemm(self.device, int(transA), int(transB), 1, M, N, K, float(alpha),
+                                           A.data_ptr(), 0, lda, B.data_ptr(), 0, ldb, float(beta),
+                                           Cm.data_ptr(), 0, ldc, self.stream()))
+        self.launches += 1
+
+    def mm(self, A, B, transA=False, transB=False, out=None, alpha=1.0, beta=0.0):
+        """out = alpha * op(A) . op(B) + beta * out for contiguous 2-D (or 1-D = column) tensors."""
+        A2 = A if A.dim() == 2 else A.unsqueeze(1)
+        B2 = B if B.dim() == 2 else B.unsqueeze(1)
+        M, K = (A2.shape[1], A2.shape[0]) if transA else A2.shape
+        N = B2.shape[0] if transB else B2.shape[1]
+        assert (B2.shape[1] if transB else B2.shape[0]) == K
+        if out is None:
+            out = self.empty(M, N) if (B.dim() == 2 or transB) else self.empty(M)
+        self.gemm(transA, transB, M, N, K, alpha, A2, A2.stride(0), B2, B2.stride(0), beta, out,
+                  out.stride(0) if out.dim() == 2 else 1)
+        return out
+
+    def potrf(self, A, shift, L, linv, info):
+        n = A.shape[0]
+        _cabi.check(_cabi.lib.b200lm_potrf(self.device, n, A.data_ptr(), A.stride(0), float(shift), L.data_ptr(),
+                                           L.stride(0), linv.data_ptr(), info.data_ptr(), self.stream()))
+        self.launches += 3 * ((n + 63) // 64)
+        return int(info.item()) == 0
+
+    def trsm(self, L, linv, trans, B, X):
+        n = L.shape[0]
+        nrhs = 1 if B.dim() == 1 else B.shape[1]
+        _cabi.check(_cabi.lib.b200lm_trsm(self.device, n, nrhs, L.data_ptr(), L.stride(0), linv.data_ptr(), int(trans),
+                                          B.data_ptr(), nrhs if B.dim() == 1 else B.stride(0),
+                                          X.data_ptr(), nrhs if X.dim() == 1 else X.stride(0), self.stream()))
+        self.launches += 2 * ((n + 63) // 64)
+        return X
+
+
+class DenseFit(object):
+    """Least-squares fit of one large multi-exponential model ``f(t) = sum_k a_k exp(-E_k t)``,
+    parameters ``p = [a_0..a_{K-1}, E_0..E_{K-1}]``, to correlated data with Gaussian priors.
+
+    ``data = (t, ymean, ycov)``; ``prior = (pmean, psdev)`` (independent priors).  Attributes follow
+    the reference's ``nonlinear_fit`` (src/lsqfit/__init__.py:665-725): ``pmean psdev cov chi2 dof Q
+    logGBF nit stopping_criterion error svdcut svdn time``; ``p_cov`` / ``D`` are the propagated
+    covariance and derivative matrix of ``fit.p`` (``_getp``, :897-922).
+    """
+
+    def __init__(self, data, prior, p0=None, svdcut=1e-12, eps=None, tol=1e-8, maxit=1000, scaler="more",
+                 polish=0, device=0, pdf=None):
+        t, ymean, ycov = data
+        pm, psd = prior
+        la = self.la = _LA(device)
+        self.t = np.asarray(t, dtype=float).reshape(-1)
+        ymean = np.asarray(ymean, dtype=float).reshape(-1)
+        pm = np.asarray(pm, dtype=float).reshape(-1)
+        psd = np.asarray(psd, dtype=float).reshape(-1)
+        self.ny, self.np = ymean.size, pm.size
+        if self.np % 2:
+            raise ValueError("multiexp needs an even number of parameters [a..., E...]")
+        self.K = self.np // 2
+        self.tol = normalize_tol(tol)
+        self.maxit = int(maxit)
+        self.scaler = scaler
+        self.times = {}
+        t0 = time.perf_counter()
+        # ---- whitening of the data block(s) on the device (a-1) ----
+        dev = la.tdev
+        ycov = None if ycov is None else np.asarray(ycov, dtype=float)
+        if pdf is None and ycov.ndim == 2 and np.count_nonzero(ycov) == ycov.size:
+            # one fully correlated block: W and the corrected covariance never leave the device
+            from .whiten import whiten_blocks
+            if svdcut is not None:
+                eps = None
+            W, Cc, nout, nmod, logdet = whiten_blocks([self.ny], ycov.reshape(-1), svdcut, eps, device, as_torch=True)
+            nd = int(nout[0])
+            self.Wd = W[:nd * self.ny].view(nd, self.ny)
+            self._Cd = Cc.view(self.ny, self.ny)
+            self.svdcut, self.eps, self.svdn = svdcut, eps, int(nmod[0])
+            data_logdet = float(logdet[0])
+            data_mean = ymean
+        else:
+            if pdf is None:
+                pdf = PDF(ymean, ycov, svdcut=svdcut, eps=eps, device=device)
+            self.svdcut, self.eps, self.svdn = pdf.svdcut, pdf.eps, pdf.nmod
+            nd = pdf.nchiv
+            Wd = np.zeros((nd, self.ny))
+            idx0, w0 = pdf.i_invwgts[0]
+            Wd[np.arange(len(idx0)), idx0] = w0
+            r = len(idx0)
+            for idx, Wk in pdf.i_invwgts[1:]:
+                Wd[r:r + Wk.shape[0], idx] = Wk
+                r += Wk.shape[0]
+            self.Wd = torch.as_tensor(Wd).to(dev)
+            self._Cd = torch.as_tensor(pdf.cov).to(dev)
+            data_logdet = pdf.logdet
+            data_mean = pdf.mean
+        torch.cuda.synchronize(dev)
+        self.times["whiten"] = time.perf_counter() - t0
+        self.pdf = pdf
+        self.nd = nd
+        self.d_t = torch.as_tensor(self.t).to(dev)
+        self.d_y = torch.as_tensor(np.ascontiguousarray(data_mean)).to(dev)
+        self.d_pm = torch.as_tensor(pm).to(dev)
+        self.d_wp = torch.as_tensor(1.0 / psd).to(dev)
+        self.prior_mean, self.prior_sdev = pm, psd
+        self.logdet_pdf = data_logdet + 2.0 * float(np.sum(np.log(psd)))
+        self.nchiv = nd + self.np
+        self.dof = self.nchiv - self.np
+        # ---- workspaces ----
+        n = self.np
+        self.G = la.empty(self.ny, n)
+        self.delta = la.empty(self.ny)
+        self.J = la.empty(nd, n)
+        self.A = la.empty(n, n)
+        self.As = la.empty(n, n)
+        self.L = la.empty(n, n)
+        self.linv = la.empty((n + 63) // 64, 64, 64)
+        self.info = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.polish = int(polish)
+        x0 = pm.copy() if p0 is None else np.asarray(p0, dtype=float).reshape(-1)
+        t0 = time.perf_counter()
+        self._fit(torch.as_tensor(x0).to(dev))
+        torch.cuda.synchronize(dev)
+        self.times["fit"] = time.perf_counter() - t0
+        self._p_cov = self._D = None
+
+    # ---- residuals and Jacobian (a-2) -------------------------------------------------------
+    def _model(self, p, with_G):
+        la = self.la
+        _cabi.check(_cabi.lib.b200lm_multiexp_dense(
+            la.device, self.ny, self.K, self.d_t.data_ptr(), p.data_ptr(), self.d_y.data_ptr(),
+            self.G.data_ptr() if with_G else None, self.G.stride(0), self.delta.data_ptr(), la.stream()))
+        la.launches += 1
+
+    def residual(self, p):
+        """(f_data [nd], f_prior [np]) = whitened residuals at p."""
+        self._model(p, False)
+        fd = self.la.mm(self.Wd, self.delta)
+        fp = (p - self.d_pm) * self.d_wp
+        return fd, fp
+
+    def jacobian(self, p):
+        """Evaluates J_data = W.G into self.J, the normal matrix into self.A; returns (fd, fp, g)."""
+        la = self.la
+        self._model(p, True)
+        fd = la.mm(self.Wd, self.delta)
+        la.mm(self.Wd, self.G, out=self.J)
+        la.mm(self.J, self.J, transA=True, out=self.A)
+        self.A.diagonal().add_(self.d_wp ** 2)
+        fp = (p - self.d_pm) * self.d_wp
+        g = la.mm(self.J, fd, transA=True) + self.d_wp * fp
+        self.nfev_jac += 1
+        return fd, fp, g
+
+    # ---- trust-region sub-problem -------------------------------------------------------------
+    def _factor_solve(self, alpha, gs):
+        """chol(As + alpha I); p = -(As + alpha I)^-1 gs; returns (ok, p, |p|, |L^-1 p|^2)."""
+        la = self.la
+        ok = la.potrf(self.As, alpha, self.L, self.linv, self.info)
+        self.nfac += 1
+        if not ok:
+            return False, None, 0.0, 0.0
+        b = -gs
+        y = la.trsm(self.L, self.linv, 0, b, torch.empty_like(b))
+        p = la.trsm(self.L, self.linv, 1, y, torch.empty_like(b))
+        w = la.trsm(self.L, self.linv, 0, p.clone(), torch.empty_like(b))
+        pn = float(torch.linalg.vector_norm(p))
+        w2 = float(torch.dot(w, w))
+        return True, p, pn, w2
+
+    def _solve_tr(self, gs, Delta, alpha, cache):
+        """Levenberg parameter by safeguarded Newton on the secular equation |p(alpha)| = Delta
+        (decisions of scipy common.py: solve_lsq_trust_region; Cholesky instead of SVD)."""
+        if "gn" not in cache:
+            cache["gn"] = self._factor_solve(0.0, gs)
+        ok0, p0, pn0, w20 = cache["gn"]
+        if ok0 and pn0 <= Delta:
+            return p0, 0.0
+        alpha_upper = float(torch.linalg.vector_norm(gs)) / Delta
+        alpha_lower = 0.0
+        if ok0:
+            alpha_lower = (pn0 - Delta) * pn0 / w20
+        if alpha == 0.0 or alpha is None:
+            alpha = max(0.001 * alpha_upper, (alpha_lower * alpha_upper) ** 0.5)
+        p = None
+        for _ in range(10):
+            if alpha < alpha_lower or alpha > alpha_upper:
+                alpha = max(0.001 * alpha_upper, (alpha_lower * alpha_upper) ** 0.5)
+            ok, p_try, pn, w2 = self._factor_solve(alpha, gs)
+            if not ok:
+                alpha_lower = max(alpha_lower, alpha)
+                alpha = max(2 * alpha, 0.001 * alpha_upper)
+                continue
+            p = p_try
+            phi = pn - Delta
+            if phi < 0:
+                alpha_upper = alpha
+            ratio = -phi * pn / w2
+            alpha_lower = max(alpha_lower, alpha - ratio)
+            alpha_used = alpha
+            alpha -= (phi + Delta) * ratio / Delta
+            if abs(phi) < 0.1 * Delta:
+                self._alpha_used = alpha_used
+                break
+        if p is None:
+            raise FloatingPointError("normal matrix is not positive definite at any damping")
+        return p * (Delta / float(torch.linalg.vector_norm(p))), alpha
+
+    # ---- the fit (a-3) ---------------------------------------------------------------------
+    def _fit(self, x):
+        la = self.la
+        xtol, gtol, ftol = self.tol
+        self.nfev_jac = self.nfac = 0
+        fd, fp, g = self.jacobian(x)
+        nfev = 1
+        cost = 0.5 * float(fd @ fd + fp @ fp)
+        more = self.scaler == "more"
+
+        def colnorm():
+            return torch.sqrt(torch.sum(self.J * self.J, dim=0) + self.d_wp ** 2)
+        if more:
+            scale_inv = colnorm()
+            scale_inv[scale_inv == 0] = 1.0
+        else:
+            scale_inv = torch.ones_like(x)
+        Delta = float(torch.linalg.vector_norm(x * scale_inv)) or 1.0
+        alpha = 0.0
+        status = None
+        error = None
+        while True:
+            if float(torch.max(torch.abs(g))) < gtol:
+                status = 1
+            if status is not None or nfev >= self.maxit:
+                break
+            d = 1.0 / scale_inv
+            torch.mul(self.A, d[:, None] * d[None, :], out=self.As)
+            gs = d * g
+            cache = {}
+            actual = -1.0
+            while actual <= 0 and nfev < self.maxit:
+                step_h, alpha = self._solve_tr(gs, Delta, alpha, cache)
+                As_step = la.mm(self.As, step_h)
+                predicted = -float(0.5 * (step_h @ As_step) + gs @ step_h)
+                step = d * step_h
+                x_new = x + step
+                fd_new, fp_new = self.residual(x_new)
+                nfev += 1
+                shn = float(torch.linalg.vector_norm(step_h))
+                cost_new = 0.5 * float(fd_new @ fd_new + fp_new @ fp_new)
+                if not np.isfinite(cost_new):
+                    Delta = 0.25 * shn
+                    continue
+                actual = cost - cost_new
+                if predicted > 0:
+                    ratio = actual / predicted
+                elif predicted == actual == 0:
+                    ratio = 1.0
+                else:
+                    ratio = 0.0
+                Delta_new = Delta
+                if ratio < 0.25:
+                    Delta_new = 0.25 * shn
+                elif ratio > 0.75 and shn > 0.95 * Delta:
+                    Delta_new = 2.0 * Delta
+                step_norm = float(torch.linalg.vector_norm(step))
+                ft = actual < ftol * cost and ratio > 0.25
+                xt = step_norm < xtol * (xtol + float(torch.linalg.vector_norm(x)))
+                if ft and xt:
+                    status = 4
+                elif ft:
+                    status = 2
+                elif xt:
+                    status = 3
+                if status is not None:
+                    break
+                alpha *= Delta / Delta_new
+                Delta = Delta_new
+            if actual > 0:
+                x, cost = x_new, cost_new
+                fd, fp, g = self.jacobian(x)
+                if more:
+                    scale_inv = torch.maximum(scale_inv, colnorm())
+        if status is None:
+            status = 0
+            error = "maxit=%d iterations exceeded" % self.maxit
+        # ---- optional Gauss-Newton polish towards the exact stationary point ----
+        # (same rule as the batched kernel: a full GN step is kept while the Newton decrement shrinks)
+        d = 1.0 / scale_inv
+        dd = d[:, None] * d[None, :]
+
+        def gn(g):
+            torch.mul(self.A, dd, out=self.As)
+            ok, sh, _, _ = self._factor_solve(0.0, d * g)
+            return ok, sh, (-float((d * g) @ sh) if ok else np.inf)
+        if self.polish > 0:
+            ok, sh, dec = gn(g)
+            for _ in range(self.polish):
+                if not ok or not (dec > 1e-30 * max(1.0, 2 * cost)):
+                    break
+                x_old = x
+                x = x + d * sh
+                fd, fp, g = self.jacobian(x)
+                nfev += 1
+                ok2, sh2, dec2 = gn(g)
+                if not ok2 or not (dec2 < dec):
+                    x = x_old
+                    fd, fp, g = self.jacobian(x)
+                    break
+                sh, dec = sh2, dec2
+        # ---- results (a-5; src/lsqfit/__init__.py:665-682, 706-725) ----
+        self.nit = nfev
+        self.status = status
+        self.stopping_criterion = STOPPING_CRITERION[status]
+        self.error = error
+        self.x = x
+        self.pmean = x.cpu().numpy()
+        self.f = torch.cat([fd, fp])
+        self.chi2 = float(fd @ fd + fp @ fp)
+        from .fit import gammaQ, _logGBF
+        self.Q = float(gammaQ(self.dof / 2.0, self.chi2 / 2.0))
+        # covariance (J^T J)^-1 by CholeskyQR2: the Cholesky factor of the (scaled) normal matrix
+        # alone loses cond(J)^2 eps; one re-orthogonalisation pass  Q1 = Js L^-T,  L2 L2^T = Q1^T Q1,
+        # R = L2^T L^T  restores the cond(J) eps accuracy of the reference's SVD of J
+        # (src/lsqfit/_scipy.py:171-175) using nothing but GEMMs and the blocked Cholesky.
+        torch.mul(self.A, dd, out=self.As)
+        if not la.potrf(self.As, 0.0, self.L, self.linv, self.info):
+            self.error = "normal matrix not positive definite at the solution"
+            self.cov = None
+            return
+        n = self.np
+        eye = torch.eye(n, dtype=torch.float64, device=la.tdev)
+        X = la.trsm(self.L, self.linv, 0, eye, la.empty(n, n))           # X = L^-1
+        logdet = 2.0 * float(torch.sum(torch.log(torch.diagonal(self.L))))
+        Js = self.J * d[None, :]
+        Q1 = la.mm(Js, X, transB=True)                                   # data rows of Q1
+        del Js
+        A2 = la.mm(Q1, Q1, transA=True)
+        del Q1
+        Xp = X * (self.d_wp * d)[None, :]                                # prior rows: diag(wp d) X^T
+        la.mm(Xp, Xp, transB=True, out=A2, beta=1.0)
+        if la.potrf(A2, 0.0, self.L, self.linv, self.info):
+            eye = torch.eye(n, dtype=torch.float64, device=la.tdev)
+            X2 = la.trsm(self.L, self.linv, 0, eye, la.empty(n, n))
+            logdet += 2.0 * float(torch.sum(torch.log(torch.diagonal(self.L))))
+            X = la.mm(X2, X)
+        cov_s = la.mm(X, X, transA=True)
+        self.d_cov = cov_s * dd
+        self.cov = self.d_cov.cpu().numpy()
+        self.psdev = np.sqrt(np.diag(self.cov))
+        self.logdet_JtJ = logdet - 2.0 * float(torch.sum(torch.log(d)))
+        self.logGBF = _logGBF(self.logdet_JtJ, self.logdet_pdf, self.chi2, self.dof)
+
+    # ---- fit.p propagation (a-6; src/lsqfit/__init__.py:897-922) ------------------------------
+    def propagate(self):
+        """D = cov . J^T . W  (np x N) and cov(p) = D . C . D^T with the svd-corrected C."""
+        la = self.la
+        t0 = time.perf_counter()
+        n, ny = self.np, self.ny
+        M = la.mm(self.d_cov, self.J, transB=True)               # np x nd   = cov . J_data^T
+        Dd = la.mm(M, self.Wd)                                   # np x ny
+        Dp = self.d_cov * self.d_wp[None, :] ** 2                # cov . diag(wp) . diag(wp)
+        Cd = self._Cd                                            # svd-corrected data covariance
+        T = la.mm(Dd, Cd)
+        covp = la.mm(T, Dd, transB=True)
+        Dps = Dp * torch.as_tensor(self.prior_sdev).to(la.tdev)[None, :]
+        la.mm(Dps, Dps, transB=True, out=covp, beta=1.0)
+        torch.cuda.synchronize(la.tdev)
+        self.times["propagate"] = time.perf_counter() - t0
+        self._D = torch.cat([Dd, Dp], dim=1)
+        self._p_cov = covp
+        return self._D, covp
+
+    @property
+    def p_cov(self):
+        if self._p_cov is None:
+            self.propagate()
+        return self._p_cov.cpu().numpy()
+
+    @property
+    def D(self):
+        if self._D is None:
+            self.propagate()
+        return self._D.cpu().numpy()

@@ -122,9 +122,10 @@ class PDF(object):
         return new
 
 
-def whiten_blocks(ns, cov_flat, svdcut, eps, device=0):
+def whiten_blocks(ns, cov_flat, svdcut, eps, device=0, as_torch=False):
     """Run b200lm_whiten on concatenated row-major blocks.  Returns numpy arrays
-    (W_flat, cov_corrected_flat, nout, nmod, logdet)."""
+    (W_flat, cov_corrected_flat, nout, nmod, logdet); with ``as_torch`` the two matrices stay on
+    the device as torch tensors."""
     if not torch.cuda.is_available():
         raise RuntimeError("lsqfit_b200.whiten: no CUDA device (there is no CPU fallback)")
     dev = torch.device("cuda", device)
@@ -143,5 +144,7 @@ def whiten_blocks(ns, cov_flat, svdcut, eps, device=0):
         float(svdcut) if svdcut is not None else 0.0, float(eps) if eps is not None else 0.0, use_eps,
         d_w.data_ptr(), d_cc.data_ptr(), d_nout.data_ptr(), d_nmod.data_ptr(), d_ld.data_ptr(),
         C.c_void_p(stream)))
+    if as_torch:
+        return d_w, d_cc, d_nout.cpu().numpy(), d_nmod.cpu().numpy(), d_ld.cpu().numpy()
     return (d_w.cpu().numpy(), d_cc.cpu().numpy(), d_nout.cpu().numpy(), d_nmod.cpu().numpy(),
             d_ld.cpu().numpy())

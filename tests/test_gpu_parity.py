@@ -560,3 +560,83 @@ def test_large_block_whitening_vs_oracle(n, cut):
     # chi2 of a random residual vector is basis independent
     v = rng.standard_normal(n) * sig
     np.testing.assert_allclose(np.sum((Wd @ v) ** 2), np.sum((Wo @ v) ** 2), rtol=1e-6)
+
+
+@pytest.mark.parametrize("n", [64, 333, 1000])
+def test_dense_cholesky_and_solves(n):
+    """b200lm_potrf / b200lm_trsm (blocked Cholesky on the DMMA GEMM) vs LAPACK in numpy."""
+    _need_gpu()
+    import torch
+    from lsqfit_b200.dense import _LA
+    la = _LA(0)
+    rng = np.random.default_rng(n)
+    Q = rng.standard_normal((n, n + 7))
+    A = Q @ Q.T / n + 0.05 * np.eye(n)
+    shift = 0.3
+    dA = torch.as_tensor(A).cuda()
+    L = la.empty(n, n)
+    linv = la.empty((n + 63) // 64, 64, 64)
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    assert la.potrf(dA, shift, L, linv, info)
+    Lr = np.linalg.cholesky(A + shift * np.eye(n))
+    Ld = np.tril(L.cpu().numpy())
+    assert np.max(np.abs(Ld - Lr)) <= 1e-12 * np.max(np.abs(Lr))
+    for nrhs in (1, 5):
+        B = rng.standard_normal((n, nrhs))
+        dB = torch.as_tensor(B[:, 0].copy() if nrhs == 1 else B).cuda()
+        X = la.trsm(L, linv, 0, dB.clone(), torch.empty_like(dB)).cpu().numpy().reshape(n, nrhs)
+        Xr = np.linalg.solve(Lr, B)
+        assert np.max(np.abs(X - Xr)) <= 1e-11 * np.max(np.abs(Xr))
+        Y = la.trsm(L, linv, 1, dB.clone(), torch.empty_like(dB)).cpu().numpy().reshape(n, nrhs)
+        Yr = np.linalg.solve(Lr.T, B)
+        assert np.max(np.abs(Y - Yr)) <= 1e-11 * np.max(np.abs(Yr))
+    # a matrix that is not positive definite is reported, not factorised silently
+    dA2 = dA.clone()
+    dA2[n // 2, n // 2] = -5.0
+    assert not la.potrf(dA2, 0.0, L, linv, info)
+    assert int(info.item()) == n // 2 + 1
+
+
+def test_dense_fit_vs_oracle():
+    """Config-5 pipeline at a size the oracle finishes in seconds (300 correlated points, rank
+    deficient sample covariance => svd cut clamps > ny/2 modes, 40 parameters): whitening, fit,
+    covariance and fit.p propagation through the dense path vs the oracle."""
+    _need_gpu()
+    from lsqfit_b200 import configs
+    from lsqfit_b200.dense import DenseFit
+    from oracle.fit import nonlinear_fit as ofit
+    cfg = configs.c5(ny=300, K=20, seed=5)
+    fo = ofit("multiexp", cfg["x"], cfg["ymean"], cfg["ycov"], prior_mean=cfg["prior_mean"],
+              prior_cov=cfg["prior_sdev"], p0=cfg["p0"], svdcut=cfg["svdcut"], tol=TIGHT, x_scale="jac", maxit=5000)
+    xe, fe, Je, cove = exact_minimum(fo, iters=300)
+    sd = np.sqrt(np.diag(cove))
+    fd = DenseFit((cfg["t"], cfg["ymean"], cfg["ycov"]), (cfg["prior_mean"], cfg["prior_sdev"]),
+                  svdcut=cfg["svdcut"], tol=TIGHT, maxit=5000, polish=50)
+    assert fd.svdn == fo.yp_pdf.nmod and fd.svdn > 150
+    assert fd.dof == fo.dof
+    assert fd.error is None and fd.stopping_criterion > 0
+    gap = np.max(np.abs(fo.pmean - xe) / sd)
+    dp = np.max(np.abs(fd.pmean - xe) / sd)
+    print("dense fit: |dp|/sd device %.2e, reference %.2e, nit %d (ref %d)" % (dp, gap, fd.nit, fo.nit))
+    assert dp <= 1e-8
+    chi2e = fe @ fe
+    assert abs(fd.chi2 - chi2e) <= 1e-9 * chi2e
+    assert _rel_cov(fd.cov, cove) <= 1e-8
+    sign, ld = np.linalg.slogdet(Je.T @ Je)
+    assert abs(fd.logdet_JtJ - ld) <= 1e-8 * abs(ld)
+    assert abs(fd.logGBF - fo.logGBF) <= 1e-6 * abs(fo.logGBF)
+    # propagation: cov(fit.p) == fit.cov when nothing is lost to roundoff, and D vs the oracle
+    # (D C D^T cancels against the svd-cut covariance, condition number 1e8, on BOTH sides)
+    assert _rel_cov(fd.p_cov, cove) <= 1e-4
+    sD = np.max(np.abs(fo.D), axis=0) + 1e-300
+    assert np.max(np.abs(fd.D - fo.D) / sD) <= 1e-5
+    # default tolerances: agrees with the reference to the reference's own distance from the minimum
+    # (through the general PDF path this time: host-assembled whitening operator)
+    import lsqfit_b200 as lb
+    fd2 = DenseFit((cfg["t"], cfg["ymean"], None), (cfg["prior_mean"], cfg["prior_sdev"]),
+                   pdf=lb.PDF(cfg["ymean"], cfg["ycov"], svdcut=cfg["svdcut"]))
+    fo2 = ofit("multiexp", cfg["x"], cfg["ymean"], cfg["ycov"], prior_mean=cfg["prior_mean"],
+               prior_cov=cfg["prior_sdev"], p0=cfg["p0"], svdcut=cfg["svdcut"], x_scale="jac")
+    assert fd2.stopping_criterion > 0
+    assert np.max(np.abs(fd2.pmean - xe) / sd) <= max(1e-3, 3 * np.max(np.abs(fo2.pmean - xe) / sd))
+    assert abs(fd2.chi2 - chi2e) <= 1e-6 * chi2e

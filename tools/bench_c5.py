@@ -1,0 +1,68 @@
+"""Config 5 (2000 params x 5000 correlated data, svdcut): whitening, per-iteration and propagation
+times of the dense path, reported separately.  GPU box only."""
+import json
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from lsqfit_b200 import configs                     # noqa: E402
+from lsqfit_b200.dense import DenseFit              # noqa: E402
+
+
+def main():
+    ny = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
+    K = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+    t0 = time.perf_counter()
+    cfg = configs.c5(ny=ny, K=K)
+    t_gen = time.perf_counter() - t0
+    torch.zeros(1, device="cuda")
+    for rep in range(2):                            # second pass = warm (kernels loaded, allocator primed)
+        fit = DenseFit((cfg["t"], cfg["ymean"], cfg["ycov"]), (cfg["prior_mean"], cfg["prior_sdev"]),
+                       svdcut=cfg["svdcut"], tol=cfg["tol"], maxit=cfg["maxit"])
+        if rep == 0:
+            first = dict(fit.times)
+            del fit
+    njev_fit, nfac_fit = fit.nfev_jac, fit.nfac
+    la = fit.la
+    # steady-state timings of the pieces with CUDA events
+    def timed(fn, n=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    ms_jac = timed(lambda: fit.jacobian(fit.x))
+    ms_res = timed(lambda: fit.residual(fit.x))
+    gs = torch.ones(fit.np, dtype=torch.float64, device="cuda")
+    ms_fac = timed(lambda: fit._factor_solve(1e-3, gs))
+    ms_potrf = timed(lambda: la.potrf(fit.As, 1e-3, fit.L, fit.linv, fit.info))
+    fit.propagate()
+    ms_prop = timed(fit.propagate, n=2)
+    npar = fit.np
+    nd = fit.nd
+    f_jac = 2.0 * nd * ny * (npar + 1) + 2.0 * nd * npar * npar + 2.0 * nd * npar
+    f_prop = 2.0 * npar * nd * npar + 2.0 * npar * nd * ny + 2.0 * npar * ny * ny + 2.0 * npar * npar * ny
+    out = dict(config=cfg["name"], ny=ny, np=npar, svdn=int(fit.svdn), nit=int(fit.nit), njev=int(njev_fit),
+               nfac=int(nfac_fit), first_call=first, stopping_criterion=int(fit.stopping_criterion), error=fit.error,
+               chi2=fit.chi2, dof=fit.dof, Q=fit.Q, logGBF=fit.logGBF,
+               whiten_s=fit.times["whiten"], fit_s=fit.times["fit"],
+               per_iteration_ms=1e3 * fit.times["fit"] / max(1, fit.nit),
+               jacobian_eval_ms=ms_jac, jacobian_tflops=f_jac / ms_jac * 1e-9,
+               residual_eval_ms=ms_res, factor_solve_ms=ms_fac, potrf_ms=ms_potrf,
+               potrf_tflops=(npar ** 3 / 3.0) / ms_potrf * 1e-9,
+               propagate_ms=ms_prop, propagate_tflops=f_prop / ms_prop * 1e-9,
+               host_gen_s=t_gen, launches=la.launches)
+    chk = np.max(np.abs(fit.p_cov - fit.cov) / np.sqrt(np.outer(np.diag(fit.cov), np.diag(fit.cov))))
+    out["pcov_vs_cov"] = float(chk)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
