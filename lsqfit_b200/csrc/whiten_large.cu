@@ -1,4 +1,4 @@
-// svdcut whitening of ONE large correlated block (n > 512; BASELINE config 5: n = 5000) by a
+// svdcut whitening of ONE large correlated block (n > 112; BASELINE config 5: n = 5000) by a
 // two-sided BLOCK Jacobi eigen-solver that spans the whole GPU.
 //
 // Replaces, at this size, the eigen-decomposition inside gvar.PDF / gvar.svd that the reference
@@ -18,6 +18,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <chrono>
 #include <algorithm>
 #include <numeric>
 #include <vector>
@@ -36,6 +37,7 @@ constexpr int BJ_THREADS = 256;
 struct BJArgs {
     double* A; double* V; int n; int ld; int nb; int nbe; int round;
     double* Q;              // [nbe/2][BJ_M][BJ_M]
+    double* Qt;             // same, transposed (A operand of the tile kernel, loaded with cp.async)
     double* offsq;          // sum of squares of the off-diagonal blocks met in this sweep
     int* rotated;           // number of pairs whose sub-problem was not yet diagonal in this sweep
     int* ident;             // [nbe/2] 1 if the pair's Q of this round is the identity
@@ -54,13 +56,13 @@ __device__ __forceinline__ bool bj_pair(const BJArgs& a, int pair, int& I, int& 
 __device__ __forceinline__ int bj_gidx(int l, int I, int J, int nI) { return l < nI ? I * BJ_B + l : J * BJ_B + (l - nI); }
 
 // Two-sided cyclic Jacobi on a 64 x 64 symmetric matrix in shared memory (pitch 65), statically
-// mapped: the 32 disjoint pivot pairs of a round go to 8 lanes each (pair = tid/8); every lane
-// recomputes its pair's rotation from the pivots (no broadcast through memory), then updates 8
-// rows of the two pivot columns of S and Q, then 8 columns of the two pivot rows of S.  Two block
+// mapped: the 32 disjoint pivot pairs of a round go to 16 lanes each (pair = tid/16); every lane
+// recomputes its pair's rotation from the pivots (no broadcast through memory), then updates 4
+// rows of the two pivot columns of S and Q, then 4 columns of the two pivot rows of S.  Two block
 // barriers per round.  Rotation criterion as in jacobi_core.cuh (relative, so small eigenvalues
 // keep their relative accuracy).  Returns the number of sweeps that rotated something.
 __device__ __forceinline__ int bj_jacobi64(double* S, double* Qs, int max_sweeps) {
-    const int tid = threadIdx.x, k = tid >> 3, sub = tid & 7;
+    const int tid = threadIdx.x, k = tid >> 4, sub = tid & 15;
     int sweeps = 0;
     for (; sweeps < max_sweeps; ++sweeps) {
         int any = 0;
@@ -68,21 +70,24 @@ __device__ __forceinline__ int bj_jacobi64(double* S, double* Qs, int max_sweeps
             int p, q;
             rr_pair(BJ_M, r, k, p, q);
             const double app = S[p * BJ_LD + p], aqq = S[q * BJ_LD + q], apq = S[p * BJ_LD + q];
-            __syncwarp();                       // all 8 lanes of the pair have the pivots before anyone writes
-            const bool rot = fabs(apq) > 1.1102230246251565e-16 * sqrt(fabs(app * aqq)) && apq != 0.0;
+            __syncwarp();                       // all 16 lanes of the pair have the pivots before anyone writes
+            // |apq| > eps/2 sqrt(|app aqq|), squared (no square root on the critical path)
+            const bool rot = apq * apq > 1.232595164407831e-32 * fabs(app * aqq) && apq != 0.0;
             double c = 1.0, sn = 0.0;
             if (rot) {
-                const double tau = (aqq - app) / (2.0 * apq);
-                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                c = rsqrt(1.0 + t * t);
+                // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (aqq - app) / (2 apq), rearranged to
+                // one sqrt, one division, one rsqrt:  t = sign(d) b / (|d| + sqrt(d^2 + b^2))
+                const double d = aqq - app, b = 2.0 * apq;
+                const double t = (d >= 0.0 ? b : -b) / (fabs(d) + sqrt(fma(d, d, b * b)));
+                c = rsqrt(fma(t, t, 1.0));
                 sn = t * c;
 #pragma unroll
-                for (int ii = 0; ii < 8; ++ii) {
-                    const int i = sub + 8 * ii;
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int i = sub + 16 * ii;
                     const double aip = S[i * BJ_LD + p], aiq = S[i * BJ_LD + q];
+                    const double vip = Qs[i * BJ_LD + p], viq = Qs[i * BJ_LD + q];
                     S[i * BJ_LD + p] = c * aip - sn * aiq;
                     S[i * BJ_LD + q] = sn * aip + c * aiq;
-                    const double vip = Qs[i * BJ_LD + p], viq = Qs[i * BJ_LD + q];
                     Qs[i * BJ_LD + p] = c * vip - sn * viq;
                     Qs[i * BJ_LD + q] = sn * vip + c * viq;
                 }
@@ -90,8 +95,8 @@ __device__ __forceinline__ int bj_jacobi64(double* S, double* Qs, int max_sweeps
             __syncthreads();
             if (rot) {
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const int j = sub + 8 * jj;
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = sub + 16 * jj;
                     const double apj = S[p * BJ_LD + j], aqj = S[q * BJ_LD + j];
                     S[p * BJ_LD + j] = c * apj - sn * aqj;
                     S[q * BJ_LD + j] = sn * apj + c * aqj;
@@ -104,14 +109,17 @@ __device__ __forceinline__ int bj_jacobi64(double* S, double* Qs, int max_sweeps
     return sweeps;
 }
 
-__global__ void __launch_bounds__(BJ_THREADS) bj_diag_kernel(const __grid_constant__ BJArgs a) {
+constexpr int BJ_DT = 512;          // threads of the sub-problem kernel: 16 lanes per pivot pair
+
+__global__ void __launch_bounds__(BJ_DT) bj_diag_kernel(const __grid_constant__ BJArgs a) {
     extern __shared__ double bj_sm[];
     double* S = bj_sm;
     double* Qs = bj_sm + BJ_M * BJ_LD;
-    __shared__ double s_red[BJ_THREADS];
+    __shared__ double s_red[BJ_DT];
     const int tid = threadIdx.x;
     int I, J, nI, nJ;
     double* Qg = a.Q + (size_t)blockIdx.x * BJ_M * BJ_M;
+    double* Qtg = a.Qt + (size_t)blockIdx.x * BJ_M * BJ_M;
     bj_pair(a, blockIdx.x, I, J, nI, nJ);
     if (nJ == 0) {                                         // idle block
         if (tid == 0) a.ident[blockIdx.x] = 1;
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(BJ_THREADS) bj_diag_kernel(const __grid_consta
     }
     const int m = nI + nJ;
     double off = 0.0;
-    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
+    for (int e = tid; e < BJ_M * BJ_M; e += BJ_DT) {
         const int r = e >> 6, c = e & 63;
         double v = 0.0;
         if (r < m && c < m) v = a.A[(size_t)bj_gidx(r, I, J, nI) * a.ld + bj_gidx(c, I, J, nI)];
@@ -129,18 +137,18 @@ __global__ void __launch_bounds__(BJ_THREADS) bj_diag_kernel(const __grid_consta
     }
     s_red[tid] = off;
     __syncthreads();
-    for (int o = BJ_THREADS / 2; o > 0; o >>= 1) {
+    for (int o = BJ_DT / 2; o > 0; o >>= 1) {
         if (tid < o) s_red[tid] += s_red[tid + o];
         __syncthreads();
     }
     if (tid == 0) atomicAdd(a.offsq, 2.0 * s_red[0]);
     // symmetrise the copy (the global matrix is symmetric up to rounding)
-    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
+    for (int e = tid; e < BJ_M * BJ_M; e += BJ_DT) {
         const int r = e >> 6, c = e & 63;
         if (r < c) { const double v = 0.5 * (S[r * BJ_LD + c] + S[c * BJ_LD + r]); S[r * BJ_LD + c] = v; }
     }
     __syncthreads();
-    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
+    for (int e = tid; e < BJ_M * BJ_M; e += BJ_DT) {
         const int r = e >> 6, c = e & 63;
         if (r > c) S[r * BJ_LD + c] = S[c * BJ_LD + r];
     }
@@ -152,9 +160,10 @@ __global__ void __launch_bounds__(BJ_THREADS) bj_diag_kernel(const __grid_consta
         if (nsw > 0) atomicAdd(a.rotated, 1);              // this pair still needed rotations
     }
     if (nsw == 0) return;
-    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
+    for (int e = tid; e < BJ_M * BJ_M; e += BJ_DT) {
         const int r = e >> 6, c = e & 63;
         Qg[e] = Qs[r * BJ_LD + c];
+        Qtg[e] = Qs[c * BJ_LD + r];
         // the pair's own diagonal tile: Q^T S Q is what the rotations left in S
         if (r < m && c < m) a.A[(size_t)bj_gidx(r, I, J, nI) * a.ld + bj_gidx(c, I, J, nI)] = S[r * BJ_LD + c];
     }
@@ -186,7 +195,15 @@ __device__ __forceinline__ void bj_mma64(const double* Aop, const double* Bop, i
     }
 }
 
-// V[rows, IuJ] <- V[rows, IuJ] . Q   (grid: x = row slab of 64, y = pair).
+// 16-byte cp.async of the element pair (c2, c2+1) of a 64-wide row; bytes beyond `valid` columns are
+// zero filled (valid <= 0: the whole pair).
+__device__ __forceinline__ void bj_cp_pair(double* dst, const double* src, const double* safe, int c2, int valid) {
+    const int bytes = c2 + 1 < valid ? 16 : (c2 < valid ? 8 : 0);
+    cp_async16(dst, bytes ? src : safe, bytes);
+}
+
+// V[rows, IuJ] <- V[rows, IuJ] . Q   (grid: x = row slab of 64, y = pair).  All global->shared traffic
+// is cp.async (16 B, 16 requests in flight per thread); three CTAs per SM overlap load, DMMA and store.
 __global__ void __launch_bounds__(BJ_THREADS) bj_cols_kernel(const __grid_constant__ BJArgs a, double* X, int nrows) {
     extern __shared__ double bj_sm[];
     double* S = bj_sm;                       // [64][BJ_PA]   A operand: S[r][k]
@@ -199,11 +216,16 @@ __global__ void __launch_bounds__(BJ_THREADS) bj_cols_kernel(const __grid_consta
     const int r0 = blockIdx.x * 64;
     const int nr = min(64, nrows - r0);
     const double* Qg = a.Q + (size_t)blockIdx.y * BJ_M * BJ_M;
-    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
-        const int r = e >> 6, c = e & 63;
-        Qs[r * BJ_PB + c] = (r < m && c < m) ? Qg[e] : 0.0;
-        S[r * BJ_PA + c] = (r < nr && c < m) ? X[(size_t)(r0 + r) * a.ld + bj_gidx(c, I, J, nI)] : 0.0;
+    const int c2 = 2 * lane;
+    const int gc = bj_gidx(c2, I, J, nI);    // nI is even (32): the pair (c2, c2+1) stays inside one block
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = w + 8 * it;
+        bj_cp_pair(Qs + r * BJ_PB + c2, Qg + r * BJ_M + c2, Qg, c2, r < m ? m : 0);
+        bj_cp_pair(S + r * BJ_PA + c2, X + (size_t)(r0 + r) * a.ld + gc, X, c2, r < nr ? m : 0);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
     double acc[8][2];
     bj_mma64(S, Qs, w, lane, acc);
@@ -215,9 +237,13 @@ __global__ void __launch_bounds__(BJ_THREADS) bj_cols_kernel(const __grid_consta
         d[0] = acc[t][0]; d[1] = acc[t][1];
     }
     __syncthreads();
-    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
-        const int r = e >> 6, c = e & 63;
-        if (r < nr && c < m) X[(size_t)(r0 + r) * a.ld + bj_gidx(c, I, J, nI)] = S[r * BJ_PA + c];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = w + 8 * it;
+        if (r >= nr || c2 >= m) continue;
+        double* g = X + (size_t)(r0 + r) * a.ld + gc;
+        const double2 v = *reinterpret_cast<const double2*>(S + r * BJ_PA + c2);
+        if (c2 + 1 < m) *reinterpret_cast<double2*>(g) = v; else g[0] = v.x;
     }
 }
 
@@ -238,15 +264,21 @@ __global__ void __launch_bounds__(BJ_THREADS) bj_tile_kernel(const __grid_consta
     const bool idP = a.ident[P] != 0, idR = a.ident[R] != 0;
     if (idP && idR) return;
     const int mP = nIP + nJP, mR = nIR + nJR;
-    const double* QP = a.Q + (size_t)P * BJ_M * BJ_M;
     const double* QR = a.Q + (size_t)R * BJ_M * BJ_M;
-    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
-        const int r = e >> 6, c = e & 63;
-        S[r * BJ_PA + c] = (r < mP && c < mR) ? a.A[(size_t)bj_gidx(r, IP, JP, nIP) * a.ld + bj_gidx(c, IR, JR, nIR)] : 0.0;
-        B2[r * BJ_PB + c] = idR ? (r == c ? 1.0 : 0.0) : ((r < mR && c < mR) ? QR[e] : 0.0);
-        // Qt[c][r] = Q_P[r][c]
-        Qt[c * BJ_PA + r] = idP ? (r == c ? 1.0 : 0.0) : ((r < mP && c < mP) ? QP[e] : 0.0);
+    const double* QPt = a.Qt + (size_t)P * BJ_M * BJ_M;
+    const int c2 = 2 * lane;
+    const int gcR = bj_gidx(c2, IR, JR, nIR), gcP = bj_gidx(c2, IP, JP, nIP);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = w + 8 * it;
+        bj_cp_pair(S + r * BJ_PA + c2, a.A + (size_t)bj_gidx(r, IP, JP, nIP) * a.ld + gcR, a.A, c2, r < mP ? mR : 0);
+        if (!idR) bj_cp_pair(B2 + r * BJ_PB + c2, QR + r * BJ_M + c2, QR, c2, r < mR ? mR : 0);
+        else { B2[r * BJ_PB + c2] = r == c2 ? 1.0 : 0.0; B2[r * BJ_PB + c2 + 1] = r == c2 + 1 ? 1.0 : 0.0; }
+        if (!idP) bj_cp_pair(Qt + r * BJ_PA + c2, QPt + r * BJ_M + c2, QPt, c2, r < mP ? mP : 0);
+        else { Qt[r * BJ_PA + c2] = r == c2 ? 1.0 : 0.0; Qt[r * BJ_PA + c2 + 1] = r == c2 + 1 ? 1.0 : 0.0; }
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
     double acc[8][2];
     bj_mma64(S, B2, w, lane, acc);                  // T = tile . Q_R
@@ -264,11 +296,20 @@ __global__ void __launch_bounds__(BJ_THREADS) bj_tile_kernel(const __grid_consta
         d[0] = acc[t][0]; d[1] = acc[t][1];
     }
     __syncthreads();
-    for (int e = tid; e < BJ_M * BJ_M; e += BJ_THREADS) {
-        const int r = e >> 6, c = e & 63;
-        if (r < mP && c < mR) a.A[(size_t)bj_gidx(r, IP, JP, nIP) * a.ld + bj_gidx(c, IR, JR, nIR)] = S[r * BJ_PA + c];
-        // mirror: row index from the R pair (e >> 6), column index from the P pair (e & 63)
-        if (c < mP && r < mR) a.A[(size_t)bj_gidx(r, IR, JR, nIR) * a.ld + bj_gidx(c, IP, JP, nIP)] = S[c * BJ_PA + r];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = w + 8 * it;
+        if (r < mP && c2 < mR) {
+            double* g = a.A + (size_t)bj_gidx(r, IP, JP, nIP) * a.ld + gcR;
+            const double2 v = *reinterpret_cast<const double2*>(S + r * BJ_PA + c2);
+            if (c2 + 1 < mR) *reinterpret_cast<double2*>(g) = v; else g[0] = v.x;
+        }
+        // mirror: row r of the R pair, columns (c2, c2+1) of the P pair
+        if (r < mR && c2 < mP) {
+            double* g = a.A + (size_t)bj_gidx(r, IR, JR, nIR) * a.ld + gcP;
+            const double v0 = S[c2 * BJ_PA + r];
+            if (c2 + 1 < mP) *reinterpret_cast<double2*>(g) = make_double2(v0, S[(c2 + 1) * BJ_PA + r]); else g[0] = v0;
+        }
     }
 }
 
@@ -321,22 +362,34 @@ int whiten_large(int device, int n, const double* d_cov, double svdcut, double* 
     (void)device;
     const int ld = (n + 1) & ~1;                     // even leading dimension (aligned GEMM path)
     const int nb = (n + BJ_B - 1) / BJ_B, nbe = (nb + 1) & ~1, npairs = nbe / 2;
-    double *A = nullptr, *V = nullptr, *Q = nullptr, *Dv = nullptr, *val = nullptr, *offsq = nullptr;
+    double *A = nullptr, *V = nullptr, *Q = nullptr, *Qt = nullptr, *Dv = nullptr, *val = nullptr, *offsq = nullptr;
     int* d_rot = nullptr; int* d_ident = nullptr;
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t evQ[2] = {nullptr, nullptr}, evV[2] = {nullptr, nullptr};
     double *T = nullptr, *U = nullptr, *G = nullptr, *d_used = nullptr, *d_wgt = nullptr;
     int *d_order = nullptr, *d_sel = nullptr;
     auto cleanup = [&]() {
-        cudaFree(A); cudaFree(V); cudaFree(Q); cudaFree(Dv); cudaFree(val); cudaFree(offsq); cudaFree(d_rot); cudaFree(d_ident);
+        cudaFree(A); cudaFree(V); cudaFree(Q); cudaFree(Qt); cudaFree(Dv); cudaFree(val); cudaFree(offsq); cudaFree(d_rot); cudaFree(d_ident);
+        for (int i = 0; i < 2; ++i) { if (evQ[i]) cudaEventDestroy(evQ[i]); if (evV[i]) cudaEventDestroy(evV[i]); }
+        if (s2) cudaStreamDestroy(s2);
         cudaFree(T); cudaFree(U); cudaFree(G); cudaFree(d_used); cudaFree(d_wgt); cudaFree(d_order); cudaFree(d_sel);
     };
     WL_TRY(cudaMalloc((void**)&A, (size_t)n * ld * sizeof(double)));
     WL_TRY(cudaMalloc((void**)&V, (size_t)n * ld * sizeof(double)));
-    WL_TRY(cudaMalloc((void**)&Q, (size_t)npairs * BJ_M * BJ_M * sizeof(double)));
+    WL_TRY(cudaMalloc((void**)&Q, 2 * (size_t)npairs * BJ_M * BJ_M * sizeof(double)));   // double buffered
+    WL_TRY(cudaMalloc((void**)&Qt, 2 * (size_t)npairs * BJ_M * BJ_M * sizeof(double)));
     WL_TRY(cudaMalloc((void**)&Dv, n * sizeof(double)));
     WL_TRY(cudaMalloc((void**)&val, n * sizeof(double)));
     WL_TRY(cudaMalloc((void**)&offsq, sizeof(double)));
     WL_TRY(cudaMalloc((void**)&d_rot, sizeof(int)));
-    WL_TRY(cudaMalloc((void**)&d_ident, npairs * sizeof(int)));
+    WL_TRY(cudaMalloc((void**)&d_ident, 2 * npairs * sizeof(int)));
+    // the eigenvector update V <- V Q does not feed back into A: it runs on a second stream, one
+    // round behind, while the next round's sub-problems (which occupy only npairs SMs) are solved
+    WL_TRY(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        WL_TRY(cudaEventCreateWithFlags(&evQ[i], cudaEventDisableTiming));
+        WL_TRY(cudaEventCreateWithFlags(&evV[i], cudaEventDisableTiming));
+    }
     const size_t sm_diag = 2 * (size_t)BJ_M * BJ_LD * sizeof(double);
     const size_t sm_slab = ((size_t)BJ_M * BJ_PA + (size_t)BJ_M * BJ_PB) * sizeof(double);
     WL_TRY(cudaFuncSetAttribute(bj_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_diag));
@@ -350,19 +403,29 @@ int whiten_large(int device, int n, const double* d_cov, double svdcut, double* 
 
     BJArgs a;
     a.A = A; a.V = V; a.n = n; a.ld = ld; a.nb = nb; a.nbe = nbe; a.Q = Q; a.offsq = offsq; a.rotated = d_rot; a.round = 0; a.ident = d_ident;
-    a.inner = getenv("B200LM_BJ_INNER") ? atoi(getenv("B200LM_BJ_INNER")) : 3;
+    a.inner = getenv("B200LM_BJ_INNER") ? atoi(getenv("B200LM_BJ_INNER")) : 2;
     const dim3 gslab((n + 63) / 64, npairs);
     // ||corr||_F^2 <= n^2 (unit diagonal, |corr_ij| <= 1): convergence relative to n (trace)
     const double tol = (double)n * 1e-30 * n;         // off^2 <= (1e-15)^2 * n * trace-ish
     int sweeps = 0;
+    long long ground = 0;                             // global round counter (buffer parity)
     for (; sweeps < 30; ++sweeps) {
+        const auto t_sweep = std::chrono::steady_clock::now();
         WL_TRY(cudaMemsetAsync(offsq, 0, sizeof(double), s));
         WL_TRY(cudaMemsetAsync(d_rot, 0, sizeof(int), s));
-        for (int r = 0; r < nbe - 1; ++r) {
+        for (int r = 0; r < nbe - 1; ++r, ++ground) {
+            const int buf = (int)(ground & 1);
             a.round = r;
-            bj_diag_kernel<<<npairs, BJ_THREADS, sm_diag, s>>>(a);
+            a.Q = Q + (size_t)buf * npairs * BJ_M * BJ_M;
+            a.Qt = Qt + (size_t)buf * npairs * BJ_M * BJ_M;
+            a.ident = d_ident + buf * npairs;
+            if (ground >= 2) WL_TRY(cudaStreamWaitEvent(s, evV[buf], 0));    // V update of round-2 has consumed this Q
+            bj_diag_kernel<<<npairs, BJ_DT, sm_diag, s>>>(a);
+            WL_TRY(cudaEventRecord(evQ[buf], s));
             bj_tile_kernel<<<dim3(npairs, npairs), BJ_THREADS, sm_tile, s>>>(a);
-            bj_cols_kernel<<<gslab, BJ_THREADS, sm_slab, s>>>(a, V, n);
+            WL_TRY(cudaStreamWaitEvent(s2, evQ[buf], 0));
+            bj_cols_kernel<<<gslab, BJ_THREADS, sm_slab, s2>>>(a, V, n);
+            WL_TRY(cudaEventRecord(evV[buf], s2));
         }
         WL_TRY(cudaGetLastError());
         double h_off = 0.0;
@@ -370,9 +433,12 @@ int whiten_large(int device, int n, const double* d_cov, double svdcut, double* 
         WL_TRY(cudaMemcpyAsync(&h_off, offsq, sizeof(double), cudaMemcpyDeviceToHost, s));
         WL_TRY(cudaMemcpyAsync(&h_rot, d_rot, sizeof(int), cudaMemcpyDeviceToHost, s));
         WL_TRY(cudaStreamSynchronize(s));
-        if (getenv("B200LM_VERBOSE")) fprintf(stderr, "whiten_large: sweep %d off^2 %.3e rotated pairs %d\n", sweeps, h_off, h_rot);
+        if (getenv("B200LM_VERBOSE"))
+            fprintf(stderr, "whiten_large: sweep %d off^2 %.3e rotated pairs %d  (%.1f ms)\n", sweeps, h_off, h_rot,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_sweep).count());
         if (h_rot == 0 || !(h_off > tol)) { ++sweeps; break; }
     }
+    WL_TRY(cudaStreamSynchronize(s2));                // V complete
     // ---- spectrum on the host (n doubles), svdcut bookkeeping --------------------------------
     wl_diag_kernel<<<(n + tpb - 1) / tpb, tpb, 0, s>>>(A, n, ld, val);
     std::vector<double> h_val(n);

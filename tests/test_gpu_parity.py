@@ -526,9 +526,10 @@ def test_dgemm_vs_torch():
     run(False, True, 1, 512, 512, 1024)
 
 
-@pytest.mark.parametrize("n,cut", [(600, 1e-8), (1100, 1e-6), (777, -1e-6), (640, 0.0)])
+@pytest.mark.parametrize("n,cut", [(600, 1e-8), (1100, 1e-6), (777, -1e-6), (640, 0.0), (113, 1e-8), (200, -1e-6),
+                                   (331, 1e-10)])
 def test_large_block_whitening_vs_oracle(n, cut):
-    """Blocks beyond the single-CTA kernel (n > 512) go through the block-Jacobi solver
+    """Blocks beyond the shared-memory single-CTA kernel (n > 112) go through the block-Jacobi solver
     (csrc/whiten_large.cu); config-5 style input: a rank-deficient sample covariance."""
     _need_gpu()
     import lsqfit_b200 as lb
