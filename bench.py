@@ -87,6 +87,16 @@ def cpu_fits_per_sec(means, cores):
     return len(means) / dt, float(np.mean(nit))
 
 
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fit kernel, per launch, from the committed
+    `ncu --set full` capture (profiles/traffic_r01_v8.json); None if absent."""
+    try:
+        t = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r01_v8.json")))
+        return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -323,7 +333,7 @@ def run_ours(args, rank, local_rank, world):
     peak, peak_src = fp64_peak()
     achieved = flops_launch / (tk_ms / args.steps * 1e-3) / 1e12
     roofline = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                    traffic=None, kernel="fit_kernel<MultiExp<8>>", peak_source=peak_src,
+                    traffic=_ncu_traffic(), kernel="fit_kernel<MultiExp<8>>", peak_source=peak_src,
                     flops_per_launch=flops_launch, flops_per_launch_survey_formula=nfev * F_eval,
                     nfev_per_fit=nfev / B, njev_per_fit=njev / B, chol_per_fit=nfac / B,
                     kernel_ms=tk_ms / args.steps)
