@@ -184,6 +184,22 @@ int b200lm_potrf(int device, int n, const double* d_A, int lda, double shift, do
 int b200lm_trsm(int device, int n, int nrhs, const double* d_L, int ldl, const double* d_linv, int trans,
                 double* d_B, int ldb, double* d_X, int ldx, void* stream);
 
+/* ---- bootstrap / simulated copies of the means ------------------------------
+ * d_z[count] <- standard normals number first .. first+count-1 of the stream keyed by `seed`
+ * (Philox4x32-10, counter = pair index, Box-Muller on 53-bit uniforms); any sub-range is
+ * bit-identical to the same elements of a larger call.  d_raw (may be NULL) receives the four raw
+ * Philox words of every pair touched (known-answer testing). */
+int b200lm_normals(int device, long long first, long long count, unsigned long long seed, double* d_z,
+                   unsigned int* d_raw, void* stream);
+
+/* d_out[b][0..N) = d_mean + L z_b for copies first .. first+B-1, z_b = normals [(first+b)*M, +M) of
+ * the stream, L row-major N x M (L L^T = covariance of y (+) prior after the svd correction); d_z is
+ * a B*M workspace that returns the normals.  Replaces gvar.bootstrap_iter / raniter as driven by
+ * src/lsqfit/__init__.py:1532-1535 and 1615-1624 (one Python iteration per copy there). */
+int b200lm_bootstrap_means(int device, long long B, long long first, int N, int M, const double* d_mean,
+                           const double* d_L, int ldl, unsigned long long seed, double* d_z,
+                           double* d_out, long long out_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,9 @@ SIGNATURES = {
                                C.c_void_p, C.c_void_p]),
     "b200lm_trsm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                               C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200lm_normals": (C.c_int, [C.c_int, C.c_longlong, C.c_longlong, C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200lm_bootstrap_means": (C.c_int, [C.c_int, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "b200lm_propagate": (C.c_int, [handle_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
 }

@@ -137,6 +137,7 @@ class nonlinear_fit(object):
         self.palt = (self.pmean, self.psdev)
         self.logGBF = None if noprior else _logGBF(fit.logdet_JtJ, pdf.logdet, self.chi2, self.dof)
         self._p = None
+        self._L = None
         self._spec = spec
         self.time = time.perf_counter() - clock
 
@@ -178,18 +179,18 @@ class nonlinear_fit(object):
                              scaler=args.pop("scaler", "more"), polish=args.pop("polish", 0))
         return BatchFits(self, out)
 
-    def bootstrap_means(self, n, seed=None):
-        """n bootstrap copies of the y (+) prior means: mean + L z with L L^T = cov
-        (gvar.bootstrap_iter as used at __init__.py:1615-1623), generated on the device."""
-        C = self.yp_pdf.cov
-        val, vec = np.linalg.eigh(C)
-        L = vec * np.sqrt(np.clip(val, 0.0, None))
-        dev = torch.device("cuda", self.device)
-        g = torch.Generator(device=dev)
-        g.manual_seed(0 if seed is None else int(seed))
-        z = torch.randn((n, C.shape[0]), generator=g, device=dev, dtype=torch.float64)
-        tL = torch.as_tensor(L).to(dev)
-        return torch.as_tensor(self.yp_pdf.mean).to(dev)[None, :] + z @ tL.T
+    def bootstrap_means(self, n, seed=None, first=0):
+        """Copies first .. first+n-1 of the bootstrap stream of y (+) prior means: mean + L z with
+        L L^T = cov (gvar.bootstrap_iter as used at __init__.py:1615-1623), generated on the device
+        by b200lm_bootstrap_means (counter-based Philox: any shard of copies is reproducible on its
+        own, so ranks of a multi-GPU job generate only their slice)."""
+        from .bootstrap import bootstrap_means
+        if self._L is None:
+            C = self.yp_pdf.cov
+            val, vec = np.linalg.eigh(C)
+            self._L = vec * np.sqrt(np.clip(val, 0.0, None))
+        return bootstrap_means(self.yp_pdf.mean, self._L, n, 0 if seed is None else int(seed), first=first,
+                               device=self.device)
 
     def bootstrapped_fits(self, n=None, means=None, seed=None, **kargs):
         """All bootstrap fits in ONE launch (what bootstrapped_fit_iter loops over,

@@ -116,3 +116,18 @@ def test_config_generators():
     # F_eval(C3) ~ 1.88e5, F_eval(C4) ~ 6.5e4
     assert abs(configs.eval_flops(64, 16, 8) - 1.88e5) < 2e3
     assert abs(configs.eval_flops(64, 6, 3) - 6.5e4) < 2e3
+
+
+def test_philox_known_answers():
+    """The numpy Philox4x32-10 that the GPU test compares the device generator with reproduces the
+    known-answer vectors published with Random123 (Salmon et al., SC'11)."""
+    from oracle.philox import philox4x32_10, normals
+    def h(a):
+        return " ".join("%08x" % x for x in a)
+    assert h(philox4x32_10(np.array([0, 0, 0, 0]), (0, 0))) == "6627e8d5 e169c58d bc57ac4c 9b00dbd8"
+    assert h(philox4x32_10(np.array([0xffffffff] * 4), (0xffffffff, 0xffffffff))) == "408f276d 41c83b0e a20bc7c6 6d5451fd"
+    assert h(philox4x32_10(np.array([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344]),
+                           (0xa4093822, 0x299f31d0))) == "d16cfe09 94fdcceb 5001e420 24126ea1"
+    z, _ = normals(3, 200001, 12345)
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1) < 0.01
+    assert np.array_equal(normals(0, 1000, 5)[0][10:20], normals(10, 10, 5)[0])

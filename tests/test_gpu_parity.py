@@ -641,3 +641,41 @@ def test_dense_fit_vs_oracle():
     assert fd2.stopping_criterion > 0
     assert np.max(np.abs(fd2.pmean - xe) / sd) <= max(1e-3, 3 * np.max(np.abs(fo2.pmean - xe) / sd))
     assert abs(fd2.chi2 - chi2e) <= 1e-6 * chi2e
+
+
+def test_bootstrap_generator():
+    """b200lm_normals / b200lm_bootstrap_means: Philox words and normals vs the numpy restatement
+    (oracle/philox.py, itself pinned to the published known-answer vectors), sub-range == slice of the
+    full stream (bit-exact: what lets every rank generate only its shard), and the distribution
+    mean + L z of the copies (reference src/lsqfit/__init__.py:1615-1624)."""
+    _need_gpu()
+    from lsqfit_b200 import bootstrap as bs, configs
+    from oracle import philox
+    seed = 0x1234567887654321
+    z, w = bs.normals(100001, seed, first=7, raw=True)
+    zo, wo = philox.normals(7, 100001, seed)
+    assert np.array_equal(w.cpu().numpy().view(np.uint32), wo)
+    np.testing.assert_allclose(z.cpu().numpy(), zo, rtol=0, atol=1e-13)
+    full = bs.normals(50000, seed).cpu().numpy()
+    for first, cnt in ((0, 1), (1, 1), (12345, 3333), (49999, 1), (17, 20000)):
+        assert np.array_equal(bs.normals(cnt, seed, first=first).cpu().numpy(), full[first:first + cnt])
+    cfg = configs.correlator(3)
+    N = cfg["ny"] + cfg["np"]
+    cov = np.zeros((N, N))
+    cov[:cfg["ny"], :cfg["ny"]] = cfg["ycov"]
+    cov[cfg["ny"]:, cfg["ny"]:] = np.diag(cfg["prior_sdev"] ** 2)
+    mean = np.concatenate([cfg["f"], cfg["prior_mean"]])
+    val, vec = np.linalg.eigh(cov)
+    L = vec * np.sqrt(np.clip(val, 0, None))
+    B = 200000
+    m, zz = bs.bootstrap_means(mean, L, B, 99, return_z=True)
+    m, zz = m.cpu().numpy(), zz.cpu().numpy()
+    np.testing.assert_allclose(m, mean[None, :] + zz @ L.T, rtol=1e-12, atol=1e-15)      # the GEMM
+    part = bs.bootstrap_means(mean, L, 1000, 99, first=4321).cpu().numpy()
+    assert np.array_equal(part, m[4321:5321])                                             # shard == slice
+    sd = np.sqrt(np.diag(cov))
+    assert np.max(np.abs(m.mean(axis=0) - mean) / sd) < 5.0 / np.sqrt(B)
+    emp = np.cov(m.T)
+    assert np.max(np.abs(emp - cov) / np.outer(sd, sd)) < 6.0 * np.sqrt(2.0 / B)
+    assert abs(zz.mean()) < 5.0 / np.sqrt(zz.size) and abs(zz.std() - 1.0) < 5.0 / np.sqrt(2 * zz.size)
+    assert np.max(np.abs(zz)) > 4.5                                                       # tails are populated
