@@ -14,6 +14,8 @@ from .engine import Plan, BatchResult, STOPPING_CRITERION, normalize_tol
 from .whiten import PDF, cov_blocks
 from .fitter import b200_lm, ChivSpec, DeviceChiv
 from .fit import nonlinear_fit, gammaQ, BatchFits, FitView
+from .dense import DenseFit
+from .bootstrap import bootstrap_means, normals
 
 __version__ = "0.1.0"
 
