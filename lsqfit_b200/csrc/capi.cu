@@ -236,6 +236,7 @@ int b200lm_fit_batch(b200lm_handle h, int B,
                      int* d_nit, int* d_status, double* d_f, double* d_J, void* stream) {
     int rc = check_ready(h);
     if (rc) return rc;
+    if (B == 0) return B200LM_OK;                 // empty batch: nothing to read or write
     if (B < 0 || !d_mean || !d_p0 || !d_x || !d_chi2 || !d_nit || !d_status)
         return set_error(h, B200LM_EINVAL, "NULL required argument");
     if ((mean_stride != 0 && mean_stride < h->N) || (p0_stride != 0 && p0_stride < h->np))
@@ -314,9 +315,9 @@ int b200lm_fit_batch_host(b200lm_handle h, int B,
                           int* h_nit, int* h_status, double* h_f, double* h_J) {
     int rc = check_ready(h);
     if (rc) return rc;
+    if (B == 0) return B200LM_OK;                 // empty batch
     if (B < 0 || !h_mean || !h_p0 || !h_x || !h_chi2 || !h_nit || !h_status)
         return set_error(h, B200LM_EINVAL, "NULL required argument");
-    if (B == 0) return B200LM_OK;
     CUDA_TRY(h, cudaSetDevice(h->device), "cudaSetDevice");
     const size_t np = h->np, N = h->N, nchiv = h->nchiv;
     const size_t n_mean = mean_stride ? (size_t)B * mean_stride : N;

@@ -679,3 +679,62 @@ def test_bootstrap_generator():
     assert np.max(np.abs(emp - cov) / np.outer(sd, sd)) < 6.0 * np.sqrt(2.0 / B)
     assert abs(zz.mean()) < 5.0 / np.sqrt(zz.size) and abs(zz.std() - 1.0) < 5.0 / np.sqrt(2 * zz.size)
     assert np.max(np.abs(zz)) > 4.5                                                       # tails are populated
+
+
+def test_edge_cases():
+    """Empty and one-element batches, per-fit starting points, no-prior fits, non-finite data, maxit
+    exhaustion: the cases the reference's tests exercise around the fitter seam
+    (tests/test_lsqfit.py:1684-1777) restated for a batch."""
+    _need_gpu()
+    import torch
+    import lsqfit_b200 as lb
+    from oracle.fit import nonlinear_fit as ofit
+    x = np.linspace(0.1, 2.0, 12)
+    ptrue = np.array([0.7, 1.3, 0.4])
+    y = (ptrue[0] + ptrue[1] * np.exp(-ptrue[2] * x)) * (1 + 1e-3 * np.cos(7 * x))
+    ysd = 1e-3 * np.ones(12)
+    pm, psd = np.array([0.5, 1.0, 0.5]), np.ones(3)
+    # ---- with prior: shared vs per-fit p0, B = 1, B = 0 ----
+    mean = np.concatenate([y, pm])
+    plan = lb.Plan("offset_exp", 3, 12, x, [(np.arange(15), 1.0 / np.concatenate([ysd, psd]))])
+    one = plan.fit_batch(mean, pm, tol=TIGHT, polish=20).numpy()
+    assert one["x"].shape == (1, 3) and one["status"][0] > 0
+    p0s = pm[None, :] * (1 + 0.05 * np.arange(5)[:, None])
+    many = plan.fit_batch(mean, p0s, tol=TIGHT, polish=20).numpy()
+    assert many["x"].shape == (5, 3)
+    sd = np.sqrt(np.diag(one["cov"][0]))
+    assert np.max(np.abs(many["x"] - one["x"][0][None]) / sd[None]) < 1e-8        # same minimum from every start
+    empty = plan.fit_batch(np.zeros((0, 15)), pm)
+    assert empty.x.shape == (0, 3) and empty.status.shape == (0,)
+    eh = plan.fit_batch_host(np.zeros((0, 15)), pm)
+    assert eh["x"].shape == (0, 3)
+    fo = ofit("offset_exp", x[:, None], y, ysd, prior_mean=pm, prior_cov=psd, tol=TIGHT, x_scale="jac")
+    xe, fe, Je, cove = exact_minimum(fo)
+    assert np.max(np.abs(one["x"][0] - xe) / np.sqrt(np.diag(cove))) < 1e-8
+    # ---- non-finite data poison only their own fit, and are reported, not raised ----
+    means = np.tile(mean, (4, 1))
+    means[2, 3] = np.nan
+    means[1, 0] = np.inf
+    bad = plan.fit_batch(means, pm, tol=TIGHT, polish=20).numpy()
+    assert bad["status"][2] < 0 and bad["status"][1] < 0
+    assert lb.STOPPING_CRITERION[int(bad["status"][2])] == 0
+    np.testing.assert_array_equal(bad["x"][0], one["x"][0])
+    np.testing.assert_array_equal(bad["x"][3], one["x"][0])
+    # ---- maxit exhausted: stopping_criterion 0, like the reference's "failed to converge" ----
+    short = plan.fit_batch(mean, pm, tol=TIGHT, maxit=2).numpy()
+    assert short["status"][0] == 0 and short["nit"][0] == 2
+    plan.close()
+    # ---- no prior (src/lsqfit/_utilities.pyx:74-77: delta = fcn(p) - mean only) ----
+    plan = lb.Plan("offset_exp", 3, 12, x, [(np.arange(12), 1.0 / ysd)], noprior=True)
+    out = plan.fit_batch(y, pm, tol=TIGHT, polish=20).numpy()
+    fo = ofit("offset_exp", x[:, None], y, ysd, p0=pm, tol=TIGHT, x_scale="jac")
+    xe, fe, Je, cove = exact_minimum(fo)
+    assert out["status"][0] > 0
+    assert np.max(np.abs(out["x"][0] - xe) / np.sqrt(np.diag(cove))) < 1e-8
+    assert abs(out["chi2"][0] - fe @ fe) <= 1e-9 * (fe @ fe) + 1e-300
+    assert _rel_cov(out["cov"][0], cove) < 1e-8
+    with pytest.raises(ValueError):
+        plan.fit_batch(np.zeros((3, 12)), np.zeros((2, 3)))           # ragged batch sizes
+    with pytest.raises(lb.B200LMError):
+        plan.fit_batch(y, pm, maxit=0)
+    plan.close()
