@@ -55,57 +55,107 @@ __device__ __forceinline__ bool bj_pair(const BJArgs& a, int pair, int& I, int& 
 // global column/row index of local index l in the (I, J) pair
 __device__ __forceinline__ int bj_gidx(int l, int I, int J, int nI) { return l < nI ? I * BJ_B + l : J * BJ_B + (l - nI); }
 
-// Two-sided cyclic Jacobi on a 64 x 64 symmetric matrix in shared memory (pitch 65), statically
-// mapped: the 32 disjoint pivot pairs of a round go to 16 lanes each (pair = tid/16); every lane
-// recomputes its pair's rotation from the pivots (no broadcast through memory), then updates 4
-// rows of the two pivot columns of S and Q, then 4 columns of the two pivot rows of S.  Two block
-// barriers per round.  Rotation criterion as in jacobi_core.cuh (relative, so small eigenvalues
-// keep their relative accuracy).  Returns the number of sweeps that rotated something.
-__device__ __forceinline__ int bj_jacobi64(double* S, double* Qs, int max_sweeps) {
+// Two-sided cyclic Jacobi on a 64 x 64 symmetric matrix in shared memory (pitch 65), 512 threads.
+// Per rotation round (32 disjoint pivot pairs, round-robin ordering):
+//   phase A  warp 0 computes the 32 rotations (one lane per pair) into a double-buffered (c, s) table
+//            while the other warps apply the PREVIOUS round's rotations to Q (Q never feeds back);
+//   phase B  every 2 x 2 block (pair k, pair k') with k <= k' is transformed ONCE, B <- J_k^T B J_k',
+//            by one thread and written back with its mirror image: half the shared-memory traffic of
+//            separate column and row passes, and S stays exactly symmetric.
+// (The first version recomputed each rotation in 16 lanes and ran a column and a row pass; ncu time
+// per round matched shared-memory traffic + the redundant FP64 sqrt/div chains.)  Rotation criterion
+// as in jacobi_core.cuh (relative, so small eigenvalues keep their relative accuracy).  Returns the
+// number of sweeps that rotated something.
+// The kernel is instruction-issue bound (ncu: 490 warp instructions per warp and rotation round in the
+// first version, 12 % of them the modulo arithmetic of the round-robin schedule), so the schedule
+// (p, q of every pair in every round) and the list of 2 x 2 block tasks are tabulated once per CTA.
+struct BJTables {
+    uchar2 pq[(BJ_M - 1) * (BJ_M / 2)];      // [round][pair] -> (p, q)
+    uchar2 task[528];                        // (k, k') with k <= k' < 32
+};
+
+// Q <- Q J for the 32 rotations of one round: 16 lanes per pair, 4 rows each
+__device__ __forceinline__ void bj_q_update(double* Qs, const double* cs, const uchar2* pq) {
     const int tid = threadIdx.x, k = tid >> 4, sub = tid & 15;
-    int sweeps = 0;
+    const double sn = cs[2 * k + 1];
+    if (sn == 0.0) return;
+    const double c = cs[2 * k];
+    const uchar2 t = pq[k];
+    double* qp = Qs + sub * BJ_LD + t.x;
+    double* qq = Qs + sub * BJ_LD + t.y;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const double vip = qp[16 * jj * BJ_LD], viq = qq[16 * jj * BJ_LD];
+        qp[16 * jj * BJ_LD] = c * vip - sn * viq;
+        qq[16 * jj * BJ_LD] = sn * vip + c * viq;
+    }
+}
+
+__device__ __forceinline__ int bj_jacobi64(double* S, double* Qs, int max_sweeps, double* s_cs /*[2][64]*/,
+                                           int* s_any /*[2]*/, const BJTables& tb) {
+    const int tid = threadIdx.x;
+    int sweeps = 0, g = 0, rprev = -1;
     for (; sweeps < max_sweeps; ++sweeps) {
         int any = 0;
-        for (int r = 0; r < BJ_M - 1; ++r) {
-            int p, q;
-            rr_pair(BJ_M, r, k, p, q);
-            const double app = S[p * BJ_LD + p], aqq = S[q * BJ_LD + q], apq = S[p * BJ_LD + q];
-            __syncwarp();                       // all 16 lanes of the pair have the pivots before anyone writes
-            // |apq| > eps/2 sqrt(|app aqq|), squared (no square root on the critical path)
-            const bool rot = apq * apq > 1.232595164407831e-32 * fabs(app * aqq) && apq != 0.0;
-            double c = 1.0, sn = 0.0;
-            if (rot) {
-                // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (aqq - app) / (2 apq), rearranged to
-                // one sqrt, one division, one rsqrt:  t = sign(d) b / (|d| + sqrt(d^2 + b^2))
-                const double d = aqq - app, b = 2.0 * apq;
-                const double t = (d >= 0.0 ? b : -b) / (fabs(d) + sqrt(fma(d, d, b * b)));
-                c = rsqrt(fma(t, t, 1.0));
-                sn = t * c;
-#pragma unroll
-                for (int ii = 0; ii < 4; ++ii) {
-                    const int i = sub + 16 * ii;
-                    const double aip = S[i * BJ_LD + p], aiq = S[i * BJ_LD + q];
-                    const double vip = Qs[i * BJ_LD + p], viq = Qs[i * BJ_LD + q];
-                    S[i * BJ_LD + p] = c * aip - sn * aiq;
-                    S[i * BJ_LD + q] = sn * aip + c * aiq;
-                    Qs[i * BJ_LD + p] = c * vip - sn * viq;
-                    Qs[i * BJ_LD + q] = sn * vip + c * viq;
+        for (int r = 0; r < BJ_M - 1; ++r, ++g) {
+            double* cs = s_cs + (g & 1) * BJ_M;
+            const uchar2* pq = tb.pq + r * (BJ_M / 2);
+            // ---- phase A: the 32 rotations of this round (warp 0, one lane per pair) ... ----
+            if (tid < 32) {
+                const uchar2 t = pq[tid];
+                const int p = t.x, q = t.y;
+                const double app = S[p * BJ_LD + p], aqq = S[q * BJ_LD + q], apq = S[p * BJ_LD + q];
+                // |apq| > eps/2 sqrt(|app aqq|), squared
+                const bool rot = apq * apq > 1.232595164407831e-32 * fabs(app * aqq) && apq != 0.0;
+                double c = 1.0, sn = 0.0;
+                if (rot) {
+                    // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (aqq - app) / (2 apq), as one sqrt,
+                    // one division, one rsqrt:  t = sign(d) b / (|d| + sqrt(d^2 + b^2))
+                    const double d = aqq - app, b = 2.0 * apq;
+                    const double tt = (d >= 0.0 ? b : -b) / (fabs(d) + sqrt(fma(d, d, b * b)));
+                    c = rsqrt(fma(tt, tt, 1.0));
+                    sn = tt * c;
+                }
+                cs[2 * tid] = c;
+                cs[2 * tid + 1] = sn;
+                const unsigned m = __ballot_sync(0xffffffffu, rot);
+                if (tid == 0) s_any[g & 1] = m != 0u;
+            }
+            // ---- ... while the previous round's rotations reach Q (Q never feeds back into S) ----
+            if (rprev >= 0) bj_q_update(Qs, s_cs + ((g - 1) & 1) * BJ_M, tb.pq + rprev * (BJ_M / 2));
+            __syncthreads();
+            rprev = r;
+            if (!s_any[g & 1]) continue;         // uniform: nothing rotates in this round
+            any = 1;
+            // ---- phase B: 2 x 2 blocks (k, k'), k <= k' ----
+            for (int e = tid; e < 528; e += BJ_M * 8) {
+                const uchar2 kk = tb.task[e];
+                const double c1 = cs[2 * kk.x], s1 = cs[2 * kk.x + 1], c2 = cs[2 * kk.y], s2 = cs[2 * kk.y + 1];
+                if (s1 == 0.0 && s2 == 0.0) continue;
+                const uchar2 t1 = pq[kk.x], t2 = pq[kk.y];
+                double* rp = S + t1.x * BJ_LD;
+                double* rq = S + t1.y * BJ_LD;
+                const double b00 = rp[t2.x], b01 = rp[t2.y], b10 = rq[t2.x], b11 = rq[t2.y];
+                // T = B J_k'  (columns), then B' = J_k^T T (rows)
+                const double t00 = c2 * b00 - s2 * b01, t01 = s2 * b00 + c2 * b01;
+                const double t10 = c2 * b10 - s2 * b11, t11 = s2 * b10 + c2 * b11;
+                double n00 = c1 * t00 - s1 * t10, n01 = c1 * t01 - s1 * t11;
+                double n10 = s1 * t00 + c1 * t10, n11 = s1 * t01 + c1 * t11;
+                if (kk.x == kk.y) { n01 = 0.0; n10 = 0.0; }      // the annihilated pivot
+                rp[t2.x] = n00; rp[t2.y] = n01; rq[t2.x] = n10; rq[t2.y] = n11;
+                if (kk.x != kk.y) {
+                    double* cp = S + t2.x * BJ_LD;
+                    double* cq = S + t2.y * BJ_LD;
+                    cp[t1.x] = n00; cq[t1.x] = n01; cp[t1.y] = n10; cq[t1.y] = n11;
                 }
             }
             __syncthreads();
-            if (rot) {
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int j = sub + 16 * jj;
-                    const double apj = S[p * BJ_LD + j], aqj = S[q * BJ_LD + j];
-                    S[p * BJ_LD + j] = c * apj - sn * aqj;
-                    S[q * BJ_LD + j] = sn * apj + c * aqj;
-                }
-            }
-            any |= __syncthreads_or(rot ? 1 : 0);
         }
         if (!any) break;
     }
+    // the last round's rotations have not reached Q yet
+    if (rprev >= 0) bj_q_update(Qs, s_cs + ((g - 1) & 1) * BJ_M, tb.pq + rprev * (BJ_M / 2));
+    __syncthreads();
     return sweeps;
 }
 
@@ -116,6 +166,9 @@ __global__ void __launch_bounds__(BJ_DT) bj_diag_kernel(const __grid_constant__ 
     double* S = bj_sm;
     double* Qs = bj_sm + BJ_M * BJ_LD;
     __shared__ double s_red[BJ_DT];
+    __shared__ double s_cs[2 * BJ_M];
+    __shared__ int s_any[2];
+    __shared__ BJTables tb;
     const int tid = threadIdx.x;
     int I, J, nI, nJ;
     double* Qg = a.Q + (size_t)blockIdx.x * BJ_M * BJ_M;
@@ -134,6 +187,16 @@ __global__ void __launch_bounds__(BJ_DT) bj_diag_kernel(const __grid_constant__ 
         S[r * BJ_LD + c] = v;
         Qs[r * BJ_LD + c] = (r == c) ? 1.0 : 0.0;
         if (r < nI && c >= nI) off = fma(v, v, off);
+    }
+    for (int e = tid; e < (BJ_M - 1) * (BJ_M / 2); e += BJ_DT) {
+        int p, q;
+        rr_pair(BJ_M, e / (BJ_M / 2), e % (BJ_M / 2), p, q);
+        tb.pq[e] = make_uchar2((unsigned char)p, (unsigned char)q);
+    }
+    for (int e = tid; e < 1024; e += BJ_DT) {
+        const int k = e >> 5, k2 = e & 31;
+        // position of (k, k2), k <= k2, in the row-major upper triangle
+        if (k <= k2) tb.task[k * 32 - k * (k - 1) / 2 + (k2 - k)] = make_uchar2((unsigned char)k, (unsigned char)k2);
     }
     s_red[tid] = off;
     __syncthreads();
@@ -154,7 +217,7 @@ __global__ void __launch_bounds__(BJ_DT) bj_diag_kernel(const __grid_constant__ 
     }
     __syncthreads();
     // a few inner sweeps per visit are enough: the outer iteration finishes the job
-    const int nsw = bj_jacobi64(S, Qs, a.inner);
+    const int nsw = bj_jacobi64(S, Qs, a.inner, s_cs, s_any, tb);
     if (tid == 0) {
         a.ident[blockIdx.x] = nsw == 0 ? 1 : 0;            // Q == I: the slab kernels skip this pair
         if (nsw > 0) atomicAdd(a.rotated, 1);              // this pair still needed rotations
@@ -364,13 +427,16 @@ int whiten_large(int device, int n, const double* d_cov, double svdcut, double* 
     const int nb = (n + BJ_B - 1) / BJ_B, nbe = (nb + 1) & ~1, npairs = nbe / 2;
     double *A = nullptr, *V = nullptr, *Q = nullptr, *Qt = nullptr, *Dv = nullptr, *val = nullptr, *offsq = nullptr;
     int* d_rot = nullptr; int* d_ident = nullptr;
-    cudaStream_t s2 = nullptr;
+    cudaStream_t s1 = nullptr, s2 = nullptr;
+    cudaEvent_t evStart = nullptr;
     cudaEvent_t evQ[2] = {nullptr, nullptr}, evV[2] = {nullptr, nullptr};
     double *T = nullptr, *U = nullptr, *G = nullptr, *d_used = nullptr, *d_wgt = nullptr;
     int *d_order = nullptr, *d_sel = nullptr;
     auto cleanup = [&]() {
         cudaFree(A); cudaFree(V); cudaFree(Q); cudaFree(Qt); cudaFree(Dv); cudaFree(val); cudaFree(offsq); cudaFree(d_rot); cudaFree(d_ident);
         for (int i = 0; i < 2; ++i) { if (evQ[i]) cudaEventDestroy(evQ[i]); if (evV[i]) cudaEventDestroy(evV[i]); }
+        if (evStart) cudaEventDestroy(evStart);
+        if (s1) cudaStreamDestroy(s1);
         if (s2) cudaStreamDestroy(s2);
         cudaFree(T); cudaFree(U); cudaFree(G); cudaFree(d_used); cudaFree(d_wgt); cudaFree(d_order); cudaFree(d_sel);
     };
@@ -385,7 +451,13 @@ int whiten_large(int device, int n, const double* d_cov, double svdcut, double* 
     WL_TRY(cudaMalloc((void**)&d_ident, 2 * npairs * sizeof(int)));
     // the eigenvector update V <- V Q does not feed back into A: it runs on a second stream, one
     // round behind, while the next round's sub-problems (which occupy only npairs SMs) are solved
-    WL_TRY(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    // Two private streams: the Jacobi chain (sub-problems + A tiles) is the critical path and gets the
+    // highest priority, so that the V update only fills the SMs the chain leaves idle.
+    int prio_lo = 0, prio_hi = 0;
+    WL_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    WL_TRY(cudaStreamCreateWithPriority(&s1, cudaStreamNonBlocking, prio_hi));
+    WL_TRY(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, prio_lo));
+    WL_TRY(cudaEventCreateWithFlags(&evStart, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         WL_TRY(cudaEventCreateWithFlags(&evQ[i], cudaEventDisableTiming));
         WL_TRY(cudaEventCreateWithFlags(&evV[i], cudaEventDisableTiming));
@@ -400,6 +472,8 @@ int whiten_large(int device, int n, const double* d_cov, double svdcut, double* 
     const unsigned gnn = (unsigned)(((size_t)n * n + tpb - 1) / tpb);
     wl_init_kernel<<<gnn, tpb, 0, s>>>(d_cov, n, A, V, ld, Dv);
     WL_TRY(cudaGetLastError());
+    WL_TRY(cudaEventRecord(evStart, s));
+    WL_TRY(cudaStreamWaitEvent(s1, evStart, 0));
 
     BJArgs a;
     a.A = A; a.V = V; a.n = n; a.ld = ld; a.nb = nb; a.nbe = nbe; a.Q = Q; a.offsq = offsq; a.rotated = d_rot; a.round = 0; a.ident = d_ident;
@@ -411,18 +485,18 @@ int whiten_large(int device, int n, const double* d_cov, double svdcut, double* 
     long long ground = 0;                             // global round counter (buffer parity)
     for (; sweeps < 30; ++sweeps) {
         const auto t_sweep = std::chrono::steady_clock::now();
-        WL_TRY(cudaMemsetAsync(offsq, 0, sizeof(double), s));
-        WL_TRY(cudaMemsetAsync(d_rot, 0, sizeof(int), s));
+        WL_TRY(cudaMemsetAsync(offsq, 0, sizeof(double), s1));
+        WL_TRY(cudaMemsetAsync(d_rot, 0, sizeof(int), s1));
         for (int r = 0; r < nbe - 1; ++r, ++ground) {
             const int buf = (int)(ground & 1);
             a.round = r;
             a.Q = Q + (size_t)buf * npairs * BJ_M * BJ_M;
             a.Qt = Qt + (size_t)buf * npairs * BJ_M * BJ_M;
             a.ident = d_ident + buf * npairs;
-            if (ground >= 2) WL_TRY(cudaStreamWaitEvent(s, evV[buf], 0));    // V update of round-2 has consumed this Q
-            bj_diag_kernel<<<npairs, BJ_DT, sm_diag, s>>>(a);
-            WL_TRY(cudaEventRecord(evQ[buf], s));
-            bj_tile_kernel<<<dim3(npairs, npairs), BJ_THREADS, sm_tile, s>>>(a);
+            if (ground >= 2) WL_TRY(cudaStreamWaitEvent(s1, evV[buf], 0));    // V update of round-2 has consumed this Q
+            bj_diag_kernel<<<npairs, BJ_DT, sm_diag, s1>>>(a);
+            WL_TRY(cudaEventRecord(evQ[buf], s1));
+            bj_tile_kernel<<<dim3(npairs, npairs), BJ_THREADS, sm_tile, s1>>>(a);
             WL_TRY(cudaStreamWaitEvent(s2, evQ[buf], 0));
             bj_cols_kernel<<<gslab, BJ_THREADS, sm_slab, s2>>>(a, V, n);
             WL_TRY(cudaEventRecord(evV[buf], s2));
@@ -430,15 +504,16 @@ int whiten_large(int device, int n, const double* d_cov, double svdcut, double* 
         WL_TRY(cudaGetLastError());
         double h_off = 0.0;
         int h_rot = 0;
-        WL_TRY(cudaMemcpyAsync(&h_off, offsq, sizeof(double), cudaMemcpyDeviceToHost, s));
-        WL_TRY(cudaMemcpyAsync(&h_rot, d_rot, sizeof(int), cudaMemcpyDeviceToHost, s));
-        WL_TRY(cudaStreamSynchronize(s));
+        WL_TRY(cudaMemcpyAsync(&h_off, offsq, sizeof(double), cudaMemcpyDeviceToHost, s1));
+        WL_TRY(cudaMemcpyAsync(&h_rot, d_rot, sizeof(int), cudaMemcpyDeviceToHost, s1));
+        WL_TRY(cudaStreamSynchronize(s1));
         if (getenv("B200LM_VERBOSE"))
             fprintf(stderr, "whiten_large: sweep %d off^2 %.3e rotated pairs %d  (%.1f ms)\n", sweeps, h_off, h_rot,
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_sweep).count());
         if (h_rot == 0 || !(h_off > tol)) { ++sweeps; break; }
     }
-    WL_TRY(cudaStreamSynchronize(s2));                // V complete
+    WL_TRY(cudaStreamSynchronize(s1));
+    WL_TRY(cudaStreamSynchronize(s2));                // A and V complete; the rest runs on the caller's stream
     // ---- spectrum on the host (n doubles), svdcut bookkeeping --------------------------------
     wl_diag_kernel<<<(n + tpb - 1) / tpb, tpb, 0, s>>>(A, n, ld, val);
     std::vector<double> h_val(n);
