@@ -74,9 +74,8 @@ struct BJTables {
     uchar2 task[528];                        // (k, k') with k <= k' < 32
 };
 
-// Q <- Q J for the 32 rotations of one round: 16 lanes per pair, 4 rows each
-__device__ __forceinline__ void bj_q_update(double* Qs, const double* cs, const uchar2* pq) {
-    const int tid = threadIdx.x, k = tid >> 4, sub = tid & 15;
+// Q <- Q J for one rotation: 16 lanes, 4 rows each
+__device__ __forceinline__ void bj_q_rotate(double* Qs, const double* cs, const uchar2* pq, int k, int sub) {
     const double sn = cs[2 * k + 1];
     if (sn == 0.0) return;
     const double c = cs[2 * k];
@@ -89,6 +88,14 @@ __device__ __forceinline__ void bj_q_update(double* Qs, const double* cs, const 
         qp[16 * jj * BJ_LD] = c * vip - sn * viq;
         qq[16 * jj * BJ_LD] = sn * vip + c * viq;
     }
+}
+// ... for the 32 rotations of a round, by warps 1..15 (warp 0 is busy with the next rotations): 30 pairs
+// in one pass, pairs 30 and 31 in a second pass of warp 1
+__device__ __forceinline__ void bj_q_update(double* Qs, const double* cs, const uchar2* pq) {
+    const int t = threadIdx.x - 32;
+    if (t < 0) return;
+    bj_q_rotate(Qs, cs, pq, t >> 4, t & 15);
+    if (t < 32) bj_q_rotate(Qs, cs, pq, 30 + (t >> 4), t & 15);
 }
 
 __device__ __forceinline__ int bj_jacobi64(double* S, double* Qs, int max_sweeps, double* s_cs /*[2][64]*/,
@@ -109,12 +116,15 @@ __device__ __forceinline__ int bj_jacobi64(double* S, double* Qs, int max_sweeps
                 const bool rot = apq * apq > 1.232595164407831e-32 * fabs(app * aqq) && apq != 0.0;
                 double c = 1.0, sn = 0.0;
                 if (rot) {
-                    // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (aqq - app) / (2 apq), as one sqrt,
-                    // one division, one rsqrt:  t = sign(d) b / (|d| + sqrt(d^2 + b^2))
+                    // Jacobi angle without the tan: with d = aqq - app, b = 2 apq, r = sqrt(d^2 + b^2)
+                    //   cos^2 = (1 + |d|/r) / 2 ,  sin = sign(d) b / (2 r cos)
+                    // two rsqrt on the critical path instead of sqrt -> divide -> rsqrt
                     const double d = aqq - app, b = 2.0 * apq;
-                    const double tt = (d >= 0.0 ? b : -b) / (fabs(d) + sqrt(fma(d, d, b * b)));
-                    c = rsqrt(fma(tt, tt, 1.0));
-                    sn = tt * c;
+                    const double rinv = rsqrt(fma(d, d, b * b));
+                    const double c2 = fma(0.5 * fabs(d), rinv, 0.5);
+                    const double cinv = rsqrt(c2);
+                    c = c2 * cinv;
+                    sn = (d >= 0.0 ? 0.5 : -0.5) * b * rinv * cinv;
                 }
                 cs[2 * tid] = c;
                 cs[2 * tid + 1] = sn;
@@ -128,7 +138,11 @@ __device__ __forceinline__ int bj_jacobi64(double* S, double* Qs, int max_sweeps
             if (!s_any[g & 1]) continue;         // uniform: nothing rotates in this round
             any = 1;
             // ---- phase B: 2 x 2 blocks (k, k'), k <= k' ----
-            for (int e = tid; e < 528; e += BJ_M * 8) {
+            // tasks 512..527 go to the upper half of the LAST warp (warp 0 already carries the rotations)
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                if (pass == 1 && tid < 496) break;
+                const int e = pass == 0 ? tid : tid + 16;
                 const uchar2 kk = tb.task[e];
                 const double c1 = cs[2 * kk.x], s1 = cs[2 * kk.x + 1], c2 = cs[2 * kk.y], s2 = cs[2 * kk.y + 1];
                 if (s1 == 0.0 && s2 == 0.0) continue;
