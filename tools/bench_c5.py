@@ -1,6 +1,7 @@
 """Config 5 (2000 params x 5000 correlated data, svdcut): whitening, per-iteration and propagation
 times of the dense path, reported separately.  GPU box only."""
 import json
+import os
 import sys
 import time
 
@@ -13,8 +14,9 @@ from lsqfit_b200.dense import DenseFit              # noqa: E402
 
 
 def main():
-    ny = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
-    K = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+    pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+    ny = int(pos[0]) if len(pos) > 0 else 5000
+    K = int(pos[1]) if len(pos) > 1 else 1000
     t0 = time.perf_counter()
     cfg = configs.c5(ny=ny, K=K)
     t_gen = time.perf_counter() - t0
@@ -61,6 +63,23 @@ def main():
                host_gen_s=t_gen, launches=la.launches)
     chk = np.max(np.abs(fit.p_cov - fit.cov) / np.sqrt(np.outer(np.diag(fit.cov), np.diag(fit.cov))))
     out["pcov_vs_cov"] = float(chk)
+    if "--oracle" in sys.argv:
+        # the CPU restatement of the reference on the SAME problem (test infrastructure; minutes at full size)
+        import warnings
+        warnings.simplefilter("ignore")
+        from oracle.fit import nonlinear_fit as ofit
+        t0 = time.perf_counter()
+        fo = ofit("multiexp", cfg["x"], cfg["ymean"], cfg["ycov"], prior_mean=cfg["prior_mean"],
+                  prior_cov=cfg["prior_sdev"], p0=cfg["p0"], svdcut=cfg["svdcut"], tol=cfg["tol"], x_scale="jac")
+        t_cpu = time.perf_counter() - t0
+        sd = fo.psdev
+        out["oracle"] = dict(cpu_s=t_cpu, cores=os.cpu_count(), nit=int(fo.nit), svdn=int(fo.yp_pdf.nmod),
+                             chi2=float(fo.chi2), logGBF=float(fo.logGBF),
+                             max_dp_over_sdev=float(np.max(np.abs(fit.pmean - fo.pmean) / sd)),
+                             chi2_rel_diff=float(abs(fit.chi2 - fo.chi2) / fo.chi2),
+                             max_sdev_rel_diff=float(np.max(np.abs(fit.psdev / sd - 1.0))),
+                             logGBF_rel_diff=float(abs(fit.logGBF - fo.logGBF) / abs(fo.logGBF)),
+                             speedup_whiten_fit_propagate=t_cpu / (fit.times["whiten"] + fit.times["fit"] + 1e-3 * ms_prop))
     print(json.dumps(out))
 
 
