@@ -42,6 +42,7 @@ struct BJArgs {
     int* rotated;           // number of pairs whose sub-problem was not yet diagonal in this sweep
     int* ident;             // [nbe/2] 1 if the pair's Q of this round is the identity
     int inner;              // Jacobi sweeps per sub-problem visit
+    int sort;               // 1: ordering rotations (larger eigenvalue first)
 };
 
 __device__ __forceinline__ bool bj_pair(const BJArgs& a, int pair, int& I, int& J, int& nI, int& nJ) {
@@ -99,7 +100,7 @@ __device__ __forceinline__ void bj_q_update(double* Qs, const double* cs, const 
 }
 
 __device__ __forceinline__ int bj_jacobi64(double* S, double* Qs, int max_sweeps, double* s_cs /*[2][64]*/,
-                                           int* s_any /*[2]*/, const BJTables& tb) {
+                                           int* s_any /*[2]*/, const BJTables& tb, bool sort_desc) {
     const int tid = threadIdx.x;
     int sweeps = 0, g = 0, rprev = -1;
     for (; sweeps < max_sweeps; ++sweeps) {
@@ -125,6 +126,13 @@ __device__ __forceinline__ int bj_jacobi64(double* S, double* Qs, int max_sweeps
                     const double cinv = rsqrt(c2);
                     c = c2 * cinv;
                     sn = (d >= 0.0 ? 0.5 : -0.5) * b * rinv * cinv;
+                    if (sort_desc) {
+                        // de Rijk's ordering: take the rotation that leaves the larger eigenvalue at p (the
+                        // same 2 x 2 diagonalisation composed with a quarter turn) -- sorts the spectrum as
+                        // it converges, which pushes a (near) null space out of the way early
+                        const double t = sn / c;
+                        if (app - t * apq < aqq + t * apq) { const double c_old = c; c = -sn; sn = c_old; }
+                    }
                 }
                 cs[2 * tid] = c;
                 cs[2 * tid + 1] = sn;
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(BJ_DT) bj_diag_kernel(const __grid_constant__ 
     }
     __syncthreads();
     // a few inner sweeps per visit are enough: the outer iteration finishes the job
-    const int nsw = bj_jacobi64(S, Qs, a.inner, s_cs, s_any, tb);
+    const int nsw = bj_jacobi64(S, Qs, a.inner, s_cs, s_any, tb, a.sort != 0);
     if (tid == 0) {
         a.ident[blockIdx.x] = nsw == 0 ? 1 : 0;            // Q == I: the slab kernels skip this pair
         if (nsw > 0) atomicAdd(a.rotated, 1);              // this pair still needed rotations
@@ -492,6 +500,7 @@ int whiten_large(int device, int n, const double* d_cov, double svdcut, double* 
     BJArgs a;
     a.A = A; a.V = V; a.n = n; a.ld = ld; a.nb = nb; a.nbe = nbe; a.Q = Q; a.offsq = offsq; a.rotated = d_rot; a.round = 0; a.ident = d_ident;
     a.inner = getenv("B200LM_BJ_INNER") ? atoi(getenv("B200LM_BJ_INNER")) : 2;
+    a.sort = getenv("B200LM_BJ_SORT") ? atoi(getenv("B200LM_BJ_SORT")) : 0;
     const dim3 gslab((n + 63) / 64, npairs);
     // ||corr||_F^2 <= n^2 (unit diagonal, |corr_ij| <= 1): convergence relative to n (trace)
     const double tol = (double)n * 1e-30 * n;         // off^2 <= (1e-15)^2 * n * trace-ish
