@@ -12,9 +12,12 @@ Weak scaling: every rank fits its own 10^4 copies (different seed).
 Prints ONE JSON line on rank 0.
 """
 import os
-# NCCL writes its version banner to STDOUT at NCCL_DEBUG=VERSION/INFO (read when the library
-# initialises); the contract is ONE JSON line on stdout
-os.environ["NCCL_DEBUG"] = os.environ.get("B200LM_NCCL_DEBUG", "WARN")
+# NCCL writes its version banner to STDOUT at NCCL_DEBUG=VERSION/WARN/INFO; the contract is ONE JSON
+# line on stdout, so NCCL's log goes to stderr (and is off unless B200LM_NCCL_DEBUG asks for it)
+os.environ.pop("NCCL_DEBUG", None)
+if os.environ.get("B200LM_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = os.environ["B200LM_NCCL_DEBUG"]
+os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
 import argparse
 import json
 import os

@@ -9,7 +9,8 @@ shard on its own and compares bit for bit -- the sharded job must give exactly t
   python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_c4_dist.py [nfits]
 """
 import json, os, sys, time
-os.environ["NCCL_DEBUG"] = os.environ.get("B200LM_NCCL_DEBUG", "WARN")
+os.environ.pop("NCCL_DEBUG", None)
+os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import lsqfit_b200 as lb
@@ -20,7 +21,6 @@ local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
-    os.environ["NCCL_DEBUG"] = os.environ.get("B200LM_NCCL_DEBUG", "WARN")
     dist.init_process_group("nccl", device_id=dev)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 cfg = configs.c4(B=B)
