@@ -143,6 +143,73 @@ cudaError_t trsm(int n, int nrhs, const double* L, int ldl, const double* d_linv
     return cudaSuccess;
 }
 
+// Single right-hand side: the whole blocked substitution in ONE CTA (the GEMM-based path above costs
+// 64 launches of tiny products per solve; the trust-region iteration does three solves per
+// factorisation).  The vector lives in shared memory; per 64-wide panel the diagonal block is applied
+// through its stored inverse, then the remaining entries are updated with the panel of L:
+//   forward  (L y = b):   warp per row, lanes across the 64 panel columns  (coalesced 512-byte rows)
+//   backward (L^T x = b): thread per column, walking down the 64 panel rows (coalesced across threads)
+template <int TRANS>
+__global__ void __launch_bounds__(1024) trsv_kernel(int n, const double* __restrict__ L, int ldl,
+                                                    const double* __restrict__ linv, const double* __restrict__ b,
+                                                    double* __restrict__ x) {
+    extern __shared__ double tv_sm[];
+    double* v = tv_sm;            // [n] running right-hand side
+    double* xk = tv_sm + n;       // [64] solution of the current panel
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int i = tid; i < n; i += 1024) v[i] = b[i];
+    __syncthreads();
+    const int nblk = (n + PB - 1) / PB;
+    for (int q = 0; q < nblk; ++q) {
+        const int kb = TRANS ? nblk - 1 - q : q;
+        const int k0 = kb * PB, bs = min(PB, n - k0), k1 = k0 + bs;
+        const double* li = linv + (size_t)kb * PB * PB;
+        // x_k = inv(L_kk) b_k   or   inv(L_kk)^T b_k : 16 lanes per entry
+        {
+            const int i = tid >> 4, sub = tid & 15;
+            double acc = 0.0;
+            if (i < bs)
+                for (int j = sub; j < bs; j += 16) acc = fma(TRANS ? li[j * PB + i] : li[i * PB + j], v[k0 + j], acc);
+            for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, 16);
+            if (i < bs && sub == 0) xk[i] = acc;
+        }
+        __syncthreads();
+        if (tid < bs) x[k0 + tid] = xk[tid];
+        if (!TRANS) {
+            for (int i = k1 + w; i < n; i += 32) {
+                const double* row = L + (size_t)i * ldl + k0;
+                double acc = 0.0;
+                for (int j = lane; j < bs; j += 32) acc = fma(row[j], xk[j], acc);
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) v[i] -= acc;
+            }
+        } else {
+            for (int c = tid; c < k0; c += 1024) {
+                double acc = 0.0;
+                for (int j = 0; j < bs; ++j) acc = fma(L[(size_t)(k0 + j) * ldl + c], xk[j], acc);
+                v[c] -= acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t trsv(int n, const double* L, int ldl, const double* d_linv, int trans, const double* b, double* x,
+                 cudaStream_t s) {
+    const size_t smem = ((size_t)n + PB) * sizeof(double);
+    cudaError_t e;
+    if (trans) {
+        e = cudaFuncSetAttribute(trsv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        trsv_kernel<1><<<1, 1024, smem, s>>>(n, L, ldl, d_linv, b, x);
+    } else {
+        e = cudaFuncSetAttribute(trsv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        trsv_kernel<0><<<1, 1024, smem, s>>>(n, L, ldl, d_linv, b, x);
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace b200lm
 
 using namespace b200lm;
@@ -164,7 +231,11 @@ extern "C" int b200lm_trsm(int device, int n, int nrhs, const double* d_L, int l
         return set_error(nullptr, B200LM_EINVAL, "bad trsm argument");
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
-    e = trsm(n, nrhs, d_L, ldl, d_linv, trans, d_B, ldb, d_X, ldx, (cudaStream_t)stream);
+    // one right-hand side that fits in shared memory: the single-CTA substitution kernel
+    if (nrhs == 1 && ldb == 1 && ldx == 1 && (size_t)(n + 64) * sizeof(double) <= 200 * 1024)
+        e = trsv(n, d_L, ldl, d_linv, trans, d_B, d_X, (cudaStream_t)stream);
+    else
+        e = trsm(n, nrhs, d_L, ldl, d_linv, trans, d_B, ldb, d_X, ldx, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(nullptr, e, "trsm");
     return B200LM_OK;
 }
