@@ -650,7 +650,12 @@ static cudaError_t onesided_eigen(int n, int ld, double* A, double* V, double* Q
     double *Nt = nullptr, *Nt2 = nullptr, *P1 = nullptr, *G = nullptr, *linv = nullptr;
     int *used = nullptr, *pivlist = nullptr, *d_keep = nullptr, *d_slot = nullptr, *d_info = nullptr;
     PCState* st = nullptr;
+    cudaStream_t gs = nullptr;
+    cudaGraphExec_t gexec_pc = nullptr, gexec_sweep = nullptr;
     auto cleanup = [&]() {
+        if (gexec_pc) cudaGraphExecDestroy(gexec_pc);
+        if (gexec_sweep) cudaGraphExecDestroy(gexec_sweep);
+        if (gs) cudaStreamDestroy(gs);
         cudaFree(d); cudaFree(ray); cudaFree(gram); cudaFree(val); cudaFree(scale); cudaFree(Nt); cudaFree(Nt2); cudaFree(P1);
         cudaFree(G); cudaFree(linv); cudaFree(used); cudaFree(pivlist); cudaFree(d_keep); cudaFree(d_slot); cudaFree(d_info);
         cudaFree(st);
@@ -675,18 +680,27 @@ static cudaError_t onesided_eigen(int n, int ld, double* A, double* V, double* Q
     if (!(lam_lo > 0.0)) { cleanup(); return cudaSuccess; }
     const double trace_tol = 1024.0 * 2.220446049250313e-16 * lam_lo;      // LAPACK-level absolute accuracy
     PCState h_st;
-    for (int j = 0; j < n; ++j) {
-        pc_pivot_kernel<<<1, 1024, 0, s>>>(d, used, n, trace_tol, st, pivlist);
-        pc_column_kernel<<<gw, 256, 0, s>>>(A, n, ld, V, d, used, st);
-        if ((j & 127) == 127 || j == n - 1) {
-            OS_TRY(cudaMemcpyAsync(&h_st, st, sizeof(PCState), cudaMemcpyDeviceToHost, s));
-            OS_TRY(cudaStreamSynchronize(s));
-            if (h_st.done) break;
+    // The step kernels take the same arguments every time (the state is on the device), so 128 steps are
+    // captured once into a CUDA graph and replayed: ~10^4 launches would otherwise be paced by the host.
+    OS_TRY(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
+    {
+        cudaGraph_t g = nullptr;
+        OS_TRY(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+        for (int j = 0; j < 128; ++j) {
+            pc_pivot_kernel<<<1, 1024, 0, gs>>>(d, used, n, trace_tol, st, pivlist);
+            pc_column_kernel<<<gw, 256, 0, gs>>>(A, n, ld, V, d, used, st);
         }
+        OS_TRY(cudaStreamEndCapture(gs, &g));
+        OS_TRY(cudaGraphInstantiate(&gexec_pc, g, 0));
+        cudaGraphDestroy(g);
+    }
+    for (int j = 0; j < n; j += 128) {
+        OS_TRY(cudaGraphLaunch(gexec_pc, gs));
+        OS_TRY(cudaMemcpyAsync(&h_st, st, sizeof(PCState), cudaMemcpyDeviceToHost, gs));
+        OS_TRY(cudaStreamSynchronize(gs));
+        if (h_st.done || h_st.ncol >= n) break;
     }
     OS_TRY(cudaGetLastError());
-    OS_TRY(cudaMemcpyAsync(&h_st, st, sizeof(PCState), cudaMemcpyDeviceToHost, s));
-    OS_TRY(cudaStreamSynchronize(s));
     const int r = h_st.ncol;
     if (verbose)
         fprintf(stderr, "whiten_large: pivoted Cholesky rank %d of %d, remaining trace %.3e (lambda_max >= %.3e)  (%.1f ms)\n", r, n,
@@ -709,22 +723,30 @@ static cudaError_t onesided_eigen(int n, int ld, double* A, double* V, double* Q
     double off_prev = 1e300;
     int sweeps = 0;
     bool converged = false;
-    for (; sweeps < 30 && !converged; ++sweeps) {
-        const auto t_sweep = std::chrono::steady_clock::now();
-        OS_TRY(cudaMemsetAsync(offsq, 0, sizeof(double), s));
-        OS_TRY(cudaMemsetAsync(d_rot, 0, sizeof(int), s));
+    {
+        // one sweep = (nbe - 1) x (gram, sub-problems, column update), a strict chain: one graph, replayed
+        cudaGraph_t g = nullptr;
+        OS_TRY(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+        OS_TRY(cudaMemsetAsync(offsq, 0, sizeof(double), gs));
+        OS_TRY(cudaMemsetAsync(d_rot, 0, sizeof(int), gs));
         for (int rd = 0; rd < nbe - 1; ++rd) {
             a.round = rd;
-            os_gram_kernel<<<ggram, BJ_THREADS, sm_gram, s>>>(a, V, n, gram);
-            bj_diag_kernel<<<npairs, BJ_DT, sm_diag, s>>>(a);
-            bj_cols_kernel<<<gslab, BJ_THREADS, sm_slab, s>>>(a, V, n);
+            os_gram_kernel<<<ggram, BJ_THREADS, sm_gram, gs>>>(a, V, n, gram);
+            bj_diag_kernel<<<npairs, BJ_DT, sm_diag, gs>>>(a);
+            bj_cols_kernel<<<gslab, BJ_THREADS, sm_slab, gs>>>(a, V, n);
         }
-        OS_TRY(cudaGetLastError());
+        OS_TRY(cudaStreamEndCapture(gs, &g));
+        OS_TRY(cudaGraphInstantiate(&gexec_sweep, g, 0));
+        cudaGraphDestroy(g);
+    }
+    for (; sweeps < 30 && !converged; ++sweeps) {
+        const auto t_sweep = std::chrono::steady_clock::now();
+        OS_TRY(cudaGraphLaunch(gexec_sweep, gs));
         double h_off = 0.0;
         int h_rot = 0;
-        OS_TRY(cudaMemcpyAsync(&h_off, offsq, sizeof(double), cudaMemcpyDeviceToHost, s));
-        OS_TRY(cudaMemcpyAsync(&h_rot, d_rot, sizeof(int), cudaMemcpyDeviceToHost, s));
-        OS_TRY(cudaStreamSynchronize(s));
+        OS_TRY(cudaMemcpyAsync(&h_off, offsq, sizeof(double), cudaMemcpyDeviceToHost, gs));
+        OS_TRY(cudaMemcpyAsync(&h_rot, d_rot, sizeof(int), cudaMemcpyDeviceToHost, gs));
+        OS_TRY(cudaStreamSynchronize(gs));
         if (verbose)
             fprintf(stderr, "whiten_large: one-sided sweep %d off^2 %.3e rotated pairs %d  (%.1f ms)\n", sweeps, h_off, h_rot,
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_sweep).count());
