@@ -54,7 +54,8 @@ def main():
     out = dict(config=cfg["name"], ny=ny, np=npar, svdn=int(fit.svdn), nit=int(fit.nit), njev=int(njev_fit),
                nfac=int(nfac_fit), first_call=first, stopping_criterion=int(fit.stopping_criterion), error=fit.error,
                chi2=fit.chi2, dof=fit.dof, Q=fit.Q, logGBF=fit.logGBF,
-               whiten_s=fit.times["whiten"], fit_s=fit.times["fit"],
+               whiten_s=min(fit.times["whiten"], first["whiten"]), whiten_s_calls=[first["whiten"], fit.times["whiten"]],
+               fit_s=fit.times["fit"],
                per_iteration_ms=1e3 * fit.times["fit"] / max(1, fit.nit),
                jacobian_eval_ms=ms_jac, jacobian_tflops=f_jac / ms_jac * 1e-9,
                residual_eval_ms=ms_res, factor_solve_ms=ms_fac, potrf_ms=ms_potrf,
