@@ -13,7 +13,7 @@ from .functors import Functor, FAMILY, NIST_FORM
 from .engine import Plan, BatchResult, STOPPING_CRITERION, normalize_tol
 from .whiten import PDF, cov_blocks
 from .fitter import b200_lm, ChivSpec, DeviceChiv
-from .fit import nonlinear_fit, gammaQ, BatchFits, FitView
+from .fit import nonlinear_fit, gammaQ, BatchFits, FitView, wavg, WAvg
 from .dense import DenseFit
 from .bootstrap import bootstrap_means, normals
 

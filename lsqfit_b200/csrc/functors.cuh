@@ -30,7 +30,7 @@ namespace b200lm {
 // family ids (stable ABI; mirrored in lsqfit_b200/functors.py)
 enum FunctorFamily : int {
     F_MULTIEXP = 0, F_MULTIEXP_DE = 1, F_SIMPLE = 2, F_OFFSET_EXP = 3, F_POLY = 4,
-    F_EXP_POLY = 5, F_XERR_LOGISTIC = 6,
+    F_EXP_POLY = 5, F_XERR_LOGISTIC = 6, F_GATHER = 7,
     F_MISRA1A = 10, F_CHWIRUT = 11, F_LANCZOS = 12, F_GAUSS = 13, F_DANWOOD = 14,
     F_MISRA1B = 15, F_MISRA1C = 16, F_MISRA1D = 17, F_KIRBY2 = 18, F_HAHN1 = 19,
     F_NELSON = 20, F_MGH17 = 21, F_ROSZMAN1 = 22, F_ENSO = 23, F_MGH09 = 24,
@@ -146,6 +146,29 @@ struct Poly {
         double tn = 1.0, f = 0.0;
 #pragma unroll 1
         for (int n = 0; n < NP; ++n) { g[n] = w * tn; f = fma(p[n], tn, f); tn *= t; }
+        return f;
+    }
+};
+
+// f_i = p[idx_i], idx_i = (int) x_i: the model behind lsqfit.wavg (reference src/lsqfit/_extras.py:499-507:
+// every datum is an estimate of one component of p; ragged inputs simply use fewer indices)
+template <int NP_>
+struct Gather {
+    static constexpr int NP = NP_;
+    static constexpr int NX = 1;
+    __device__ __forceinline__ static double value(const double* __restrict__ x, int, const double* p) {
+        const int k = (int)x[0];
+        double f = 0.0;
+#pragma unroll
+        for (int n = 0; n < NP; ++n) f = (n == k) ? p[n] : f;
+        return f;
+    }
+    __device__ __forceinline__ static double value_grad(const double* __restrict__ x, int,
+                                                        const double* p, double w, double* g) {
+        const int k = (int)x[0];
+        double f = 0.0;
+#pragma unroll
+        for (int n = 0; n < NP; ++n) { g[n] = (n == k) ? w : 0.0; f = (n == k) ? p[n] : f; }
         return f;
     }
 };

@@ -292,3 +292,44 @@ class BatchFits(object):
         m = x.mean(dim=0)
         d = x - m
         return m.cpu().numpy(), (d.T @ d / max(1, x.shape[0] - 1)).cpu().numpy()
+
+
+class WAvg(object):
+    """Result of ``wavg``: ``mean``, ``cov``, ``sdev`` of the average plus the attributes the reference
+    attaches (``chi2 dof Q time svdcorrection-free fit``; src/lsqfit/_extras.py:412-431)."""
+
+    def __init__(self, fit):
+        self.fit = fit
+        self.mean, self.cov, self.sdev = fit.pmean, fit.cov, fit.psdev
+        self.chi2, self.dof, self.Q, self.time = fit.chi2, fit.dof, fit.Q, fit.time
+        self.svdn = fit.svdn
+
+
+def wavg(means, cov, index=None, nparam=None, svdcut=1e-12, eps=None, **fitterargs):
+    """Weighted average of correlated estimates (array form of ``lsqfit.wavg``,
+    src/lsqfit/_extras.py:358-516): a least-squares fit of the data ``means`` (flat, covariance ``cov``:
+    matrix or vector of standard deviations) to ``f_i = p[index[i]]`` without a prior, started at the
+    plain average of the inputs (:478-494) -- run on the device with the ``gather`` functor.
+
+    ``means`` may be 2-d ``[M, np]`` (M estimates of np quantities; then ``index`` defaults to
+    ``arange(np)`` tiled M times); ragged inputs pass a flat ``means`` and an explicit ``index``."""
+    means = np.asarray(means, dtype=float)
+    if index is None:
+        if means.ndim != 2:
+            means = means.reshape(-1, 1)
+        M, npar = means.shape
+        index = np.tile(np.arange(npar), M)
+    index = np.asarray(index, dtype=int).reshape(-1)
+    y = means.reshape(-1)
+    if index.size != y.size:
+        raise ValueError("index and means disagree on the number of data")
+    npar = int(index.max()) + 1 if nparam is None else int(nparam)
+    p0 = np.zeros(npar)
+    cnt = np.zeros(npar)
+    np.add.at(p0, index, y)
+    np.add.at(cnt, index, 1.0)
+    if np.any(cnt == 0):
+        raise ValueError("every component of the average needs at least one datum")
+    fit = nonlinear_fit(data=(index.astype(float), y, cov), fcn=Functor("gather"), p0=p0 / cnt, svdcut=svdcut, eps=eps,
+                        **fitterargs)
+    return WAvg(fit)

@@ -12,7 +12,7 @@ import numpy as np
 
 # family ids == enum FunctorFamily in csrc/functors.cuh
 FAMILY = dict(
-    multiexp=0, multiexp_de=1, simple=2, offset_exp=3, poly=4, exp_poly=5, xerr_logistic=6,
+    multiexp=0, multiexp_de=1, simple=2, offset_exp=3, poly=4, exp_poly=5, xerr_logistic=6, gather=7,
     misra1a=10, chwirut=11, lanczos=12, gauss=13, danwood=14, misra1b=15, misra1c=16,
     misra1d=17, kirby2=18, hahn1=19, nelson=20, mgh17=21, roszman1=22, enso=23, mgh09=24,
     rat42=25, mgh10=26, eckerle4=27, rat43=28, bennett5=29,
@@ -88,6 +88,7 @@ _HOST = dict(
     poly=_poly,
     exp_poly=lambda x, p: np.exp(-_poly(x, p)),
     xerr_logistic=_xerr,
+    gather=lambda x, p: np.asarray(p)[np.asarray(_col(x)).astype(int)],
     misra1a=lambda x, b: b[0] * (1 - np.exp(-b[1] * _col(x))),
     chwirut=lambda x, b: np.exp(-b[0] * _col(x)) / (b[1] + b[2] * _col(x)),
     lanczos=lambda x, b: (b[0] * np.exp(-b[1] * _col(x)) + b[2] * np.exp(-b[3] * _col(x))

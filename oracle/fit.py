@@ -127,3 +127,22 @@ class nonlinear_fit(object):
         out = self.flatfcn(D.Dual.variables(p))
         G = D.deriv(out, self.pmean.size)
         return D.value(out), G @ self.p_cov @ G.T
+
+
+def wavg(means, cov, index=None, svdcut=1e-12, eps=None, **fitterargs):
+    """lsqfit.wavg in array form (reference src/lsqfit/_extras.py:358-516): fit of the data to
+    f_i = p[index[i]] with no prior, p0 = plain average of the inputs (:478-494)."""
+    means = np.asarray(means, dtype=float)
+    if index is None:
+        if means.ndim != 2:
+            means = means.reshape(-1, 1)
+        M, npar = means.shape
+        index = np.tile(np.arange(npar), M)
+    index = np.asarray(index, dtype=int).reshape(-1)
+    y = means.reshape(-1)
+    npar = int(index.max()) + 1
+    p0 = np.zeros(npar)
+    cnt = np.zeros(npar)
+    np.add.at(p0, index, y)
+    np.add.at(cnt, index, 1.0)
+    return nonlinear_fit("gather", index.astype(float)[:, None], y, cov, p0=p0 / cnt, svdcut=svdcut, eps=eps, **fitterargs)

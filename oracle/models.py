@@ -85,6 +85,11 @@ def xerr_logistic(x, p):
     return b0 / ((1.0 + exp(b1 - b2 * xi)) ** (1.0 / b3))
 
 
+def gather(x, p):
+    """f_i = p[idx_i]: the fit function lsqfit.wavg builds (src/lsqfit/_extras.py:499-507)."""
+    return p[np.asarray(_x(x)).astype(int)]
+
+
 # ---- NIST StRD forms (examples/nist.py:<line>) ------------------------------
 
 def misra1a(x, b):          # :112 (also boxbod :1114)
@@ -188,7 +193,7 @@ def bennett5(x, b):         # :1291
 MODELS = dict(
     multiexp=multiexp, multiexp_de=multiexp_de, simple=simple,
     offset_exp=offset_exp, poly=poly, exp_poly=exp_poly,
-    xerr_logistic=xerr_logistic,
+    xerr_logistic=xerr_logistic, gather=gather,
     misra1a=misra1a, chwirut=chwirut, lanczos=lanczos, gauss=gauss,
     danwood=danwood, misra1b=misra1b, misra1c=misra1c, misra1d=misra1d,
     kirby2=kirby2, hahn1=hahn1, nelson=nelson, mgh17=mgh17,

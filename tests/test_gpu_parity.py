@@ -738,3 +738,42 @@ def test_edge_cases():
     with pytest.raises(lb.B200LMError):
         plan.fit_batch(y, pm, maxit=0)
     plan.close()
+
+
+def test_wavg_goldens_and_batch():
+    """Device ``wavg`` (gather functor, no prior) vs the reference's known answers
+    (tests/test_lsqfit.py:581-596) and vs the oracle; a batch of averages in one launch."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from oracle.fit import wavg as owavg
+    C3 = np.array([[0.5, 0.25, 0.5], [0.25, 0.5, 0.5], [0.5, 0.5, 1.0]])
+    assert abs(lb.wavg([1.0, 1.0, 1.0], C3, index=[0, 0, 0], svdcut=1 - 1e-16).cov[0, 0] - 0.4561552812808828) < 1e-12
+    assert abs(lb.wavg([1.0, 1.0, 1.0], C3, index=[0, 0, 0], svdcut=1e-18).cov[0, 0] - 1.0 / 3.0) < 1e-9
+    assert abs(lb.wavg([1.0, 1.0, 1.0], np.ones(3), index=[0, 0, 0]).cov[0, 0] - 1.0 / 3.0) < 1e-12
+    cov = np.zeros((4, 4))
+    cov[np.ix_([0, 1], [0, 1])] = 1.0
+    cov[np.ix_([2, 3], [2, 3])] = 100.0
+    w = lb.wavg([[2.1, 6.1], [1.9, 5.9]], cov)
+    np.testing.assert_allclose(w.mean, [2.09802, 6.09802], rtol=1e-4)
+    np.testing.assert_allclose(w.sdev, [0.995037, 0.995037], rtol=1e-4)
+    # correlated, ragged: 5 estimates of p0, 3 of p1, 4 of p2
+    rng = np.random.default_rng(3)
+    index = np.array([0, 1, 2, 0, 1, 2, 0, 2, 0, 1, 2, 0])
+    A = rng.standard_normal((12, 12))
+    cov = A @ A.T / 12 + 0.5 * np.eye(12)
+    y = np.array([1.0, 2.0, 3.0])[index] + np.linalg.cholesky(cov) @ rng.standard_normal(12)
+    d, o = lb.wavg(y, cov, index=index, tol=TIGHT, polish=5), owavg(y, cov, index=index, tol=TIGHT)
+    assert d.dof == o.dof == 9
+    assert np.max(np.abs(d.mean - o.pmean) / o.psdev) < 1e-8
+    assert abs(d.chi2 - o.chi2) <= 1e-9 * o.chi2
+    assert _rel_cov(d.cov, o.cov) < 1e-8
+    assert abs(d.Q - o.Q) < 1e-9
+    # the same average for 1000 bootstrap copies of the inputs in ONE launch
+    ys = y[None, :] + (np.linalg.cholesky(cov) @ rng.standard_normal((12, 1000))).T
+    out = d.fit._chiv.b200.plan(0).fit_batch(ys, d.mean, tol=TIGHT, polish=5).numpy()
+    Wt = np.linalg.inv(cov)
+    G = np.zeros((12, 3))
+    G[np.arange(12), index] = 1.0
+    exact = np.linalg.solve(G.T @ Wt @ G, G.T @ Wt @ ys.T).T          # the linear least-squares answer
+    assert np.max(np.abs(out["x"] - exact) / d.sdev[None, :]) < 1e-8
+    assert np.all(out["status"] > 0) and out["nit"].max() <= 4

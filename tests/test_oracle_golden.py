@@ -63,11 +63,13 @@ def test_model_jacobians_fd():
                 "lanczos": 6, "gauss": 8, "danwood": 2, "misra1b": 2, "misra1c": 2,
                 "misra1d": 2, "kirby2": 5, "hahn1": 7, "nelson": 3, "mgh17": 5,
                 "roszman1": 4, "enso": 9, "mgh09": 4, "rat42": 3, "mgh10": 3,
-                "eckerle4": 3, "rat43": 4, "bennett5": 3}[name]
+                "eckerle4": 3, "rat43": 4, "bennett5": 3, "gather": 3}[name]
         ny = 7
         x = rng.uniform(0.5, 2.0, size=(ny, 2))
         if name == "simple":
             x[:, 1] = [0, 0, 0, 1, 0, 1, 0]
+        if name == "gather":
+            x[:, 0] = [0, 1, 2, 2, 0, 1, 0]
         p = rng.uniform(0.5, 1.5, size=npar)
         f, G = M.value_and_jacobian(name, x, p)
         for j in range(npar):
@@ -271,3 +273,27 @@ def test_whiten_negative_svdcut_drops_modes():
     assert pdf.nchiv == 3 and pdf.nmod == 3
     blocks = cov_blocks(np.diag([1., 2, 3]))
     assert list(blocks[0]) == [0, 1, 2] and blocks[1] == []
+
+
+def _wavg_cases():
+    """Inputs of reference tests/test_lsqfit.py:581-596 as arrays: (a+b)/2, (a+c)/2, a with a, b, c = 1(1)."""
+    C3 = np.array([[0.5, 0.25, 0.5], [0.25, 0.5, 0.5], [0.5, 0.5, 1.0]])
+    return C3
+
+
+def test_wavg_known_answers():
+    """lsqfit.wavg known answers (reference tests/test_lsqfit.py:581-596): svd-cut variances
+    0.4561552812808828 and 1/3, and the array average [2.09802, 6.09802] +- 0.995037."""
+    from oracle.fit import wavg
+    C3 = _wavg_cases()
+    assert abs(wavg([1.0, 1.0, 1.0], C3, index=[0, 0, 0], svdcut=1 - 1e-16).cov[0, 0] - 0.4561552812808828) < 1e-12
+    assert abs(wavg([1.0, 1.0, 1.0], C3, index=[0, 0, 0], svdcut=1e-18).cov[0, 0] - 1.0 / 3.0) < 1e-9
+    assert abs(wavg([1.0, 1.0, 1.0], np.ones(3), index=[0, 0, 0]).cov[0, 0] - 1.0 / 3.0) < 1e-12
+    # [gvar(2.1,1), 4+gvar(2.1,1)] and [gvar(1.9,10), 4+gvar(1.9,10)]: the two components of each estimate are
+    # the same random variable (fully correlated within an estimate)
+    cov = np.zeros((4, 4))
+    cov[np.ix_([0, 1], [0, 1])] = 1.0
+    cov[np.ix_([2, 3], [2, 3])] = 100.0
+    f = wavg([[2.1, 6.1], [1.9, 5.9]], cov)
+    np.testing.assert_allclose(f.pmean, [2.09802, 6.09802], rtol=1e-4)
+    np.testing.assert_allclose(f.psdev, [0.995037, 0.995037], rtol=1e-4)
