@@ -495,7 +495,9 @@ __device__ __noinline__ bool factor_solve(const double* A, const double* dsc, do
         __syncwarp();
         const double* lt = LT + j * LDA + j;                         // lt[m] = L[j+m][j]
 #pragma unroll
-        for (int m = 1; m < NP; ++m) r[m - 1] = fma(-lij, lt[m], r[m]);   // entries past the row end are junk, never used
+        // entries past the row end are junk and never used (they alias the next row of LT, which the next
+        // step overwrites: compute-sanitizer racecheck reports that write-after-read as a warning; benign)
+        for (int m = 1; m < NP; ++m) r[m - 1] = fma(-lij, lt[m], r[m]);
         r[NP - 1] = 0.0;
     }
     ok = __all_sync(B200LM_FULL, ok);
@@ -820,6 +822,7 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
                 cost = cost_new;
                 __syncwarp();
                 if (act && P.scaler == 1) sinv = fmax(sinv, sqrt(c.A[lane * LDA + lane]));
+                __syncwarp();      // the diagonal has been read before anything (polish, QR pass) reuses this buffer
             }
             if (term != -2) {
                 // the solver behind the reference re-tests gtol before leaving (trf.py loop head)
