@@ -17,7 +17,7 @@ def timed(fn, reps=3):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps, out
 
-res = dict(nist=[], c4=None)
+res = dict(nist=[], c4=None, c1=None)
 probs = json.load(open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "nist.json")))["problems"]
 B = 10000
 for k, pr in enumerate(probs):
@@ -73,5 +73,25 @@ res["c4"].update(generate_ms=tg, pipeline_ms=tp, pipeline_fits_per_s=n4 / tp * 1
                  pmean_bias_sigma=float(torch.max(torch.abs(xm - p0d) / oo.x.std(dim=0) * (n4 ** 0.5))))
 print("C4 device pipeline: generate %.2f ms, generate+fit+stats %.2f ms (%.0f fits/s), |<p>-pexact| = %.2f sigma_mean" % (
     tg, tp, n4 / tp * 1e3, res["c4"]["pmean_bias_sigma"]))
+# ---- C1: examples/simple.py, ONE fit -- latency of the whole call (device launch and host-buffer call)
+ex = json.load(open(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "examples.json")))["examples"]["simple"]
+ny1 = len(ex["ymean"]); yc = np.zeros((ny1, ny1)); i = 0
+for b in ex["ycov_blocks"]:
+    b = np.array(b); yc[i:i + len(b), i:i + len(b)] = b; i += len(b)
+t0 = time.perf_counter()
+f1 = lb.nonlinear_fit(data=(np.array(ex["x"]), ex["ymean"], yc), fcn="simple", prior=(ex["prior_mean"], ex["prior_sdev"]))
+t_first = time.perf_counter() - t0
+plan1 = f1._spec.plan(0)
+mean1 = np.concatenate([ex["ymean"], ex["prior_mean"]]); p01 = f1.p0
+md1 = torch.as_tensor(mean1).cuda(); pd1 = torch.as_tensor(p01).cuda()
+t_dev, _ = timed(lambda: plan1.fit_batch(md1, pd1), reps=50)
+for _ in range(5): plan1.fit_batch_host(mean1[None, :], p01)
+t0 = time.perf_counter()
+for _ in range(50): plan1.fit_batch_host(mean1[None, :], p01)
+t_host = (time.perf_counter() - t0) / 50
+res["c1"] = dict(device_launch_us=1e3 * t_dev, host_call_us=1e6 * t_host, full_nonlinear_fit_ms=1e3 * t_first, nit=int(f1.nit),
+                 chi2_dof=float(f1.chi2 / f1.dof))
+print("C1 simple.py single fit: device launch %.0f us, host-buffer call %.0f us, whole nonlinear_fit (whitening, fit, results) %.1f ms, nit %d" % (
+    1e3 * t_dev, 1e6 * t_host, 1e3 * t_first, f1.nit))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/configs_r01.json", "w"), indent=1)
