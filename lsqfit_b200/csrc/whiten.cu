@@ -227,6 +227,8 @@ using namespace b200lm;
 namespace b200lm {
 int whiten_large(int device, int n, const double* d_cov, double svdcut, double* d_w, double* d_cov_out,
                  int* d_nout, int* d_nmod, double* d_logdet, cudaStream_t stream);
+int whiten_large_eps(int device, int n, const double* d_cov, double eps, double* d_w, double* d_cov_out,
+                     int* d_nout, int* d_nmod, double* d_logdet, cudaStream_t stream);
 }
 
 extern "C" int b200lm_whiten(int device, int nblk, const int* h_n, const double* d_cov,
@@ -261,7 +263,9 @@ extern "C" int b200lm_whiten(int device, int nblk, const int* h_n, const double*
             int rc;
             if (h_n[k] > (use_eps ? WH_NMAX : large_min)) {
                 if (use_eps)
-                    return set_error(nullptr, B200LM_ESIZE, "eps (Cholesky) regulator is not implemented for blocks > 512");
+                    rc = whiten_large_eps(device, h_n[k], d_cov + off[k], eps, d_w + off[k], d_cov_out + off[k],
+                                          d_nout + k, d_nmod + k, d_logdet + k, s);
+                else
                 rc = whiten_large(device, h_n[k], d_cov + off[k], svdcut, d_w + off[k], d_cov_out + off[k],
                                   d_nout + k, d_nmod + k, d_logdet + k, s);
             } else {

@@ -1007,4 +1007,80 @@ int whiten_large(int device, int n, const double* d_cov, double svdcut, double* 
     return B200LM_OK;
 }
 
+// ---- eps (Cholesky) regulator for large blocks: corr + eps |corr|_inf I = L L^T,  W = L^-1 D ------------------
+// (gvar.regulate / gvar.PDF(eps=...) as the reference uses them at src/lsqfit/__init__.py:1895-1898; semantics
+// as in the small-block kernel and oracle/whiten.py: whiten_block_eps -- parity unpinned)
+__global__ void wl_rowabs_kernel(const double* __restrict__ A, int n, int ld, double* __restrict__ rowsum) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    double acc = 0.0;
+    for (int j = lane; j < n; j += 32) acc += fabs(A[(size_t)w * ld + j]);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) rowsum[w] = acc;
+}
+// W[r][j] = Linv[r][j] D[j]   and   cov_out = cov + shift diag(cov)
+__global__ void wl_eps_out_kernel(const double* __restrict__ X, int n, int ld, const double* __restrict__ Dv,
+                                  const double* __restrict__ cov, double shift, double* __restrict__ W,
+                                  double* __restrict__ cov_out) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)n * n) return;
+    const int r = (int)(e / n), j = (int)(e % n);
+    W[e] = j <= r ? X[(size_t)r * ld + j] * Dv[j] : 0.0;
+    cov_out[e] = cov[e] + (r == j ? shift * cov[e] : 0.0);
+}
+__global__ void wl_logdiag_kernel(const double* __restrict__ L, int n, int ld, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = log(L[(size_t)i * ld + i]);
+}
+
+int whiten_large_eps(int device, int n, const double* d_cov, double eps, double* d_w, double* d_cov_out,
+                     int* d_nout, int* d_nmod, double* d_logdet, cudaStream_t s) {
+    (void)device;
+    const int ld = (n + 1) & ~1;
+    double *A = nullptr, *V = nullptr, *X = nullptr, *Dv = nullptr, *tmp = nullptr, *linv = nullptr;
+    int* d_info = nullptr;
+    auto cleanup = [&]() { cudaFree(A); cudaFree(V); cudaFree(X); cudaFree(Dv); cudaFree(tmp); cudaFree(linv); cudaFree(d_info); };
+    WL_TRY(cudaMalloc((void**)&A, (size_t)n * ld * sizeof(double)));
+    WL_TRY(cudaMalloc((void**)&V, (size_t)n * ld * sizeof(double)));
+    WL_TRY(cudaMalloc((void**)&X, (size_t)n * ld * sizeof(double)));
+    WL_TRY(cudaMalloc((void**)&Dv, n * sizeof(double)));
+    WL_TRY(cudaMalloc((void**)&tmp, n * sizeof(double)));
+    WL_TRY(cudaMalloc((void**)&linv, (size_t)((n + 63) / 64) * 4096 * sizeof(double)));
+    WL_TRY(cudaMalloc((void**)&d_info, sizeof(int)));
+    const int tpb = 256;
+    const unsigned gnn = (unsigned)(((size_t)n * n + tpb - 1) / tpb);
+    wl_init_kernel<<<gnn, tpb, 0, s>>>(d_cov, n, A, V, ld, Dv);          // A = corr, V = I, Dv = 1/sd
+    double shift = 0.0;
+    std::vector<double> h(n);
+    if (eps > 0.0) {
+        wl_rowabs_kernel<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, s>>>(A, n, ld, tmp);
+        WL_TRY(cudaMemcpyAsync(h.data(), tmp, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        WL_TRY(cudaStreamSynchronize(s));
+        double nrm = 0.0;
+        for (int i = 0; i < n; ++i) nrm = std::max(nrm, h[i]);
+        shift = eps * nrm;
+    }
+    WL_TRY(potrf(n, A, ld, shift, A, ld, linv, d_info, s));
+    int h_info = 0;
+    WL_TRY(cudaMemcpyAsync(&h_info, d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
+    WL_TRY(cudaStreamSynchronize(s));
+    if (h_info != 0) { cleanup(); return set_error(nullptr, B200LM_EINVAL, "whiten (eps): covariance block is not positive definite"); }
+    WL_TRY(trsm(n, n, A, ld, linv, 0, V, ld, X, ld, s));                  // X = L^-1
+    wl_eps_out_kernel<<<gnn, tpb, 0, s>>>(X, n, ld, Dv, d_cov, shift, d_w, d_cov_out);
+    wl_logdiag_kernel<<<(n + tpb - 1) / tpb, tpb, 0, s>>>(A, n, ld, tmp);
+    WL_TRY(cudaMemcpyAsync(h.data(), tmp, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    std::vector<double> hD(n);
+    WL_TRY(cudaMemcpyAsync(hD.data(), Dv, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    WL_TRY(cudaStreamSynchronize(s));
+    double logdet = 0.0;
+    for (int i = 0; i < n; ++i) logdet += 2.0 * h[i] - 2.0 * log(hD[i]);
+    const int nmod = eps > 0.0 ? n : 0;
+    WL_TRY(cudaMemcpyAsync(d_nout, &n, sizeof(int), cudaMemcpyHostToDevice, s));
+    WL_TRY(cudaMemcpyAsync(d_nmod, &nmod, sizeof(int), cudaMemcpyHostToDevice, s));
+    WL_TRY(cudaMemcpyAsync(d_logdet, &logdet, sizeof(double), cudaMemcpyHostToDevice, s));
+    WL_TRY(cudaStreamSynchronize(s));
+    cleanup();
+    return B200LM_OK;
+}
+
 }  // namespace b200lm

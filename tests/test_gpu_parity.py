@@ -777,3 +777,31 @@ def test_wavg_goldens_and_batch():
     exact = np.linalg.solve(G.T @ Wt @ G, G.T @ Wt @ ys.T).T          # the linear least-squares answer
     assert np.max(np.abs(out["x"] - exact) / d.sdev[None, :]) < 1e-8
     assert np.all(out["status"] > 0) and out["nit"].max() <= 4
+
+
+@pytest.mark.parametrize("n,eps", [(600, 1e-12), (700, 1e-3), (130, 1e-6)])
+def test_large_block_eps_regulator_vs_oracle(n, eps):
+    """eps (Cholesky) regulator on blocks beyond the single-CTA kernel: corr + eps |corr|_inf I = L L^T,
+    W = L^-1 D on the blocked Cholesky / triangular solve (parity unpinned in the reference: checked against
+    the oracle restatement, like the small-block branch)."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from oracle.whiten import PDF as OPDF
+    rng = np.random.default_rng(n)
+    idx = np.arange(n)
+    base = np.exp(-np.abs(idx[:, None] - idx[None, :]) / 30.0)
+    sig = rng.uniform(0.5, 2.0, size=n) * 1e-2
+    cov = base * sig[:, None] * sig[None, :]
+    o = OPDF(np.zeros(n), cov, svdcut=None, eps=eps)
+    d = lb.PDF(np.zeros(n), cov, svdcut=None, eps=eps)
+    assert d.nmod == o.nmod and d.nchiv == o.nchiv == n
+    np.testing.assert_allclose(d.logdet, o.logdet, rtol=1e-10)
+    Wd, Wo = d.i_invwgts[1][1], o.i_invwgts[1][1]
+    assert Wd.shape == Wo.shape == (n, n)
+    icd, ico = Wd.T @ Wd, Wo.T @ Wo
+    sc = np.sqrt(np.diag(ico))
+    assert np.max(np.abs(icd - ico) / (sc[:, None] * sc[None, :])) < 1e-8
+    sc = np.sqrt(np.diag(o.cov))
+    assert np.max(np.abs(d.cov - o.cov) / (sc[:, None] * sc[None, :])) < 1e-13
+    z = rng.standard_normal(n)
+    np.testing.assert_allclose(np.sum((Wd @ z) ** 2), np.sum((Wo @ z) ** 2), rtol=1e-9)
