@@ -527,15 +527,17 @@ def test_dgemm_vs_torch():
 
 
 @pytest.mark.parametrize("n,cut", [(600, 1e-8), (1100, 1e-6), (777, -1e-6), (640, 0.0), (113, 1e-8), (200, -1e-6),
-                                   (331, 1e-10)])
+                                   (331, 1e-10), (-700, 1e-8), (-450, 1e-3)])
 def test_large_block_whitening_vs_oracle(n, cut):
     """Blocks beyond the shared-memory single-CTA kernel (n > 112) go through the block-Jacobi solver
     (csrc/whiten_large.cu); config-5 style input: a rank-deficient sample covariance."""
     _need_gpu()
     import lsqfit_b200 as lb
     from oracle.whiten import PDF as OPDF
+    full_rank = n < 0 or cut == 0.0                  # negative n: full-rank block with a positive svd cut
+    n = abs(n)
     rng = np.random.default_rng(n)
-    ns = n // 2 if cut != 0.0 else 2 * n             # fewer samples than dimensions -> singular
+    ns = 2 * n if full_rank else n // 2              # fewer samples than dimensions -> singular
     idx = np.arange(n)
     base = np.exp(-np.abs(idx[:, None] - idx[None, :]) / 50.0)
     L = np.linalg.cholesky(base + 1e-10 * np.eye(n))
