@@ -38,6 +38,19 @@ cudaError_t dgemm(bool transA, bool transB, int batch, int M, int N, int K, doub
     g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
     g.A = A; g.sA = sA; g.lda = lda; g.B = B; g.sB = sB; g.ldb = ldb; g.C = C; g.sC = sC; g.ldc = ldc;
     g.lower = lower ? 1 : 0;
+    if (M <= 32 && batch >= 64 && !lower) {
+        // many small products: the small-tile kernel
+        for (int b0 = 0; b0 < batch; b0 += 65535) {
+            GemmArgs h = g;
+            h.A += (size_t)b0 * g.sA; h.B += (size_t)b0 * g.sB; h.C += (size_t)b0 * g.sC;
+            const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+            dim3 grid((N + SM_N - 1) / SM_N, (M + SM_M - 1) / SM_M, nb);
+            dgemm_small_kernel<<<grid, SM_THREADS, 0, stream>>>(h, transA ? 1 : 0, transB ? 1 : 0);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     const bool aligned = ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && (lda % 2 == 0) && (ldb % 2 == 0) &&
                          (sA % 2 == 0) && (sB % 2 == 0);
     // A_KC: A stored [M][K]  <=> !transA ;  B_KC: B stored [N][K] <=> transB

@@ -176,6 +176,60 @@ __global__ void __launch_bounds__(GTHREADS, 1) dgemm_kernel(const __grid_constan
     }
 }
 
+// Many small products (batched fit.p propagation: M = np <= 32 rows per fit): the 128 x 128 tile above would
+// be > 85 % padding.  CTA tile 16 x 64 x 16, 4 warps (warp w: both 8-row tiles x column tiles 2w, 2w+1),
+// plain loads through shared memory -- thousands of CTAs per launch hide the latency.
+constexpr int SM_M = 16, SM_N = 64, SM_K = 16, SM_THREADS = 128;
+static __global__ void __launch_bounds__(SM_THREADS) dgemm_small_kernel(const __grid_constant__ GemmArgs g, int transA, int transB) {
+    __shared__ double As[SM_M][SM_K + 4];          // [m][k]
+    __shared__ double Bs[SM_K][SM_N + 8];          // [k][n]
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int m0 = blockIdx.y * SM_M, n0 = blockIdx.x * SM_N;
+    const double* A = g.A + (size_t)blockIdx.z * g.sA;
+    const double* B = g.B + (size_t)blockIdx.z * g.sB;
+    double* C = g.C + (size_t)blockIdx.z * g.sC;
+    double acc[2][2][2] = {};
+    for (int k0 = 0; k0 < g.K; k0 += SM_K) {
+        for (int e = tid; e < SM_M * SM_K; e += SM_THREADS) {
+            const int m = e / SM_K, k = e % SM_K;
+            const int gm = m0 + m, gk = k0 + k;
+            As[m][k] = (gm < g.M && gk < g.K) ? (transA ? A[(size_t)gk * g.lda + gm] : A[(size_t)gm * g.lda + gk]) : 0.0;
+        }
+        for (int e = tid; e < SM_K * SM_N; e += SM_THREADS) {
+            int k, n;
+            if (transB) { n = e / SM_K; k = e % SM_K; } else { k = e / SM_N; n = e % SM_N; }   // contiguous global reads
+            const int gk = k0 + k, gn = n0 + n;
+            Bs[k][n] = (gk < g.K && gn < g.N) ? (transB ? B[(size_t)gn * g.ldb + gk] : B[(size_t)gk * g.ldb + gn]) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s4 = 0; s4 < SM_K; s4 += 4) {
+            double af[2], bf[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) af[i] = As[8 * i + (lane >> 2)][s4 + (lane & 3)];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) bf[j] = Bs[s4 + (lane & 3)][16 * w + 8 * j + (lane >> 2)];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) gemm_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + 8 * i + (lane >> 2);
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int n = n0 + 16 * w + 8 * j + 2 * (lane & 3);
+            double* cp = C + (size_t)m * g.ldc + n;
+            if (n < g.N) cp[0] = g.beta != 0.0 ? fma(g.alpha, acc[i][j][0], g.beta * cp[0]) : g.alpha * acc[i][j][0];
+            if (n + 1 < g.N) cp[1] = g.beta != 0.0 ? fma(g.alpha, acc[i][j][1], g.beta * cp[1]) : g.alpha * acc[i][j][1];
+        }
+    }
+}
+
 template <bool A_KC, bool B_KC>
 inline size_t dgemm_smem_bytes() {
     return (size_t)GSTAGES * ((A_KC ? TILE_KC : TILE_MN) + (B_KC ? TILE_KC : TILE_MN)) * sizeof(double);

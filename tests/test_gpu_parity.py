@@ -520,6 +520,8 @@ def test_dgemm_vs_torch():
             run(tA, tB, 1, 128, 128, 64)
             run(tA, tB, 1, 257, 131, 77)                 # ragged edges
             run(tA, tB, 3, 16, 80, 16, shareB=True)      # propagate-like: tiny M, shared B
+            run(tA, tB, 100, 16, 80, 80, shareB=True)    # many small products: the small-tile kernel
+            run(tA, tB, 70, 19, 99, 35, alpha=1.5, beta=-0.5)
             run(tA, tB, 2, 100, 50, 33, pad=1)           # odd leading dimension -> scalar-copy path
             run(tA, tB, 1, 300, 200, 500, alpha=-0.5, beta=2.0)
     run(False, False, 1, 1, 1, 1)
