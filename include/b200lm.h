@@ -131,12 +131,14 @@ int b200lm_residual_jacobian(b200lm_handle h, int B, const double* d_p, long lon
  * (call sites src/lsqfit/__init__.py:1895,1898; semantics doc/source/overview.rst:1546-1611).
  * Batched over nblk blocks on `device`; block k is n[k] x n[k], stored contiguously one
  * after another in d_cov (row-major).  Per block: D = diag^-1/2, corr = D cov D,
- * eigen-decomposition by parallel Jacobi in shared memory, then
+ * eigen-decomposition by parallel Jacobi (n <= 112: one CTA per block in shared memory; larger blocks:
+ * pivoted Cholesky + one-sided block Jacobi over the whole GPU, two-sided block Jacobi as fallback), then
  *   svdcut > 0 : eigenvalues < svdcut*max are replaced by svdcut*max (nmod counts them)
  *   svdcut < 0 : those modes are dropped (nout[k] < n[k])
  *   use_eps    : corr += eps*norm_inf(corr) I and inverse-Cholesky instead
  * Outputs: d_w (same layout as d_cov) rows W[i] = val_i^-1/2 vec_i D, largest eigenvalue
- * first, unused rows zero; d_cov_out the corrected covariance; d_nout, d_nmod [nblk];
+ * first, unused rows zero (for blocks > 112 the rows of the clamped null space are an arbitrary
+ * orthonormal basis of it -- W^T W, i.e. the inverse of the corrected covariance, is the same); d_cov_out the corrected covariance; d_nout, d_nmod [nblk];
  * d_logdet [nblk] (log det of the corrected block).  h_n is a host array. */
 int b200lm_whiten(int device, int nblk, const int* h_n, const double* d_cov,
                   double svdcut, double eps, int use_eps,
