@@ -86,8 +86,87 @@ def solve_tr(A, g, Delta, alpha0, rtol=0.01, max_iter=10):
     return p, alpha, nfac
 
 
-def lm_fit(fun, jac, x0, xtol=1e-8, gtol=1e-10, ftol=1e-10, maxit=1000, scaler="more"):
-    """Device algorithm model.  Returns dict(x, f, J, nfev, status, nfac)."""
+def solve_tr_device(A, g, Delta, alpha, gn, stats=None):
+    """The kernel's variant (csrc/lm_kernel.cuh: solve_tr): same safeguarded Newton iteration, but
+      * the Gauss-Newton factorisation (alpha = 0) is cached in ``gn`` across rejected trials and skipped
+        when the warm-started alpha > 0 already gives a step longer than Delta;
+      * the iteration stops at |phi| < 0.1 Delta (MINPACK's lmpar tolerance) and the last iterate's step is
+        rescaled to the boundary instead of being recomputed at the updated alpha.
+    Returns (p, alpha, number of factorisations)."""
+    nfac = 0
+    tried_warm = warm_ok = False
+    warm = None
+    if not gn.get("valid") and alpha > 0.0:
+        nfac += 1
+        tried_warm = True
+        ok, L, pw = _chol_solve(A, alpha, g)
+        if ok:
+            w = np.linalg.solve(L, pw)
+            warm = (pw, np.linalg.norm(pw), w @ w)
+            warm_ok = True
+    need_gn = not (tried_warm and warm_ok and warm[1] - Delta > 0.0)
+    if not gn.get("valid") and need_gn:
+        nfac += 1
+        ok, L, p0 = _chol_solve(A, 0.0, g)
+        gn.update(valid=True, full_rank=ok)
+        if ok:
+            w = np.linalg.solve(L, p0)
+            gn.update(p=p0, pn=np.linalg.norm(p0), w2=w @ w)
+    full_rank = gn.get("valid") and gn.get("full_rank")
+    if full_rank and gn["pn"] <= Delta:
+        if stats is not None:
+            stats.append(("gn", nfac))
+        return gn["p"], 0.0, nfac
+    alpha_upper = np.linalg.norm(g) / Delta
+    alpha_lower = 0.0
+    p = None
+    if full_rank:
+        alpha_lower = (gn["pn"] - Delta) * gn["pn"] / gn["w2"]
+        p = gn["p"]
+    if not full_rank and alpha == 0.0:
+        alpha = max(0.001 * alpha_upper, (alpha_lower * alpha_upper) ** 0.5)
+    rounds = 0
+    for it in range(10):
+        if it == 0 and tried_warm:
+            ok = warm_ok
+            if ok:
+                pt, pn, w2 = warm
+        else:
+            if alpha < alpha_lower or alpha > alpha_upper:
+                alpha = max(0.001 * alpha_upper, (alpha_lower * alpha_upper) ** 0.5)
+            nfac += 1
+            ok, L, pt = _chol_solve(A, alpha, g)
+            if ok:
+                w = np.linalg.solve(L, pt)
+                pn, w2 = np.linalg.norm(pt), w @ w
+        rounds += 1
+        if not ok:
+            alpha_lower = max(alpha_lower, alpha)
+            alpha = max(2 * alpha, 0.001 * alpha_upper)
+            if alpha > alpha_upper:
+                alpha_upper = 2 * alpha
+            continue
+        p = pt
+        phi = pn - Delta
+        if phi < 0:
+            alpha_upper = alpha
+        ratio = -phi * pn / w2
+        alpha_lower = max(alpha_lower, alpha - ratio)
+        alpha -= (phi + Delta) * ratio / Delta
+        if abs(phi) < 0.1 * Delta:
+            break
+    if p is None:
+        p = -g
+    p = p * (Delta / np.linalg.norm(p))
+    if stats is not None:
+        stats.append(("boundary", nfac))
+    return p, alpha, nfac
+
+
+def lm_fit(fun, jac, x0, xtol=1e-8, gtol=1e-10, ftol=1e-10, maxit=1000, scaler="more", device_solver=False,
+           stats=None):
+    """Device algorithm model.  Returns dict(x, f, J, nfev, status, nfac).  ``device_solver=True`` uses the
+    kernel's variant of the sub-problem solver (solve_tr_device) instead of the literal scipy iteration."""
     x = np.array(x0, dtype=float)
     f = fun(x)
     nfev = 1
@@ -116,8 +195,12 @@ def lm_fit(fun, jac, x0, xtol=1e-8, gtol=1e-10, ftol=1e-10, maxit=1000, scaler="
         A = (J.T @ J) * d[:, None] * d[None, :]
         g_h = d * g
         actual_reduction = -1.0
+        gn = {}
         while actual_reduction <= 0 and nfev < maxit:
-            step_h, alpha, k = solve_tr(A, g_h, Delta, alpha)
+            if device_solver:
+                step_h, alpha, k = solve_tr_device(A, g_h, Delta, alpha, gn, stats)
+            else:
+                step_h, alpha, k = solve_tr(A, g_h, Delta, alpha)
             nfac += k
             predicted_reduction = -(0.5 * step_h @ A @ step_h + g_h @ step_h)
             step = d * step_h
