@@ -9,13 +9,18 @@ reference's ``scipy_least_squares`` plugin (src/lsqfit/_scipy.py:156-161) -- and
 import warnings
 
 import numpy as np
+import pytest
 
 import lm_model
 from oracle import dual as D
 from oracle.fit import nonlinear_fit as ofit
 
 
-def test_cholesky_secular_trf_matches_scipy_on_nist(nist_problems):
+@pytest.mark.parametrize("device_solver,min_same", [(False, 22), (True, 19)])
+def test_cholesky_secular_trf_matches_scipy_on_nist(nist_problems, device_solver, min_same):
+    """device_solver=False: the literal scipy sub-problem iteration on Cholesky factors (measured: 24 of 27
+    problems with identical nfev); True: the kernel's variant with the Gauss-Newton cache, the warm-start skip
+    and MINPACK's 0.1 Delta tolerance (21 of 27; the others differ by a few evaluations)."""
     same, worst = 0, 0.0
     for pr in nist_problems:
         x = np.array(pr["x"])
@@ -27,12 +32,13 @@ def test_cholesky_secular_trf_matches_scipy_on_nist(nist_problems):
             chiv = fo._chiv
             r = lm_model.lm_fit(lambda p: np.asarray(chiv(p)),
                                 lambda p: D.deriv(chiv(D.Dual.variables(p)), p.size),
-                                np.array(pr["p0"], dtype=float), xtol=1e-10, gtol=1e-10, ftol=1e-10, maxit=1000)
+                                np.array(pr["p0"], dtype=float), xtol=1e-10, gtol=1e-10, ftol=1e-10, maxit=1000,
+                                device_solver=device_solver)
         assert r["status"] > 0, pr["name"]
         same += int(r["nfev"] == fo.nit)
         assert abs(r["nfev"] - fo.nit) <= max(4, fo.nit // 10), (pr["name"], r["nfev"], fo.nit)
         dp = np.max(np.abs(r["x"] - fo.pmean) / fo.psdev)
         if pr["name"] != "lanczos1":          # sigma_y = 9e-14: rounding of exp() is amplified 1e13-fold
             worst = max(worst, dp)
-    assert same >= 22, same                  # measured: 24 of 27 identical
+    assert same >= min_same, same
     assert worst < 1e-6, worst               # both stop at the same tolerances, not at the exact minimum
