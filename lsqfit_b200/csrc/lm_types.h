@@ -32,7 +32,8 @@ struct FitParams {
     int wt_total;               // doubles in blk_wt
     int wt_in_smem;             // stage blk_wt in shared memory
     int rb;                     // rows of the per-warp row buffer
-    int nblkrows;               // total residual rows produced by the correlated blocks
+    int dual_from;              // from this evaluation count on, the secular equation is evaluated at two
+                                // values of alpha per factorisation round (np <= 16); < 0: never
     int warps;                  // warps per CTA
     // ---- batch ------------------------------------------------------------
     int B;
