@@ -96,9 +96,9 @@ def cpu_fits_per_sec(means, cores):
 
 def _ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the fit kernel, per launch, from the committed
-    `ncu --set full` capture (profiles/traffic_r01_v8.json); None if absent."""
+    `ncu --set full` capture (profiles/traffic_r01_v9.json); None if absent."""
     try:
-        t = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r01_v8.json")))
+        t = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r01_v9.json")))
         return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
     except (OSError, ValueError, KeyError):
         return None
