@@ -722,8 +722,8 @@ struct TRCand {
 // Trust-region sub-problem with TWO shifts per factorisation round: the warm-started alpha and the
 // prediction of the linear model (or the Gauss-Newton shift 0 when it is still needed), then Newton and
 // secant iterates side by side.  Same acceptance rule as solve_tr (|phi| < 0.1 Delta, step rescaled to the
-// boundary).  On the slow C3 copies this needs 1.1 rounds per trial instead of 1.8 factorisations
-// (numpy prototype).  Falls back to solve_tr if no shift could be factorised.
+// boundary).  On the slow C3 copies this needs 1.3 rounds per trial instead of 1.8 factorisations
+// (numpy model tests/lm_model.py: solve_tr_dual).  Falls back to solve_tr if no shift could be factorised.
 template <class F>
 __device__ double solve_tr_dual(WarpCtx<F>& c, double gh, double Delta, double& alpha, int& nfac, GNCache& gn,
                                 LinModel& lm) {

@@ -163,8 +163,134 @@ def solve_tr_device(A, g, Delta, alpha, gn, stats=None):
     return p, alpha, nfac
 
 
+def _fac(A, alpha, g):
+    ok, L, p = _chol_solve(A, alpha, g)
+    if not ok:
+        return dict(ok=False, a=alpha, pn=0.0, w2=0.0, p=None)
+    w = np.linalg.solve(L, p)
+    return dict(ok=True, a=alpha, pn=np.linalg.norm(p), w2=w @ w, p=p)
+
+
+def solve_tr_dual(A, g, Delta, alpha, gn, lm, stats=None):
+    """The kernel's two-shifts-per-round variant (csrc/lm_kernel.cuh: solve_tr_dual, used for np = 12..16):
+    every factorisation round evaluates TWO shifts -- the warm-started alpha and the prediction of a linear
+    model of 1/|p(alpha)| carried over from the previous trial (``lm``), or the Gauss-Newton shift 0 while
+    that step is still unknown; later rounds pair the Newton and the secant iterate.  Same acceptance rule
+    as solve_tr_device.  Returns (p, alpha, rounds)."""
+    best = second = None
+    rounds = 0
+
+    def insert(t):
+        nonlocal best, second
+        if not t["ok"] or not t["a"] > 0.0:
+            return
+        d = abs(t["pn"] - Delta)
+        if best is None or d < abs(best["pn"] - Delta):
+            second, best = best, t
+        elif second is None or d < abs(second["pn"] - Delta):
+            second = t
+
+    def take_gn(t):
+        gn.update(valid=True, full_rank=t["ok"], p=t["p"], pn=t["pn"], w2=t["w2"])
+
+    alpha_upper = np.linalg.norm(g) / Delta
+    alpha_lower = 0.0
+
+    def predict():
+        if not lm.get("valid"):
+            return -1.0
+        pr = (1.0 / Delta - lm["a"]) / lm["b"]
+        return pr if 0.0 < pr < 1e300 else -1.0
+
+    if not gn.get("valid") and not alpha > 0.0:
+        take_gn(_fac(A, 0.0, g))
+        rounds += 1
+    else:
+        x1 = alpha if alpha > 0.0 else -1.0
+        x2 = predict()
+        if x1 < 0.0:
+            nl = (gn["pn"] - Delta) * gn["pn"] / gn["w2"] if gn.get("valid") and gn.get("full_rank") else 0.0
+            x1 = x2 if x2 > 0.0 else max(nl, 0.001 * alpha_upper)
+            x2 = -1.0
+        if x2 < 0.0 or abs(x2 - x1) < 1e-3 * x1:
+            x2 = 1.5 * x1 if gn.get("valid") else 0.0
+        lo, hi = _fac(A, x1, g), _fac(A, x2, g)
+        rounds += 1
+        if x2 == 0.0:
+            take_gn(hi)
+        else:
+            insert(hi)
+        insert(lo)
+    if gn.get("valid") and gn.get("full_rank") and gn["pn"] <= Delta:
+        if stats is not None:
+            stats.append(rounds)
+        return gn["p"], 0.0, rounds
+    for it in range(5):
+        if gn.get("valid") and gn.get("full_rank"):
+            alpha_lower = max(alpha_lower, (gn["pn"] - Delta) * gn["pn"] / gn["w2"])
+        for t in (best, second):
+            if t is not None:
+                if t["pn"] < Delta:
+                    alpha_upper = min(alpha_upper, t["a"])
+                else:
+                    alpha_lower = max(alpha_lower, t["a"])
+        if best is not None and abs(best["pn"] - Delta) < 0.1 * Delta and (gn.get("valid") or best["pn"] >= Delta):
+            break
+        if best is not None:
+            phi = best["pn"] - Delta
+            an = best["a"] - (phi + Delta) * (-phi * best["pn"] / best["w2"]) / Delta
+        else:
+            an = 2.0 * alpha if alpha > 0.0 else 0.0
+        if not alpha_lower < an < alpha_upper:
+            an = max(0.001 * alpha_upper, (alpha_lower * alpha_upper) ** 0.5)
+        if not gn.get("valid") and best is not None and best["pn"] < Delta:
+            a2 = 0.0
+        else:
+            a2 = -1.0
+            if best is not None and second is not None and second["a"] != best["a"]:
+                y0, y1 = 1.0 / best["pn"], 1.0 / second["pn"]
+                if y1 != y0:
+                    a2 = best["a"] + (1.0 / Delta - y0) * (second["a"] - best["a"]) / (y1 - y0)
+            if not alpha_lower < a2 < alpha_upper or abs(a2 - an) < 1e-3 * an:
+                a2 = 0.5 * (an + alpha_lower) if best is not None and best["pn"] < Delta else min(1.5 * an, 0.5 * (an + alpha_upper))
+            if not a2 > 0.0:
+                a2 = 1.5 * an
+        lo, hi = _fac(A, an, g), _fac(A, a2, g)
+        rounds += 1
+        if a2 == 0.0:
+            take_gn(hi)
+            if gn["full_rank"] and gn["pn"] <= Delta:
+                if stats is not None:
+                    stats.append(rounds)
+                return gn["p"], 0.0, rounds
+        else:
+            insert(hi)
+        insert(lo)
+        if not lo["ok"] and (a2 == 0.0 or not hi["ok"]):
+            alpha_lower = max(alpha_lower, an, a2)
+            alpha = max(2.0 * max(an, a2), 0.001 * alpha_upper)
+            if alpha > alpha_upper:
+                alpha_upper = 2.0 * alpha
+    if best is None:
+        p, alpha, k = solve_tr_device(A, g, Delta, alpha, gn)
+        if stats is not None:
+            stats.append(rounds + k)
+        return p, alpha, rounds + k
+    if second is not None and second["a"] != best["a"]:
+        b = (1.0 / second["pn"] - 1.0 / best["pn"]) / (second["a"] - best["a"])
+    else:
+        b = best["w2"] / best["pn"] ** 3
+    lm.update(valid=b > 0.0, b=b, a=1.0 / best["pn"] - b * best["a"])
+    phi = best["pn"] - Delta
+    an = best["a"] - (phi + Delta) * (-phi * best["pn"] / best["w2"]) / Delta
+    alpha = an if an > 0.0 else best["a"]
+    if stats is not None:
+        stats.append(rounds)
+    return best["p"] * (Delta / best["pn"]), alpha, rounds
+
+
 def lm_fit(fun, jac, x0, xtol=1e-8, gtol=1e-10, ftol=1e-10, maxit=1000, scaler="more", device_solver=False,
-           stats=None):
+           stats=None, dual=False):
     """Device algorithm model.  Returns dict(x, f, J, nfev, status, nfac).  ``device_solver=True`` uses the
     kernel's variant of the sub-problem solver (solve_tr_device) instead of the literal scipy iteration."""
     x = np.array(x0, dtype=float)
@@ -185,6 +311,7 @@ def lm_fit(fun, jac, x0, xtol=1e-8, gtol=1e-10, ftol=1e-10, maxit=1000, scaler="
     alpha = 0.0
     status = None
     nfac = 0
+    lm_state = {}
     while True:
         g_norm = np.max(np.abs(g))
         if g_norm < gtol:
@@ -197,7 +324,9 @@ def lm_fit(fun, jac, x0, xtol=1e-8, gtol=1e-10, ftol=1e-10, maxit=1000, scaler="
         actual_reduction = -1.0
         gn = {}
         while actual_reduction <= 0 and nfev < maxit:
-            if device_solver:
+            if dual:
+                step_h, alpha, k = solve_tr_dual(A, g_h, Delta, alpha, gn, lm_state, stats)
+            elif device_solver:
                 step_h, alpha, k = solve_tr_device(A, g_h, Delta, alpha, gn, stats)
             else:
                 step_h, alpha, k = solve_tr(A, g_h, Delta, alpha)

@@ -46,3 +46,33 @@ def test_cholesky_secular_trf_matches_scipy_on_nist(nist_problems, device_solver
     assert same >= min_same, same
     # both stop at the same tolerances, not at the exact minimum (measured: 4.8e-7 / 3.5e-6 sdev)
     assert worst < (1e-5 if device_solver else 1e-6), worst
+
+
+def test_two_shifts_per_round_model(nist_problems):
+    """The kernel's two-shifts-per-round sub-problem solver (np = 12..16 on the device), restated in numpy:
+    same end points as the reference on the NIST suite, and fewer factorisation rounds than the one-shift
+    variant needs factorisations."""
+    rounds, singles, worst = [], [], 0.0
+    for pr in nist_problems:
+        x = np.array(pr["x"])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            fo = ofit(pr["form"], x[:, None] if x.ndim == 1 else x, pr["y"], np.array(pr["ysdev"]),
+                      prior_mean=pr["prior_mean"], prior_cov=np.array(pr["prior_sdev"]), p0=pr["p0"],
+                      tol=1e-10, maxit=1000, x_scale="jac")
+            chiv = fo._chiv
+            fun = lambda p: np.asarray(chiv(p))
+            jac = lambda p: D.deriv(chiv(D.Dual.variables(p)), p.size)
+            st2, st1 = [], []
+            r2 = lm_model.lm_fit(fun, jac, np.array(pr["p0"], dtype=float), xtol=1e-10, gtol=1e-10, ftol=1e-10,
+                                 maxit=1000, dual=True, stats=st2)
+            lm_model.lm_fit(fun, jac, np.array(pr["p0"], dtype=float), xtol=1e-10, gtol=1e-10, ftol=1e-10,
+                            maxit=1000, device_solver=True, stats=st1)
+        assert r2["status"] > 0, pr["name"]
+        assert r2["nfev"] <= 3 * fo.nit + 5, (pr["name"], r2["nfev"], fo.nit)
+        if pr["name"] != "lanczos1":
+            worst = max(worst, np.max(np.abs(r2["x"] - fo.pmean) / fo.psdev))
+        rounds += st2
+        singles += [k for _, k in st1]
+    assert worst < 1e-5, worst
+    assert np.mean(rounds) < np.mean(singles), (np.mean(rounds), np.mean(singles))
