@@ -297,3 +297,23 @@ def test_wavg_known_answers():
     f = wavg([[2.1, 6.1], [1.9, 5.9]], cov)
     np.testing.assert_allclose(f.pmean, [2.09802, 6.09802], rtol=1e-4)
     np.testing.assert_allclose(f.psdev, [0.995037, 0.995037], rtol=1e-4)
+
+
+from parity_util import _y_noerr_problem, Y_NOERR_OUT      # noqa: E402  (shared with the GPU test)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+def test_y_noerr(n):
+    """examples/y-noerr.out (svd cut modifies 2-3 modes of a data (+) prior covariance whose data and prior
+    parts are correlated; tol = 1e-15).  The nexp = 5 fit of the example is not pinned: its printed logGBF
+    (83.141) belongs to a fit that the GSL fitter left after 249 iterations short of the minimum the first
+    four digits of its parameters already agree with."""
+    x, ymod, cov, pm = _y_noerr_problem(n)
+    fit = nonlinear_fit("multiexp", x[:, None], ymod, yp_cov=cov, prior_mean=pm, svdcut=1e-12, tol=1e-15)
+    chi2dof, dof, Q, logGBF, svdn, a_exp, E_exp = Y_NOERR_OUT[n]
+    assert fit.dof == dof and fit.yp_pdf.nmod == svdn
+    assert gvfmt.agrees_g(fit.chi2 / fit.dof, chi2dof, 2)
+    assert gvfmt.agrees_g(fit.Q, Q, 2)
+    assert abs(fit.logGBF - float(logGBF)) < 1.5e-3
+    for m, s, e in zip(fit.pmean, fit.psdev, a_exp + E_exp):
+        assert gvfmt.agrees(m, s, e, slack=1.01), (m, s, e)
