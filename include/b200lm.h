@@ -115,6 +115,12 @@ int b200lm_fit_batch_host(b200lm_handle h, int B,
 /* totals of the last fit_batch on this handle: out[0] function evaluations, out[1] Jacobian
  * evaluations, out[2] Cholesky factorisations.  Synchronises the handle's last stream. */
 int b200lm_last_stats(b200lm_handle h, unsigned long long out[3]);
+/* diagnostics: the first n (<= 16) counters of the last fit_batch.  [0..2] as above; [3..5] SM cycles the
+ * driving warps spent in evaluations / in the trust-region sub-problem / in total; [6..10] leader cycles of the
+ * team kernel's evaluation phases (prior + 1x1 rows, model rows, W.G, normal equations, reduction). */
+int b200lm_last_stats_ex(b200lm_handle h, unsigned long long* out, int n);
+/* warps per fit used by the last fit_batch launch: 1 (one warp per fit), 2 or 4 (team kernel) */
+int b200lm_last_team(b200lm_handle h);
 /* number of kernel launches issued through this handle so far */
 long long b200lm_launch_count(b200lm_handle h);
 

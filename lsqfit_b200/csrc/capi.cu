@@ -31,6 +31,8 @@ void fill_params(b200lm_handle_s* h, FitParams& P) {
     P.nd_pr = h->nd_pr; P.dpr_idx = h->d_dpr_idx; P.dpr_w = h->d_dpr_w;
     P.nblk = h->nblk; P.blk = h->d_blk; P.blk_idx = h->d_blk_idx; P.blk_wt = h->d_blk_wt;
     P.wt_total = h->wt_total;
+    P.blk_wt2 = h->d_blk_wt2; P.wt2_total = h->wt2_total;
+    P.nblk_idx = (int)h->h_blk_idx.size();
     P.rb = h->rb;
     {
         const char* e = getenv("B200LM_DUAL_FROM");
@@ -47,11 +49,23 @@ static std::vector<FunctorEntry>& registry() {
         int n = 0;
         const FunctorEntry* e;
         e = registry_multiexp(&n); r.insert(r.end(), e, e + n);
+        e = registry_multiexp_b(&n); r.insert(r.end(), e, e + n);
         e = registry_nist_a(&n);   r.insert(r.end(), e, e + n);
         e = registry_nist_b(&n);   r.insert(r.end(), e, e + n);
         e = registry_misc(&n);     r.insert(r.end(), e, e + n);
     }
     return r;
+}
+
+// default number of warps per fit.  The choice depends on the problem's shape only, never on the batch
+// size: a fit's result must not depend on how many other fits share its launch (the two kernels sum in a
+// different order).  Measured on C3 (np = 16, one 64 x 64 block; tools/team_check.py): a team of four warps
+// cuts the latency of one trial point by a third (B = 1000: 5.3 ms instead of 8.4 ms) but keeps fewer fits in
+// flight per SM (B = 10^4: 14.6 vs 13.3 ms), so one warp per fit stays the default; B200LM_TEAM=4 selects
+// the team kernel.
+static int default_team(b200lm_handle_s* h, int B) {
+    (void)h; (void)B;
+    return 1;
 }
 
 #define CUDA_TRY(h, call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(h, e_, what); } while (0)
@@ -124,7 +138,7 @@ int b200lm_create(int family, int ny, int np, int nx, int noprior, int device, b
     h->sm_count = prop.multiProcessorCount;
     h->smem_budget = prop.sharedMemPerBlockOptin;
     e = cudaMalloc((void**)&h->d_counter, sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_stats, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_stats, 16 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { b200lm_destroy(h); return cuda_fail(nullptr, e, "handle allocation"); }
     *out = h;
@@ -136,7 +150,7 @@ void b200lm_destroy(b200lm_handle h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_x);
     cudaFree(h->d_dfn_idx); cudaFree(h->d_dfn_w); cudaFree(h->d_dpr_idx); cudaFree(h->d_dpr_w);
-    cudaFree(h->d_blk); cudaFree(h->d_blk_idx); cudaFree(h->d_blk_wt); cudaFree(h->d_wfull);
+    cudaFree(h->d_blk); cudaFree(h->d_blk_idx); cudaFree(h->d_blk_wt); cudaFree(h->d_blk_wt2); cudaFree(h->d_wfull);
     cudaFree(h->d_counter); cudaFree(h->d_stats); cudaFree(h->d_stage); cudaFree(h->d_scratch);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -176,7 +190,7 @@ int b200lm_set_weights(b200lm_handle h, int ndiag, const int* diag_idx, const do
         } else { prior_seen = true; pr_idx.push_back(idx); pr_w.push_back(diag_w[i]); }
     }
     std::vector<BlockDesc> blk(nblk);
-    std::vector<double> wt;
+    std::vector<double> wt, wt2;
     int idx_off = 0, chiv_off = ndiag, w_off = 0;
     const int rb = 32;
     for (int k = 0; k < nblk; ++k) {
@@ -200,6 +214,15 @@ int b200lm_set_weights(b200lm_handle h, int ndiag, const int* diag_idx, const do
         for (int r = 0; r < nout; ++r)
             for (int j = 0; j < nin; ++j)
                 wt[b.wt_off + (size_t)r * ldw + j] = blk_w[w_off + (size_t)r * nin + j];
+        // team-kernel copy: 16-byte fragment loads want a row stride == 8 (mod 16) >= n_in rounded to 8
+        int ldw2 = (nin + 7) & ~7;
+        while ((ldw2 & 15) != 8) ldw2 += 8;
+        b.ldw2 = ldw2; b.wt2_off = (int)wt2.size();
+        const int nout64 = ((nout + 63) & ~63) > 0 ? ((nout + 63) & ~63) : 64;     // whole 64-row groups: no row guards
+        wt2.resize(wt2.size() + (size_t)nout64 * ldw2, 0.0);
+        for (int r = 0; r < nout; ++r)
+            for (int j = 0; j < nin; ++j)
+                wt2[b.wt2_off + (size_t)r * ldw2 + j] = blk_w[w_off + (size_t)r * nin + j];
         idx_off += nin; w_off += nin * nout; chiv_off += nout;
     }
     for (int i = 0; i < N; ++i)
@@ -215,6 +238,8 @@ int b200lm_set_weights(b200lm_handle h, int ndiag, const int* diag_idx, const do
     CUDA_TRY(h, upload(&h->d_blk, blk.data(), blk.size()), "upload weights");
     CUDA_TRY(h, upload(&h->d_blk_idx, blk_idx, (size_t)idx_off), "upload weights");
     CUDA_TRY(h, upload(&h->d_blk_wt, wt.data(), wt.size()), "upload weights");
+    CUDA_TRY(h, upload(&h->d_blk_wt2, wt2.data(), wt2.size()), "upload weights");
+    h->wt2_total = (int)wt2.size();
     h->nblk = nblk; h->wt_total = (int)wt.size(); h->rb = rb; h->nchiv = chiv_off;
     h->h_diag_idx.assign(diag_idx, diag_idx + ndiag); h->h_diag_w.assign(diag_w, diag_w + ndiag);
     h->h_blk = blk; h->h_blk_idx.assign(blk_idx, blk_idx + idx_off);
@@ -257,8 +282,21 @@ int b200lm_fit_batch(b200lm_handle h, int B,
     P.x_out = d_x; P.chi2 = d_chi2; P.cov = d_cov; P.logdet = d_logdet; P.nit = d_nit; P.status = d_status;
     P.f_out = d_f; P.J_out = d_J;
     CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s), "reset work queue");
-    CUDA_TRY(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), s), "reset stats");
-    CUDA_TRY(h, h->fe->fit(P, h->sm_count, h->smem_budget, s), "fit kernel launch");
+    CUDA_TRY(h, cudaMemsetAsync(h->d_stats, 0, 16 * sizeof(unsigned long long), s), "reset stats");
+    // kernel choice: one warp per fit, or a team of 2 / 4 warps per fit where the functor has one
+    // (B200LM_TEAM = 0/1, 2, 4 overrides the default policy)
+    int team = default_team(h, B);
+    if (const char* env = getenv("B200LM_TEAM")) team = atoi(env);
+    const int ti = team == 4 ? 1 : (team == 2 ? 0 : -1);
+    if (ti >= 0 && h->fe->fit_team[ti] &&
+        h->fe->team_bytes[ti](h->N) <= h->smem_budget) {
+        P.team = team;
+        CUDA_TRY(h, h->fe->fit_team[ti](P, h->sm_count, h->smem_budget, s), "fit kernel launch");
+    } else {
+        P.team = 1;
+        CUDA_TRY(h, h->fe->fit(P, h->sm_count, h->smem_budget, s), "fit kernel launch");
+    }
+    h->last_team = P.team;
     h->last_stream = s;
     h->launches += 1;
     return B200LM_OK;
@@ -266,13 +304,24 @@ int b200lm_fit_batch(b200lm_handle h, int B,
 
 int b200lm_last_stats(b200lm_handle h, unsigned long long out[3]) {
     if (!h || !out) return set_error(h, B200LM_EINVAL, "NULL argument");
-    CUDA_TRY(h, cudaSetDevice(h->device), "cudaSetDevice");
-    CUDA_TRY(h, cudaStreamSynchronize(h->last_stream), "stream sync");
-    unsigned long long tmp[4];
-    CUDA_TRY(h, cudaMemcpy(tmp, h->d_stats, sizeof tmp, cudaMemcpyDeviceToHost), "read stats");
+    unsigned long long tmp[16];
+    int rc = b200lm_last_stats_ex(h, tmp, 16);
+    if (rc) return rc;
     out[0] = tmp[0]; out[1] = tmp[1]; out[2] = tmp[2];
     return B200LM_OK;
 }
+
+int b200lm_last_stats_ex(b200lm_handle h, unsigned long long* out, int n) {
+    if (!h || !out || n < 1 || n > 16) return set_error(h, B200LM_EINVAL, "bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device), "cudaSetDevice");
+    CUDA_TRY(h, cudaStreamSynchronize(h->last_stream), "stream sync");
+    unsigned long long tmp[16];
+    CUDA_TRY(h, cudaMemcpy(tmp, h->d_stats, sizeof tmp, cudaMemcpyDeviceToHost), "read stats");
+    for (int i = 0; i < n; ++i) out[i] = tmp[i];
+    return B200LM_OK;
+}
+
+int b200lm_last_team(b200lm_handle h) { return h ? h->last_team : B200LM_EINVAL; }
 
 long long b200lm_launch_count(b200lm_handle h) { return h ? h->launches : 0; }
 

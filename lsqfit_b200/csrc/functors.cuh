@@ -5,8 +5,9 @@
 //     static constexpr int NP;   number of fit parameters (compile time)
 //     static constexpr int NX;   number of x columns the row reads
 //     double value     (const double* xrow, int row, const double* p)
-//     double value_grad(const double* xrow, int row, const double* p, double w, double* out /*[NP]*/)
-//            returns f and writes out[j] = w * df/dp_j (straight into the warp's row buffer)
+//     double value_grad(const double* xrow, int row, const double* p, double w, G out /*[NP]*/)
+//            returns f and writes out[j] = w * df/dp_j straight into the row buffer; G is double* (row-major
+//            buffer of the warp kernel) or a strided accessor (transposed buffer of the team kernel)
 // x is row-major [ny][NX] in global memory; p points to the warp's parameter vector in shared
 // memory.  value() and value_grad() return bit-identical f (same operation order), so that
 // results do not depend on which of the two evaluated the final residuals.  Loops over
@@ -50,8 +51,9 @@ struct ADFunctor {
         for (int j = 0; j < NP; ++j) q[j] = p[j];
         return Body::template eval<double>(x, q);
     }
+    template <class G>
     __device__ __forceinline__ static double value_grad(const double* __restrict__ x, int,
-                                                        const double* p, double w, double* g) {
+                                                        const double* p, double w, G g) {
         Dual<NP> q[NP];
 #pragma unroll
         for (int j = 0; j < NP; ++j) q[j] = Dual<NP>::variable(p[j], j);
@@ -77,8 +79,9 @@ struct MultiExp {
         for (int k = 0; k < K; ++k) f = fma(p[k], ::exp(-p[K + k] * t), f);
         return f;
     }
+    template <class G>
     __device__ __forceinline__ static double value_grad(const double* __restrict__ x, int,
-                                                        const double* p, double w, double* g) {
+                                                        const double* p, double w, G g) {
         const double t = x[0];
         const double wt = -w * t;
         double f = 0.0;
@@ -92,7 +95,34 @@ struct MultiExp {
         }
         return f;
     }
+    // Two lanes per row (team kernel): part 0 evaluates the exponentials [0, KH), part 1 [KH, K), each
+    // writes its own columns of the gradient and returns its share of f.  The loop is unrolled: the
+    // exponentials of one lane are independent, so their ~150-cycle latencies overlap.
+    template <class G>
+    __device__ __forceinline__ static double value_grad_part(const double* __restrict__ x, int,
+                                                             const double* p, double w, G g, int part) {
+        constexpr int KH = (K + 1) / 2;
+        const double t = x[0];
+        const double wt = -w * t;
+        const int k0 = part * KH;
+        double f = 0.0;
+#pragma unroll
+        for (int u = 0; u < KH; ++u) {
+            const int k = k0 + u;
+            if (k < K) {
+                const double e = ::exp(-p[K + k] * t);
+                const double a = p[k];
+                g[k] = w * e;
+                g[K + k] = wt * (a * e);
+                f = fma(a, e, f);
+            }
+        }
+        return f;
+    }
 };
+
+// number of lanes this functor can spread one row's value_grad over (value_grad_part); primary template: lm_kernel.cuh
+template <int K> struct SplitOf<MultiExp<K>> { static constexpr int value = K >= 2 ? 2 : 1; };
 
 // E_k = dE_0 + ... + dE_k ; params [a_0..a_K-1, dE_0..dE_K-1]
 template <int K>
@@ -106,8 +136,9 @@ struct MultiExpDE {
         for (int k = 0; k < K; ++k) { E += p[K + k]; f = fma(p[k], ::exp(-E * t), f); }
         return f;
     }
+    template <class G>
     __device__ __forceinline__ static double value_grad(const double* __restrict__ x, int,
-                                                        const double* p, double w, double* g) {
+                                                        const double* p, double w, G g) {
         const double t = x[0];
         const double wt = -w * t;
         double f = 0.0, E = 0.0;
@@ -140,8 +171,9 @@ struct Poly {
         for (int n = 0; n < NP; ++n) { f = fma(p[n], tn, f); tn *= t; }
         return f;
     }
+    template <class G>
     __device__ __forceinline__ static double value_grad(const double* __restrict__ x, int,
-                                                        const double* p, double w, double* g) {
+                                                        const double* p, double w, G g) {
         const double t = x[0];
         double tn = 1.0, f = 0.0;
 #pragma unroll 1
@@ -163,8 +195,9 @@ struct Gather {
         for (int n = 0; n < NP; ++n) f = (n == k) ? p[n] : f;
         return f;
     }
+    template <class G>
     __device__ __forceinline__ static double value_grad(const double* __restrict__ x, int,
-                                                        const double* p, double w, double* g) {
+                                                        const double* p, double w, G g) {
         const int k = (int)x[0];
         double f = 0.0;
 #pragma unroll
@@ -181,8 +214,9 @@ struct ExpPoly {
     __device__ __forceinline__ static double value(const double* __restrict__ x, int r, const double* p) {
         return ::exp(-Poly<NP>::value(x, r, p));
     }
+    template <class G>
     __device__ __forceinline__ static double value_grad(const double* __restrict__ x, int r,
-                                                        const double* p, double w, double* g) {
+                                                        const double* p, double w, G g) {
         const double f = ::exp(-Poly<NP>::value_grad(x, r, p, 1.0, g));
         const double wf = -w * f;
 #pragma unroll 1
@@ -203,8 +237,9 @@ struct XerrLogistic {
     __device__ __forceinline__ static double value(const double* __restrict__, int row, const double* p) {
         return body<double>(p[0], p[1], p[2], p[3], p[4 + row]);
     }
+    template <class G>
     __device__ __forceinline__ static double value_grad(const double* __restrict__, int row,
-                                                        const double* p, double w, double* g) {
+                                                        const double* p, double w, G g) {
         typedef Dual<5> D5;
         const D5 r = body<D5>(D5::variable(p[0], 0), D5::variable(p[1], 1), D5::variable(p[2], 2),
                               D5::variable(p[3], 3), D5::variable(p[4 + row], 4));

@@ -17,6 +17,7 @@ struct b200lm_handle_s {
     int* d_dpr_idx = nullptr; double* d_dpr_w = nullptr; int nd_pr = 0;
     b200lm::BlockDesc* d_blk = nullptr; int nblk = 0;
     int* d_blk_idx = nullptr; double* d_blk_wt = nullptr; int wt_total = 0;
+    double* d_blk_wt2 = nullptr; int wt2_total = 0;      // team-kernel layout of the same weights
     int rb = 64;
     bool have_weights = false, have_const = false;
     // host copies (used by propagate)
@@ -29,6 +30,7 @@ struct b200lm_handle_s {
     unsigned long long* d_stats = nullptr;
     cudaStream_t last_stream = nullptr;
     long long launches = 0;
+    int last_team = 1;          // warps per fit of the last fit_batch launch
     // staging for the host-pointer API
     void* d_stage = nullptr; size_t stage_bytes = 0;
     void* h_pinned = nullptr; size_t pinned_bytes = 0;

@@ -41,6 +41,9 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// number of lanes a functor can spread one row's value_grad over (value_grad_part); specialised in functors.cuh
+template <class F> struct SplitOf { static constexpr int value = 1; };
+
 template <class F>
 struct FitLayout {
     static constexpr int NP = F::NP;
@@ -69,7 +72,7 @@ struct FitLayout {
         // R | dvec | A0 | A1 | L | vectors (+ second gradient).  A0/A1, g0/g1: the Jacobian is
         // evaluated speculatively at every trial point, so the normal equations of the current
         // point must survive a rejected trial.
-        int n = rb * LDR + rb + 3 * NP * LDA + (NVEC + 1) * NP;
+        int n = rb * LDR + rb + 3 * NP * LDA + (NVEC + 1) * NP + 64;      // + column broadcast buffers
         return (n + 1) & ~1;
     }
 };
@@ -80,7 +83,7 @@ struct WarpCtx {
     const FitParams& P;
     const double* wt;       // whitening matrices (shared or global)
     const double* mean;     // this fit's y(+)prior means
-    double *R, *dvec, *A, *L, *p, *pn, *g, *sinv, *dsc, *idg;
+    double *R, *dvec, *A, *L, *p, *pn, *g, *sinv, *dsc, *idg, *colb;
     double *Abuf[2], *gbuf[2];      // c.A / c.g point at the buffer the next evaluation writes
     int lane;
     __device__ WarpCtx(const FitParams& P_) : P(P_) {}
@@ -439,20 +442,146 @@ __device__ __forceinline__ double eval_full(WarpCtx<F>& c, const double* pv, dou
 // ---------------------------------------------------------------------------
 // small dense kernels on the warp: lane i owns row i, everything in registers
 // ---------------------------------------------------------------------------
-// One Cholesky factorisation + the solves every caller needs, as ONE out-of-line function with
-// ROLLED loops: the kernel is instruction-fetch bound when this code is unrolled (ncu: more than
-// half of the stall samples were "no instruction"), so code size matters more than a few moves.
-// Lane i owns row i.  r[m] holds the live entry (i, j+m) of the trailing matrix at step j: the
-// update writes r[m-1] = r[m] - L_ij L_(j+m)j, which rotates the row so that the pivot column is
-// always r[0] and every register index is static.  Finished columns go to shared memory as rows
-// of L^T (LT[j][i] = L[i][j]); the update reads them back by broadcast, the substitutions read
-// L[i][j] = LT[j][i] and L[j][i] = LT[i][j].
-//     L L^T = d_i A_ij d_j + alpha delta_ij
-//     p = -(L L^T)^-1 gh ,  res[0] = |p| ,  res[1] = |L^-1 p|^2 ,  res[2] = min_j pivot_j / diag_j
-// Returns false if the matrix is not numerically positive definite.  LT (NP x LDA) and the
-// reciprocal diagonal idg stay valid in shared memory for the covariance routine.
+#ifndef B200LM_LDL_VARIANT
+#define B200LM_LDL_VARIANT 1
+#endif
+
+// 1/x for a positive, normal x: MUFU.RCP64H seed (about 20 bits) + two Newton steps.  No slow path
+// (the pivots handed to it are tested separately), four dependent FMAs after the seed.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// One factorisation + the solves every caller needs, written for LATENCY: a fit spends most of its
+// life in this dependency chain (measured on B200: DFMA 8.5, 64-bit shuffle 26, shared-memory round
+// trip 42, fp64 divide 71 cycles).
+//     L D L^T = d_i A_ij d_j + alpha delta_ij      (unit lower L, D = pivots; no square roots)
+//     p = -(L D L^T)^-1 gh ,  res[0] = |p| ,  res[1] = p^T (L D L^T)^-1 p ,  res[2] = min_j pivot_j / diag_j
+// Lane i owns row i of the trailing matrix in registers r[0..NP); the loop over columns is fully
+// unrolled so that every register index is static, only live columns are updated, and all
+// lane == column tests are predicates -- no divergent branch anywhere.  Per column j the chain is
+//     pivot = shfl(r[j], j) + alpha  ->  1/pivot  ->  l_ij = r[j]/pivot  ->  r[j+1] -= l_ij * a_(j+1)j
+// The UNSCALED column a_kj goes to shared memory (double-buffered, one __syncwarp per column) while
+// the reciprocal is still being computed, so the broadcast is off the critical path.  The forward
+// substitution y = L^-1 (-gh) rides along.  Finished columns are stored as rows of L^T
+// (LT[j][i] = L[i][j], LT[j][j] = pivot_j) with the reciprocal pivots in idg for the covariance.
+// HALF: two systems per warp (np <= 16): lanes 0..15 use alpha_lo, lanes 16..31 alpha_hi, each half
+// with its own L^T (LT0 / LT1) -- the same instructions factor both (16-wide shuffles).
+// Per-lane outputs refer to the lane's own system; `ok` false = not numerically positive definite.
+template <int NP, int LDA, bool HALF>
+__device__ __forceinline__ void ldl_solve(const double* A, const double* dsc, double* LT0, double* LT1, double* idg,
+                                          double* colb, int lane, double alpha_lo, double alpha_hi, double gh_in,
+                                          bool want_ratio, double& p_out, double& pn_out, double& w2_out,
+                                          double& minr_out, bool& ok_out) {
+    static_assert(!HALF || NP <= 16, "two systems per warp need np <= 16");
+    static_assert(NP <= 32, "one lane per row");
+    constexpr int W = HALF ? 16 : 32;
+    const int hi = HALF ? (lane >> 4) : 0;
+    const int i = lane & (W - 1);
+    const bool act = i < NP;
+    const int ii = act ? i : NP - 1;    // idle lanes shadow the last row (same values, same addresses)
+    const double alpha = hi ? alpha_hi : alpha_lo;
+    double* LT = hi ? LT1 : LT0;
+    double* cb0 = colb + hi * 16;       // column broadcast buffers: [2][32] doubles
+    const double gh = HALF ? __shfl_sync(B200LM_FULL, gh_in, i) : gh_in;      // both halves solve for the same gradient
+    double r[NP];
+    const double di = dsc[ii];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) r[k] = A[ii * LDA + k] * di * dsc[k];
+    const double mdiag = fma(A[ii * LDA + ii] * di, di, alpha);               // diagonal entry of this lane's row
+    double myrcp = 1.0, mypiv = 1.0;
+    bool ok = true;
+    double b = act ? -gh : 0.0;
+    double pivsrc = r[0];                   // lane j holds the raw pivot of column j here when its turn comes
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        const double cj = r[j];                                              // a_ij of the trailing matrix
+        double* cb = cb0 + (j & 1) * 32;
+        cb[ii] = cj;
+        double piv;
+        if (B200LM_LDL_VARIANT & 4) {
+            __syncwarp();
+            piv = cb[j] + alpha;
+        } else {
+            piv = __shfl_sync(B200LM_FULL, (B200LM_LDL_VARIANT & 1) ? pivsrc : cj, j, W) + alpha;
+            __syncwarp();
+        }
+        const double rcp = fast_rcp(piv);
+        const double l = cj * rcp;                                           // L[i][j]  (i > j)
+        // the next pivot from registers only (lane j+1: its own column entry is a_(j+1)j): keeps the
+        // shared-memory broadcast of the column off the pivot -> reciprocal -> pivot chain
+        if (j + 1 < NP) pivsrc = fma(-l, cj, r[j + 1 < NP ? j + 1 : j]);
+        const bool me = (ii == j);            // (idle lanes shadow row NP-1: they must store what its owner stores)
+        myrcp = me ? rcp : myrcp;
+        mypiv = me ? piv : mypiv;
+        ok = ok && (!me || ((piv > 8.0 * NP * 2.220446049250313e-16 * mdiag) && (piv < 1e300)));
+        LT[j * LDA + ii] = me ? piv : l;
+        if (!(B200LM_LDL_VARIANT & 2)) {
+            const double yj = __shfl_sync(B200LM_FULL, b, j, W);             // y_j = b_j (unit diagonal)
+            b = (i > j) ? fma(-l, yj, b) : b;
+        }
+#pragma unroll
+        for (int k = j + 1; k < NP; ++k) r[k] = fma(-l, cb[k], r[k]);
+    }
+    if (B200LM_LDL_VARIANT & 2) {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const double yj = __shfl_sync(B200LM_FULL, b, j, W);
+            const double lij = LT[j * LDA + ii];
+            b = (i > j) ? fma(-lij, yj, b) : b;
+        }
+    }
+    if (!HALF && act) idg[i] = myrcp;
+    if (HALF) {
+        const unsigned okm = __ballot_sync(B200LM_FULL, ok);
+        ok = ((okm >> (16 * hi)) & 0xffffu) == 0xffffu;
+    } else {
+        ok = __all_sync(B200LM_FULL, ok);
+    }
+    __syncwarp();
+    // z = D^-1 y ;  p = L^-T z  (a system whose factorisation failed computes junk that is never used)
+    b *= myrcp;
+#pragma unroll
+    for (int j = NP - 1; j >= 0; --j) {
+        const double xj = __shfl_sync(B200LM_FULL, b, j, W);
+        const double lji = LT[ii * LDA + j];                                 // L[j][i]
+        b = (i < j) ? fma(-lji, xj, b) : b;
+    }
+    const double p = act ? b : 0.0;
+    // w = L^-1 p ;  p^T (L D L^T)^-1 p = sum_i w_i^2 / d_i
+    double w = p;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        const double wj = __shfl_sync(B200LM_FULL, w, j, W);
+        const double lij = LT[j * LDA + ii];                                 // L[i][j]
+        w = (i > j) ? fma(-lij, wj, w) : w;
+    }
+    double s = p * p, w2 = act ? w * w * myrcp : 0.0;
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(B200LM_FULL, s, o);
+        w2 += __shfl_xor_sync(B200LM_FULL, w2, o);
+    }
+    double minr = 0.0;
+    if (want_ratio) {
+        double q = act ? mypiv / mdiag : 1.0;
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) q = fmin(q, __shfl_xor_sync(B200LM_FULL, q, o));
+        minr = q;
+    }
+    __syncwarp();
+    p_out = p; pn_out = sqrt(s); w2_out = w2; minr_out = minr; ok_out = ok;
+}
+
+// out-of-line entry points (ONE copy of the unrolled code per kernel)
 template <int NP, int LDA>
-__device__ __noinline__ bool factor_solve(const double* A, const double* dsc, double* LT, double* idg,
+__device__ __noinline__ bool factor_solve(const double* A, const double* dsc, double* LT, double* idg, double* colb,
                                           int lane, double alpha, double gh, bool want_ratio,
                                           double* p_out, double* res) {
     // the matrices live in shared memory: tell the compiler, or it emits generic LD/ST
@@ -460,80 +589,12 @@ __device__ __noinline__ bool factor_solve(const double* A, const double* dsc, do
     __builtin_assume(__isShared(dsc));
     __builtin_assume(__isShared(LT));
     __builtin_assume(__isShared(idg));
-    const int i = lane;
-    const bool act = i < NP;
-    const int ii = act ? i : NP - 1;    // idle lanes shadow the last row (results unused): no selects
-    double r[NP];
-    const double di = dsc[ii];
-#pragma unroll
-    for (int k = 0; k < NP; ++k) r[k] = A[ii * LDA + k] * di * dsc[k];
-    // alpha is added when an entry becomes the pivot (only diagonal entries ever see it)
-    const double mdiag = fma(A[ii * LDA + ii] * di, di, alpha);     // diagonal entry of this lane's row
-    double myinv = 1.0, mypiv = 1.0;
-    bool ok = true;
-    double b = act ? -gh : 0.0;          // forward substitution y = L^-1 (-gh) rides along
-    __syncwarp();
-    // unrolled by 4: the row rotation costs register moves only at the loop back-edge
-#pragma unroll 4
-    for (int j = 0; j < NP; ++j) {
-        const double piv = __shfl_sync(B200LM_FULL, r[0], j) + alpha;
-        // 1/sqrt(piv): the scaled matrix has diagonal 1 + alpha, so the pivot is far from the
-        // float range limits; fp32 seed + two Newton steps in fp64 (full double accuracy)
-        double inv = (double)rsqrtf((float)piv);
-        const double hp = 0.5 * piv;
-        inv = inv * fma(-hp * inv, inv, 1.5);
-        inv = inv * fma(-hp * inv, inv, 1.5);
-        const double lij = (i == j) ? piv * inv : r[0] * inv;        // L[i][j]
-        if (i == j) {
-            myinv = inv; mypiv = piv;
-            if (!(piv > 8.0 * NP * 2.220446049250313e-16 * mdiag) || !(piv < 1e300)) ok = false;
-        }
-        if (act) LT[j * LDA + i] = lij;
-        const double yj = __shfl_sync(B200LM_FULL, b * inv, j);
-        if (i == j) b = yj;
-        else if (i > j) b = fma(-lij, yj, b);
-        __syncwarp();
-        const double* lt = LT + j * LDA + j;                         // lt[m] = L[j+m][j]
-#pragma unroll
-        // entries past the row end are junk and never used (they alias the next row of LT, which the next
-        // step overwrites: compute-sanitizer racecheck reports that write-after-read as a warning; benign)
-        for (int m = 1; m < NP; ++m) r[m - 1] = fma(-lij, lt[m], r[m]);
-        r[NP - 1] = 0.0;
-    }
-    ok = __all_sync(B200LM_FULL, ok);
-    if (act) idg[i] = myinv;
-    __syncwarp();
-    double p = 0.0, pn = 0.0, w2 = 0.0, minr = 0.0;
-    if (ok) {
-        // p = L^-T y
-#pragma unroll 1
-        for (int j = NP - 1; j >= 0; --j) {
-            const double xj = __shfl_sync(B200LM_FULL, b * myinv, j);
-            const double lji = act ? LT[i * LDA + j] : 0.0;
-            if (i == j) b = xj;
-            else if (i < j) b = fma(-lji, xj, b);
-        }
-        p = act ? b : 0.0;
-        pn = sqrt(warp_sum(p * p));
-        // w = L^-1 p
-        double w = p;
-#pragma unroll 1
-        for (int j = 0; j < NP; ++j) {
-            const double yj = __shfl_sync(B200LM_FULL, w * myinv, j);
-            const double lij = act ? LT[j * LDA + i] : 0.0;
-            if (i == j) w = yj;
-            else if (i > j) w = fma(-lij, yj, w);
-        }
-        w2 = warp_sum(act ? w * w : 0.0);
-        if (want_ratio) {
-            double q = act ? mypiv / mdiag : 1.0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) q = fmin(q, __shfl_xor_sync(B200LM_FULL, q, o));
-            minr = q;
-        }
-    }
-    *p_out = p;
-    res[0] = pn; res[1] = w2; res[2] = minr;
+    __builtin_assume(__isShared(colb));
+    double p, pn, w2, minr;
+    bool ok;
+    ldl_solve<NP, LDA, false>(A, dsc, LT, LT, idg, colb, lane, alpha, alpha, gh, want_ratio, p, pn, w2, minr, ok);
+    *p_out = ok ? p : 0.0;
+    res[0] = ok ? pn : 0.0; res[1] = ok ? w2 : 0.0; res[2] = ok ? minr : 0.0;
     return ok;
 }
 
@@ -548,7 +609,7 @@ struct GNCache {
 // (cf. scipy/optimize/_lsq/common.py: solve_lsq_trust_region, with the secular equation
 // evaluated through Cholesky factors instead of singular values.)
 template <class F>
-__device__ double solve_tr(WarpCtx<F>& c, double gh, double Delta, double& alpha, int& nfac, GNCache& gn) {
+__device__ double solve_tr(WarpCtx<F>& c, double gh, double Delta, double& alpha, int& nfac, GNCache& gn, long long& fclk) {
     typedef FitLayout<F> Lay;
     constexpr int NP = Lay::NP, LDA = Lay::LDA;
     const int lane = c.lane;
@@ -563,13 +624,17 @@ __device__ double solve_tr(WarpCtx<F>& c, double gh, double Delta, double& alpha
     if (!gn.valid && alpha > 0.0) {
         ++nfac;
         tried_warm = true;
-        warm_ok = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, alpha, gh, false, &warm_p, res);
+        const long long tq = clock64();
+        warm_ok = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, c.colb, lane, alpha, gh, false, &warm_p, res);
+        fclk += clock64() - tq;
         if (warm_ok) { warm_pn = res[0]; warm_w2 = res[1]; warm_phi = warm_pn - Delta; }
     }
     const bool need_gn = !(tried_warm && warm_ok && warm_phi > 0.0);
     if (!gn.valid && need_gn) {
         ++nfac;
-        gn.full_rank = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, 0.0, gh, false, &p, res);
+        const long long tq = clock64();
+        gn.full_rank = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, c.colb, lane, 0.0, gh, false, &p, res);
+        fclk += clock64() - tq;
         gn.p = p; gn.pn = res[0]; gn.w2 = res[1];
         gn.valid = true;
     }
@@ -598,7 +663,9 @@ __device__ double solve_tr(WarpCtx<F>& c, double gh, double Delta, double& alpha
             if (alpha < alpha_lower || alpha > alpha_upper)
                 alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
             ++nfac;
-            ok = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, alpha, gh, false, &pt, res);
+            const long long tq = clock64();
+            ok = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, c.colb, lane, alpha, gh, false, &pt, res);
+            fclk += clock64() - tq;
         }
         if (!ok) {
             alpha_lower = fmax(alpha_lower, alpha);
@@ -624,87 +691,23 @@ __device__ double solve_tr(WarpCtx<F>& c, double gh, double Delta, double& alpha
 }
 
 // ---------------------------------------------------------------------------
-// Two shifts per factorisation round (np <= 16).  Lane i owns row i, so lanes 16..31 idle during the
-// factorisation above: here they factor the SAME matrix with a second shift in the same instructions
-// (all broadcasts are 16-wide shuffles, each half has its own L^T).  Used by solve_tr_dual.
-//   lanes 0..15 : d A d + alpha_lo I      lanes 16..31 : d A d + alpha_hi I
-// Per lane outputs refer to the lane's own half: p (entry lane%16 of the step), |p|, |L^-1 p|^2, ok.
+// Two shifts per factorisation round (np <= 16): lanes 0..15 factor d A d + alpha_lo I, lanes 16..31
+// d A d + alpha_hi I in the same instructions (ldl_solve<HALF>).  Used by solve_tr_dual.
+// Per lane outputs refer to the lane's own half: p (entry lane%16 of the step), |p|, p^T M^-1 p, ok.
 // ---------------------------------------------------------------------------
 template <int NP, int LDA>
-__device__ __noinline__ void factor_solve2(const double* A, const double* dsc, double* LT0, double* LT1, int lane,
-                                           double alpha_lo, double alpha_hi, double gh_lo,
+__device__ __noinline__ void factor_solve2(const double* A, const double* dsc, double* LT0, double* LT1, double* colb,
+                                           int lane, double alpha_lo, double alpha_hi, double gh_lo,
                                            double* p_out, double* pn_out, double* w2_out, bool* ok_out) {
-    static_assert(NP <= 16, "two systems per warp need np <= 16");
     __builtin_assume(__isShared(A));
     __builtin_assume(__isShared(dsc));
     __builtin_assume(__isShared(LT0));
     __builtin_assume(__isShared(LT1));
-    const int hi = lane >> 4, i = lane & 15;
-    const bool act = i < NP;
-    const int ii = act ? i : NP - 1;
-    const double alpha = hi ? alpha_hi : alpha_lo;
-    double* LT = hi ? LT1 : LT0;
-    const double gh = __shfl_sync(B200LM_FULL, gh_lo, i);            // both halves solve for the same gradient
-    double r[NP];
-    const double di = dsc[ii];
-#pragma unroll
-    for (int k = 0; k < NP; ++k) r[k] = A[ii * LDA + k] * di * dsc[k];
-    const double mdiag = fma(A[ii * LDA + ii] * di, di, alpha);
-    double myinv = 1.0;
-    bool ok = true;
-    double b = act ? -gh : 0.0;
-    __syncwarp();
-#pragma unroll 4
-    for (int j = 0; j < NP; ++j) {
-        const double piv = __shfl_sync(B200LM_FULL, r[0], j, 16) + alpha;
-        double inv = (double)rsqrtf((float)piv);
-        const double hp = 0.5 * piv;
-        inv = inv * fma(-hp * inv, inv, 1.5);
-        inv = inv * fma(-hp * inv, inv, 1.5);
-        const double lij = (i == j) ? piv * inv : r[0] * inv;
-        if (i == j) {
-            myinv = inv;
-            if (!(piv > 8.0 * NP * 2.220446049250313e-16 * mdiag) || !(piv < 1e300)) ok = false;
-        }
-        if (act) LT[j * LDA + i] = lij;
-        const double yj = __shfl_sync(B200LM_FULL, b * inv, j, 16);
-        if (i == j) b = yj;
-        else if (i > j) b = fma(-lij, yj, b);
-        __syncwarp();
-        const double* lt = LT + j * LDA + j;
-#pragma unroll
-        for (int m = 1; m < NP; ++m) r[m - 1] = fma(-lij, lt[m], r[m]);
-        r[NP - 1] = 0.0;
-    }
-    const unsigned okm = __ballot_sync(B200LM_FULL, ok);
-    ok = ((okm >> (16 * hi)) & 0xffffu) == 0xffffu;
-    __syncwarp();
-    // p = L^-T y  (a half whose factorisation failed computes junk that is never used)
-#pragma unroll 1
-    for (int j = NP - 1; j >= 0; --j) {
-        const double xj = __shfl_sync(B200LM_FULL, b * myinv, j, 16);
-        const double lji = act ? LT[i * LDA + j] : 0.0;
-        if (i == j) b = xj;
-        else if (i < j) b = fma(-lji, xj, b);
-    }
-    const double p = act ? b : 0.0;
-    double s = p * p;
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(B200LM_FULL, s, o);
-    // w = L^-1 p
-    double w = p;
-#pragma unroll 1
-    for (int j = 0; j < NP; ++j) {
-        const double yj = __shfl_sync(B200LM_FULL, w * myinv, j, 16);
-        const double lij = act ? LT[j * LDA + i] : 0.0;
-        if (i == j) w = yj;
-        else if (i > j) w = fma(-lij, yj, w);
-    }
-    double w2 = act ? w * w : 0.0;
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) w2 += __shfl_xor_sync(B200LM_FULL, w2, o);
-    __syncwarp();
-    *p_out = p; *pn_out = sqrt(s); *w2_out = w2; *ok_out = ok;
+    __builtin_assume(__isShared(colb));
+    double p, pn, w2, minr;
+    bool ok;
+    ldl_solve<NP, LDA, true>(A, dsc, LT0, LT1, nullptr, colb, lane, alpha_lo, alpha_hi, gh_lo, false, p, pn, w2, minr, ok);
+    *p_out = p; *pn_out = pn; *w2_out = w2; *ok_out = ok;
 }
 
 // 1/|p(alpha)| is close to linear in alpha; its fit from the previous trial predicts the Levenberg
@@ -726,7 +729,7 @@ struct TRCand {
 // (numpy model tests/lm_model.py: solve_tr_dual).  Falls back to solve_tr if no shift could be factorised.
 template <class F>
 __device__ double solve_tr_dual(WarpCtx<F>& c, double gh, double Delta, double& alpha, int& nfac, GNCache& gn,
-                                LinModel& lm) {
+                                LinModel& lm, long long& fclk) {
     typedef FitLayout<F> Lay;
     constexpr int NP = Lay::NP, LDA = Lay::LDA;
     constexpr int NPD = NP <= 16 ? NP : 16;          // (never instantiated for np > 16; keeps the template legal)
@@ -744,7 +747,9 @@ __device__ double solve_tr_dual(WarpCtx<F>& c, double gh, double Delta, double& 
     auto dual = [&](double a_lo, double a_hi, TRCand& lo, TRCand& hi) {
         double p, pn, w2;
         bool ok;
-        factor_solve2<NPD, LDA>(c.A, c.dsc, c.L, LT1, lane, a_lo, a_hi, gh, &p, &pn, &w2, &ok);
+        const long long tq = clock64();
+        factor_solve2<NPD, LDA>(c.A, c.dsc, c.L, LT1, c.colb, lane, a_lo, a_hi, gh, &p, &pn, &w2, &ok);
+        fclk += clock64() - tq;
         nfac += 2;
         lo.a = a_lo; hi.a = a_hi;
         lo.p = p;
@@ -772,7 +777,9 @@ __device__ double solve_tr_dual(WarpCtx<F>& c, double gh, double Delta, double& 
     if (!gn.valid && !(alpha > 0.0)) {
         double res[3], p0;
         ++nfac;
-        gn.full_rank = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, 0.0, gh, false, &p0, res);
+        const long long tq = clock64();
+        gn.full_rank = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, c.colb, lane, 0.0, gh, false, &p0, res);
+        fclk += clock64() - tq;
         gn.p = p0; gn.pn = res[0]; gn.w2 = res[1];
         gn.valid = true;
     } else {
@@ -832,7 +839,7 @@ __device__ double solve_tr_dual(WarpCtx<F>& c, double gh, double Delta, double& 
             if (alpha > alpha_upper) alpha_upper = 2.0 * alpha;
         }
     }
-    if (!best.ok) return solve_tr<F>(c, gh, Delta, alpha, nfac, gn);
+    if (!best.ok) return solve_tr<F>(c, gh, Delta, alpha, nfac, gn, fclk);
     // model of 1/|p(alpha)| for the next trial
     if (second.ok && second.a != best.a) {
         const double b = (1.0 / second.pn - 1.0 / best.pn) / (second.a - best.a);
@@ -852,25 +859,25 @@ __device__ double solve_tr_dual(WarpCtx<F>& c, double gh, double Delta, double& 
     return p;
 }
 
-// covariance (J^T J)^-1 = d (L L^T)^-1 d from the factor of the scaled matrix at alpha=0
-// (c.L holds L^T: c.L[k*LDA + j] = L[j][k]).  Uses c.A as scratch for L^-1 (column a computed by
-// lane a).  Returns log det(J^T J).
+// covariance (J^T J)^-1 = d (L D L^T)^-1 d from the factor of the scaled matrix at alpha=0
+// (c.L holds L^T with the pivots on the diagonal: c.L[k*LDA + j] = L[j][k], c.L[j*LDA + j] = D_j; c.idg = 1/D).
+// Uses c.A as scratch for L^-1 (column a computed by lane a).  Returns log det(J^T J).
 template <class F>
 __device__ double covariance_from_chol(WarpCtx<F>& c, double* cov_out) {
     typedef FitLayout<F> Lay;
     constexpr int NP = Lay::NP, LDA = Lay::LDA;
     const int a = c.lane;
     double ld = 0.0;
-    if (a < NP) ld = 2.0 * (log(c.L[a * LDA + a]) - log(c.dsc[a]));
+    if (a < NP) ld = log(c.L[a * LDA + a]) - 2.0 * log(c.dsc[a]);
     ld = warp_sum(ld);
     __syncwarp();
     if (a < NP) {
-        // column a of Linv: x_j = (delta_ja - sum_{a<=k<j} L[j][k] x_k) / L_jj , j >= a
+        // column a of Linv (unit lower): x_j = delta_ja - sum_{a<=k<j} L[j][k] x_k , j >= a
         for (int j = 0; j < NP; ++j) {
             double s = (j == a) ? 1.0 : 0.0;
             if (j < a) { c.A[j * LDA + a] = 0.0; continue; }
             for (int k = a; k < j; ++k) s = fma(-c.L[k * LDA + j], c.A[k * LDA + a], s);
-            c.A[j * LDA + a] = s * c.idg[j];
+            c.A[j * LDA + a] = s;
         }
     }
     __syncwarp();
@@ -878,7 +885,7 @@ __device__ double covariance_from_chol(WarpCtx<F>& c, double* cov_out) {
         for (int b = 0; b < NP; ++b) {
             double s = 0.0;
             const int k0 = a > b ? a : b;
-            for (int k = k0; k < NP; ++k) s = fma(c.A[k * LDA + a], c.A[k * LDA + b], s);
+            for (int k = k0; k < NP; ++k) s = fma(c.A[k * LDA + a] * c.idg[k], c.A[k * LDA + b], s);
             cov_out[a * NP + b] = s * c.dsc[a] * c.dsc[b];
         }
     }
@@ -948,34 +955,51 @@ __device__ __forceinline__ void setup_ctx(WarpCtx<F>& c, double* smem, const Fit
     c.idg = c.dsc + Lay::NP;
     c.gbuf[0] = c.g;
     c.gbuf[1] = c.idg + Lay::NP;
+    c.colb = c.gbuf[1] + Lay::NP;
     __syncthreads();
 }
 
+// Evaluator of the one-warp-per-fit kernel: the warp evaluates all rows itself.
 template <class F>
-__global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(const __grid_constant__ FitParams P) {
+struct WarpEval {
+    // the means of fit b (global memory)
+    __device__ __forceinline__ const double* begin(WarpCtx<F>&, const FitParams& P, int b) {
+        return P.mean + (size_t)b * P.mean_stride;
+    }
+    __device__ __forceinline__ double run(WarpCtx<F>& c, const double* pv, double* fout, double* Jout, int mode) {
+        return mode == 0 ? eval_full<F, 0>(c, pv, fout, Jout) : eval_full<F, 1>(c, pv, fout, Jout);
+    }
+};
+
+// One complete fit (number b of the batch) driven by the warp that owns `c`: trust-region loop, optional
+// polish, covariance, results.  EV::run evaluates residual + Jacobian + normal equations at a point -- by
+// this warp alone (WarpEval) or by the warps of a team (lm_team.cuh: TeamEval); everything else is the
+// same code for both kernels.
+// cycle counters of the warp that drives a fit (diagnostics: b200lm_last_stats entries 3..)
+struct PhaseClock {
+    long long eval, solve, total, fact;
+    __device__ __forceinline__ void clear() { eval = 0; solve = 0; total = 0; fact = 0; }
+};
+
+template <class F, class EV>
+__device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& P, int b,
+                                        unsigned long long& tot_nfev, unsigned long long& tot_njev,
+                                        unsigned long long& tot_nfac, PhaseClock& pk) {
     typedef FitLayout<F> Lay;
     constexpr int NP = Lay::NP, LDA = Lay::LDA;
-    static_assert(NP <= 32, "one lane per parameter");
-    extern __shared__ double smem[];
-    WarpCtx<F> c(P);
-    setup_ctx<F>(c, smem, P);
     const int lane = c.lane;
     const bool act = lane < NP;
-    unsigned long long tot_nfev = 0, tot_njev = 0, tot_nfac = 0;
-
-    for (;;) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(P.counter, 1);
-        b = __shfl_sync(B200LM_FULL, b, 0);
-        if (b >= P.B) break;
-        c.mean = P.mean + (size_t)b * P.mean_stride;
+    {
+        c.mean = ev.begin(c, P, b);
         const double* p0 = P.p0 + (size_t)b * P.p0_stride;
         if (act) c.p[lane] = p0[lane];
         __syncwarp();
 
         int cur = 0;                              // buffer holding J^T J, J^T r of the current point
         c.A = c.Abuf[0]; c.g = c.gbuf[0];
-        double cost = eval_full<F>(c, c.p, nullptr, nullptr);
+        const long long t_fit0 = clock64();
+        double cost = ev.run(c, c.p, nullptr, nullptr, 0);
+        pk.eval += clock64() - t_fit0;
         int nfev = 1, njev = 1, nfac = 0;
         int status = -2;                         // -2: running
         if (!isfinite(cost)) status = -1;
@@ -1007,15 +1031,17 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
             gn.valid = false;
             while (actual_reduction <= 0.0 && nfev < P.maxit) {
                 double sh;
+                const long long t_s0 = clock64();
                 // two shifts per round pay off where the factorisation dominates a trial (np = 12..16: +8 % on
                 // C3); for small np the extra control flow and code size cost more than they save (C4, np = 6:
                 // -10 %), so those kernels do not even contain the dual path
                 if constexpr (NP >= 12 && NP <= 16) {
-                    sh = (P.dual_from >= 0 && nfev >= P.dual_from) ? solve_tr_dual<F>(c, gh, Delta, alpha, nfac, gn, lm)
-                                                                   : solve_tr<F>(c, gh, Delta, alpha, nfac, gn);
+                    sh = (P.dual_from >= 0 && nfev >= P.dual_from) ? solve_tr_dual<F>(c, gh, Delta, alpha, nfac, gn, lm, pk.fact)
+                                                                   : solve_tr<F>(c, gh, Delta, alpha, nfac, gn, pk.fact);
                 } else {
-                    sh = solve_tr<F>(c, gh, Delta, alpha, nfac, gn);
+                    sh = solve_tr<F>(c, gh, Delta, alpha, nfac, gn, pk.fact);
                 }
+                pk.solve += clock64() - t_s0;
                 const double step = act ? d * sh : 0.0;
                 if (act) { c.pn[lane] = c.p[lane] + step; c.idg[lane] = step; }
                 __syncwarp();
@@ -1031,7 +1057,9 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
                 // second pass over the rows is needed; a rejected trial leaves the current
                 // buffers untouched.
                 c.A = c.Abuf[cur ^ 1]; c.g = c.gbuf[cur ^ 1];
-                cost_new = eval_full<F>(c, c.pn, nullptr, nullptr);
+                const long long t_e0 = clock64();
+                cost_new = ev.run(c, c.pn, nullptr, nullptr, 0);
+                pk.eval += clock64() - t_e0;
                 c.A = c.Abuf[cur]; c.g = c.gbuf[cur];
                 ++nfev; ++njev;
                 const double shn = sqrt(warp_sum(act ? sh * sh : 0.0));
@@ -1088,13 +1116,13 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
                 ++nfac;
                 const double gh = act ? d * c.g[lane] : 0.0;
                 double sh, pres[3];
-                if (!factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, 0.0, gh, false, &sh, pres)) break;
+                if (!factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, c.colb, lane, 0.0, gh, false, &sh, pres)) break;
                 const double dec = -warp_sum(act ? gh * sh : 0.0);
                 if (it > 0) {
                     if (!(dec < dec_prev)) {                        // the last step did not help: undo it
                         if (act) { const double t = c.p[lane]; c.p[lane] = c.pn[lane]; c.pn[lane] = t; }
                         __syncwarp();
-                        cost = eval_full<F>(c, c.p, nullptr, nullptr);
+                        cost = ev.run(c, c.p, nullptr, nullptr, 0);
                         ++njev;
                         break;
                     }
@@ -1104,12 +1132,12 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
                 // keep the old point in pn, step to the new one
                 if (act) { const double t = c.p[lane]; c.pn[lane] = t; c.p[lane] = t + d * sh; }
                 __syncwarp();
-                const double cost_try = eval_full<F>(c, c.p, nullptr, nullptr);
+                const double cost_try = ev.run(c, c.p, nullptr, nullptr, 0);
                 ++nfev; ++njev;
                 if (!isfinite(cost_try)) {
                     if (act) c.p[lane] = c.pn[lane];
                     __syncwarp();
-                    cost = eval_full<F>(c, c.p, nullptr, nullptr);
+                    cost = ev.run(c, c.p, nullptr, nullptr, 0);
                     ++njev;
                     break;
                 }
@@ -1119,8 +1147,8 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
 
         // ---- results -----------------------------------------------------------
         if (P.f_out || P.J_out) {
-            cost = eval_full<F>(c, c.p, P.f_out ? P.f_out + (size_t)b * P.nchiv : nullptr,
-                                P.J_out ? P.J_out + (size_t)b * P.nchiv * NP : nullptr);
+            cost = ev.run(c, c.p, P.f_out ? P.f_out + (size_t)b * P.nchiv : nullptr,
+                          P.J_out ? P.J_out + (size_t)b * P.nchiv * NP : nullptr, 0);
         }
         // covariance at the solution, scaled by the current column norms for conditioning
         double dfin = 1.0;
@@ -1132,7 +1160,7 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
         __syncwarp();
         ++nfac;
         double pdummy, fres[3];
-        const bool okc = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, lane, 0.0, 0.0, true, &pdummy, fres);
+        const bool okc = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, c.colb, lane, 0.0, 0.0, true, &pdummy, fres);
         const double pivr = fres[2];
         double* cov_out = P.cov ? P.cov + (size_t)b * NP * NP : nullptr;
         double ld = nan("");
@@ -1141,7 +1169,7 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
             ld = covariance_from_chol<F>(c, cov_out);
         } else if (isfinite(cost)) {
             // ill conditioned: one more pass over the rows, Householder QR of J.diag(dsc)
-            eval_full<F, 1>(c, c.p, nullptr, nullptr);
+            ev.run(c, c.p, nullptr, nullptr, 1);
             ++njev;
             ld = covariance_from_qr<F>(c, cov_out);
         } else if (cov_out && act) {
@@ -1155,12 +1183,39 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
             if (P.logdet) P.logdet[b] = ld;
         }
         tot_nfev += nfev; tot_njev += njev; tot_nfac += nfac;
+        pk.total += clock64() - t_fit0;
         __syncwarp();
+    }
+}
+
+template <class F>
+__global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(const __grid_constant__ FitParams P) {
+    typedef FitLayout<F> Lay;
+    static_assert(Lay::NP <= 32, "one lane per parameter");
+    extern __shared__ double smem[];
+    WarpCtx<F> c(P);
+    setup_ctx<F>(c, smem, P);
+    const int lane = c.lane;
+    unsigned long long tot_nfev = 0, tot_njev = 0, tot_nfac = 0;
+    WarpEval<F> ev;
+    PhaseClock pk;
+    pk.clear();
+
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(P.counter, 1);
+        b = __shfl_sync(B200LM_FULL, b, 0);
+        if (b >= P.B) break;
+        fit_one<F>(c, ev, P, b, tot_nfev, tot_njev, tot_nfac, pk);
     }
     if (lane == 0 && P.stats) {
         atomicAdd(&P.stats[0], tot_nfev);
         atomicAdd(&P.stats[1], tot_njev);
         atomicAdd(&P.stats[2], tot_nfac);
+        atomicAdd(&P.stats[3], (unsigned long long)pk.eval);
+        atomicAdd(&P.stats[4], (unsigned long long)pk.solve);
+        atomicAdd(&P.stats[5], (unsigned long long)pk.total);
+        atomicAdd(&P.stats[11], (unsigned long long)pk.fact);
     }
 }
 

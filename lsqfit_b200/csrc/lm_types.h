@@ -13,6 +13,8 @@ struct BlockDesc {
     int idx_off;     // offset into blk_idx[]  (n_in entries: index into y(+)prior)
     int wt_off;      // offset into blk_wt[]   (W[r*ldw + k], n_out rounded up to 8 rows)
     int chiv_off;    // first residual slot of this block in chiv
+    int ldw2;        // team kernel copy: row stride (== 8 mod 16, >= n_in rounded up to 8)
+    int wt2_off;     // offset into blk_wt2[]
 };
 
 struct FitParams {
@@ -30,11 +32,17 @@ struct FitParams {
     const int* blk_idx;
     const double* blk_wt;
     int wt_total;               // doubles in blk_wt
+    const double* blk_wt2;      // the same weights in the team kernel's layout (BlockDesc::ldw2)
+    int wt2_total;
     int wt_in_smem;             // stage blk_wt in shared memory
     int rb;                     // rows of the per-warp row buffer
     int dual_from;              // from this evaluation count on, the secular equation is evaluated at two
                                 // values of alpha per factorisation round (np <= 16); < 0: never
     int warps;                  // warps per CTA
+    int nblk_idx;               // entries of blk_idx (sum of n_in)
+    int staged;                 // team kernel: weights AND the index / x tables are staged in shared memory
+    int team_stride;            // team kernel: doubles of shared memory per team
+    int team;                   // warps per fit: 0/1 = one warp per fit (fit_kernel), 2 or 4 = fit_team_kernel
     // ---- batch ------------------------------------------------------------
     int B;
     const double* mean;         // [B][N] (mean_stride = N) or shared (mean_stride = 0)

@@ -13,9 +13,14 @@ struct FunctorEntry {
     cudaError_t (*fit)(FitParams, int sm_count, size_t smem_budget, cudaStream_t);
     cudaError_t (*resjac)(FitParams, int sm_count, size_t smem_budget, cudaStream_t);
     size_t (*per_warp_bytes)(int rb);
+    // team kernels (lm_team.cuh), indexed by log2(warps per fit) - 1: [0] two warps, [1] four warps;
+    // NULL where the functor has no team instantiation
+    cudaError_t (*fit_team[2])(FitParams, int sm_count, size_t smem_budget, cudaStream_t);
+    size_t (*team_bytes[2])(int N);
 };
 
 const FunctorEntry* registry_multiexp(int* n);
+const FunctorEntry* registry_multiexp_b(int* n);
 const FunctorEntry* registry_nist_a(int* n);
 const FunctorEntry* registry_nist_b(int* n);
 const FunctorEntry* registry_misc(int* n);
@@ -24,12 +29,18 @@ const FunctorEntry* registry_misc(int* n);
 
 #ifdef B200LM_DEFINE_ENTRIES
 #include "lm_kernel.cuh"
+#include "lm_team.cuh"
 #include "functors.cuh"
 namespace b200lm {
 template <class F>
 size_t per_warp_bytes_of(int rb) { return (size_t)FitLayout<F>::per_warp_doubles(rb) * sizeof(double); }
 #define B200LM_ENTRY(family, name, ...) \
     { family, __VA_ARGS__::NP, __VA_ARGS__::NX, name, &launch_fit<__VA_ARGS__>, &launch_resjac<__VA_ARGS__>, \
-      &per_warp_bytes_of<__VA_ARGS__> }
+      &per_warp_bytes_of<__VA_ARGS__>, {nullptr, nullptr}, {nullptr, nullptr} }
+// entry with team kernels (2 and 4 warps per fit)
+#define B200LM_ENTRY_TEAM(family, name, ...) \
+    { family, __VA_ARGS__::NP, __VA_ARGS__::NX, name, &launch_fit<__VA_ARGS__>, &launch_resjac<__VA_ARGS__>, \
+      &per_warp_bytes_of<__VA_ARGS__>, {&launch_fit_team<__VA_ARGS__, 2>, &launch_fit_team<__VA_ARGS__, 4>}, \
+      {&team_bytes_of<__VA_ARGS__, 2>, &team_bytes_of<__VA_ARGS__, 4>} }
 }  // namespace b200lm
 #endif

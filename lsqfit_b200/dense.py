@@ -90,8 +90,10 @@ class DenseFit(object):
     covariance and derivative matrix of ``fit.p`` (``_getp``, :897-922).
     """
 
-    def __init__(self, data, prior, p0=None, svdcut=1e-12, eps=None, tol=1e-8, maxit=1000, scaler="more",
+    def __init__(self, data, prior, p0=None, svdcut=False, eps=False, tol=1e-8, maxit=1000, scaler="more",
                  polish=0, device=0, pdf=None):
+        from .fit import resolve_svdcut_eps
+        svdcut, eps = resolve_svdcut_eps(svdcut, eps)
         t, ymean, ycov = data
         pm, psd = prior
         la = self.la = _LA(device)

@@ -30,32 +30,39 @@ def unpack_results(packed):
 
 
 def gather_results(packed, B_total=None, group=None):
-    """All-gather the packed results of every rank in rank order.  Shards may differ in size
-    by one row, so they are padded to the largest shard and trimmed afterwards."""
+    """All-gather the packed results of every rank in rank order: ONE collective, no host
+    synchronisation.  Shards follow ``shard_range`` (sizes differ by at most one row), so every
+    rank can compute all shard sizes from ``B_total`` alone; without ``B_total`` the shards are
+    taken to be equal (the weak-scaling case).  Smaller shards are padded to the largest."""
     if not (dist.is_available() and dist.is_initialized()):
         return packed
     world = dist.get_world_size(group)
-    n = torch.tensor([packed.shape[0]], device=packed.device, dtype=torch.int64)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    n = packed.shape[0]
+    if B_total is None:
+        sizes = [n] * world
+    else:
+        sizes = [shard_range(B_total, r, world)[1] - shard_range(B_total, r, world)[0] for r in range(world)]
+        if sizes[dist.get_rank(group)] != n:
+            raise ValueError("shard of %d rows does not match shard_range(B_total=%d)" % (n, B_total))
     nmax = max(sizes)
     pad = packed
-    if packed.shape[0] < nmax:
-        pad = torch.cat([packed, packed.new_zeros((nmax - packed.shape[0], packed.shape[1]))])
+    if n < nmax:
+        pad = torch.cat([packed, packed.new_zeros((nmax - n, packed.shape[1]))])
     out = packed.new_empty((world * nmax, packed.shape[1]))
     dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
-    parts = [out[r * nmax: r * nmax + sizes[r]] for r in range(world)]
-    return torch.cat(parts)
+    if min(sizes) == nmax:
+        return out
+    return torch.cat([out[r * nmax: r * nmax + sizes[r]] for r in range(world)])
 
 
 def moments(x, ok, group=None):
     """Mean and covariance of the converged best-fit parameters over ALL ranks
     (one all-reduce of count, sum x, sum x x^T)."""
-    okf = ok.to(x.dtype)[:, None]
-    xs = x * okf
+    okb = ok.to(torch.bool)[:, None]
+    # select, do not multiply: a failed fit may hold NaN/Inf, and 0 * NaN would poison every rank
+    xs = torch.where(okb, x, torch.zeros_like(x))
     npar = x.shape[1]
-    buf = torch.cat([okf.sum().reshape(1), xs.sum(dim=0), (xs.T @ x).reshape(-1)])
+    buf = torch.cat([okb.sum().to(x.dtype).reshape(1), xs.sum(dim=0), (xs.T @ xs).reshape(-1)])
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     n = buf[0]

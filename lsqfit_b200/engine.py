@@ -146,11 +146,22 @@ class Plan(object):
         """Same fit through the host-buffer C entry point: numpy in, numpy out.
         ``out`` may hold preallocated arrays (dict with keys x, chi2, cov, logdet, nit, status)."""
         xtol, gtol, ftol = normalize_tol(tol)
-        mean = np.ascontiguousarray(mean, dtype=np.float64) if not isinstance(mean, np.ndarray) else mean
-        p0 = np.ascontiguousarray(p0, dtype=np.float64) if not isinstance(p0, np.ndarray) else p0
+        # the C entry point reads raw host pointers: dtype, contiguity and shapes are checked HERE
+        # (np.ascontiguousarray is a no-op for conforming arrays)
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        p0 = np.ascontiguousarray(p0, dtype=np.float64)
+        if mean.ndim not in (1, 2) or mean.shape[-1] != self.N:
+            raise ValueError("mean must be [N] or [B, N] with N = %d, got %s" % (self.N, mean.shape))
+        if p0.ndim not in (1, 2) or p0.shape[-1] != self.np:
+            raise ValueError("p0 must be [np] or [B, np] with np = %d, got %s" % (self.np, p0.shape))
         sm = 0 if mean.ndim == 1 else self.N
         sp = 0 if p0.ndim == 1 else self.np
         B = mean.shape[0] if sm else (p0.shape[0] if sp else 1)
+        if (sm and mean.shape[0] != B) or (sp and p0.shape[0] != B):
+            raise ValueError("mean and p0 disagree on the batch size")
+        shapes = dict(x=((B, self.np), np.float64), chi2=((B,), np.float64), cov=((B, self.np, self.np), np.float64),
+                      logdet=((B,), np.float64), nit=((B,), np.int32), status=((B,), np.int32),
+                      f=((B, self.nchiv), np.float64), J=((B, self.nchiv, self.np), np.float64))
         if out is None:
             out = dict(
                 x=np.empty((B, self.np)), chi2=np.empty(B),
@@ -158,6 +169,18 @@ class Plan(object):
                 nit=np.empty(B, dtype=np.int32), status=np.empty(B, dtype=np.int32),
                 f=np.empty((B, self.nchiv)) if want_fJ else None,
                 J=np.empty((B, self.nchiv, self.np)) if want_fJ else None)
+        else:
+            for k in ("x", "chi2", "logdet", "nit", "status"):
+                if out.get(k) is None:
+                    raise ValueError("out[%r] is required" % k)
+            for k, (shp, dt) in shapes.items():
+                a = out.get(k)
+                if a is None:
+                    continue
+                if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags["C_CONTIGUOUS"]
+                        and a.flags["WRITEABLE"] and tuple(a.shape) == shp):
+                    raise ValueError("out[%r] must be a writable C-contiguous %s array of shape %s"
+                                     % (k, np.dtype(dt).name, shp))
         sc = {"more": 1, "jac": 1, 1: 1, "none": 0, "levenberg": 0, None: 0, 0: 0}[scaler]
         ptr = lambda a: a.ctypes.data if a is not None else None
         _cabi.check(_cabi.lib.b200lm_fit_batch_host(
@@ -172,6 +195,16 @@ class Plan(object):
         buf = (C.c_ulonglong * 3)()
         _cabi.check(_cabi.lib.b200lm_last_stats(self._h, buf), self._h)
         return tuple(int(v) for v in buf)
+
+    def last_stats_ex(self, n=16):
+        """All diagnostic counters of the last batch (see b200lm_last_stats_ex); synchronises."""
+        buf = (C.c_ulonglong * 16)()
+        _cabi.check(_cabi.lib.b200lm_last_stats_ex(self._h, buf, int(n)), self._h)
+        return [int(v) for v in buf[:n]]
+
+    def last_team(self):
+        """Warps per fit of the last fit_batch launch (1 = one warp per fit, 2 / 4 = team kernel)."""
+        return int(_cabi.lib.b200lm_last_team(self._h))
 
     def launch_count(self):
         return int(_cabi.lib.b200lm_launch_count(self._h))

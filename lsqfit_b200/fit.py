@@ -43,6 +43,25 @@ def _cov2(c, n):
     return np.diag(c ** 2) if c.ndim == 1 else c
 
 
+def resolve_svdcut_eps(svdcut, eps):
+    """The reference's defaults (src/lsqfit/__init__.py:470-479): neither given -> svdcut = 1e-12,
+    eps = None; only ``eps`` given -> svdcut = None (the eps regulator is used); only ``svdcut`` given
+    -> eps = None.  ``False`` is the "not given" sentinel, as in the reference."""
+    if svdcut is False and eps is False:
+        return 1e-12, None
+    if svdcut is False:
+        return None, eps
+    if eps is False:
+        return svdcut, None
+    return svdcut, eps
+
+
+def fresh_seed():
+    """A new Philox key for unseeded calls (the reference draws from gvar's global RNG, so two
+    unseeded calls never repeat the same noise)."""
+    return int(np.random.SeedSequence().entropy) & (2 ** 64 - 1)
+
+
 def _logGBF(logdet_JtJ, pdf_logdet, chi2, dof):
     """src/lsqfit/__init__.py:720-725"""
     return 0.5 * (-logdet_JtJ - pdf_logdet - chi2 - dof * np.log(2. * np.pi))
@@ -51,10 +70,11 @@ def _logGBF(logdet_JtJ, pdf_logdet, chi2, dof):
 class nonlinear_fit(object):
     FITTERS = {"b200_lm": b200_lm}
 
-    def __init__(self, data=None, fcn=None, prior=None, p0=None, svdcut=1e-12, eps=None,
+    def __init__(self, data=None, fcn=None, prior=None, p0=None, svdcut=False, eps=False,
                  tol=1e-8, maxit=1000, fitter="b200_lm", yp_cov=None, _yp_pdf=None,
                  **fitterargs):
         clock = time.perf_counter()
+        svdcut, eps = resolve_svdcut_eps(svdcut, eps)
         if fitter not in nonlinear_fit.FITTERS:
             raise ValueError("unknown fitter: " + str(fitter))      # __init__.py:529-530
         if isinstance(fcn, str):
@@ -185,11 +205,17 @@ class nonlinear_fit(object):
         by b200lm_bootstrap_means (counter-based Philox: any shard of copies is reproducible on its
         own, so ranks of a multi-GPU job generate only their slice)."""
         from .bootstrap import bootstrap_means
+        if n is None:
+            raise ValueError("n=None (the reference's endless iterator) is not supported: a batch is one launch; "
+                             "pass the number of copies")
+        if seed is None:
+            seed = fresh_seed()
+        self.last_seed = int(seed)
         if self._L is None:
             C = self.yp_pdf.cov
             val, vec = np.linalg.eigh(C)
             self._L = vec * np.sqrt(np.clip(val, 0.0, None))
-        return bootstrap_means(self.yp_pdf.mean, self._L, n, 0 if seed is None else int(seed), first=first,
+        return bootstrap_means(self.yp_pdf.mean, self._L, n, int(seed), first=first,
                                device=self.device)
 
     def bootstrapped_fits(self, n=None, means=None, seed=None, **kargs):
@@ -203,7 +229,10 @@ class nonlinear_fit(object):
         """Iterator face of ``bootstrapped_fits`` (reference __init__.py:1548-1642).
         ``datalist`` yields mean vectors of y (+) prior (array form of the reference's data sets)."""
         if datalist is not None:
-            means = np.array([np.asarray(m, dtype=float).reshape(-1) for m, _ in zip(datalist, range(n or 10 ** 9))])
+            # n = None: every data set of a FINITE datalist (an endless generator needs n)
+            import itertools
+            it = datalist if n is None else itertools.islice(datalist, int(n))
+            means = np.array([np.asarray(m, dtype=float).reshape(-1) for m in it])
         else:
             means = None
         for f in self.bootstrapped_fits(n, means, seed, **kargs):
@@ -305,7 +334,7 @@ class WAvg(object):
         self.svdn = fit.svdn
 
 
-def wavg(means, cov, index=None, nparam=None, svdcut=1e-12, eps=None, **fitterargs):
+def wavg(means, cov, index=None, nparam=None, svdcut=False, eps=False, **fitterargs):
     """Weighted average of correlated estimates (array form of ``lsqfit.wavg``,
     src/lsqfit/_extras.py:358-516): a least-squares fit of the data ``means`` (flat, covariance ``cov``:
     matrix or vector of standard deviations) to ``f_i = p[index[i]]`` without a prior, started at the

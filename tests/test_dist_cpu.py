@@ -46,10 +46,12 @@ def _worker(rank, world, port, B, npar, q):
         st = torch.as_tensor(rng.integers(0, 4, size=B).astype(np.int32))
         lo, hi = lbdist.shard_range(B, rank, world)
         packed = lbdist.pack_results(allx[lo:hi], chi2[lo:hi], nit[lo:hi], st[lo:hi])
-        full = lbdist.gather_results(packed)
+        full = lbdist.gather_results(packed, B_total=B)
         x2, c2, n2, s2 = lbdist.unpack_results(full)
         ok = (torch.equal(x2, allx) and torch.equal(c2, chi2) and torch.equal(n2, nit) and torch.equal(s2, st))
-        m, cov, n = lbdist.moments(allx[lo:hi], st[lo:hi] > 0)
+        xbad = allx.clone()
+        xbad[st <= 0] = float('nan')                         # failed fits may hold NaN: they are selected out, not multiplied by 0
+        m, cov, n = lbdist.moments(xbad[lo:hi], st[lo:hi] > 0)
         sel = allx[st > 0]
         ok = ok and n == int((st > 0).sum())
         ok = ok and torch.allclose(m, sel.mean(dim=0), atol=1e-12)

@@ -38,7 +38,7 @@ def job():
     means = bs.bootstrap_means(m0d, Ld, hi - lo, cfg["seed"], first=lo, device=local)
     out = plan.fit_batch(means, p0d, tol=cfg["tol"], maxit=cfg["maxit"], want_cov=False)
     packed = lbdist.pack_results(out.x, out.chi2, out.nit, out.status)
-    allp = lbdist.gather_results(packed)
+    allp = lbdist.gather_results(packed, B_total=B)
     m, c, n = lbdist.moments(out.x, out.status > 0)
     return allp, m, c, n
 
