@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200lm.so")
+LIB_PATH = os.environ.get("B200LM_LIB") or os.path.join(HERE, "libb200lm.so")     # (override: A/B experiments)
 
 OK, EINVAL, ENOFUNCTOR, ECUDA, ENOMEM, ESIZE = 0, -1, -2, -3, -4, -5
 

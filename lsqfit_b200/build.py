@@ -22,7 +22,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
-          "-I", INCLUDE]
+          "-I", INCLUDE] + os.environ.get("B200LM_EXTRA_CFLAGS", "").split()
 
 
 def _sources():

@@ -35,6 +35,26 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(B200LM_FULL, v, o);
     return v;
 }
+// several sums at once: the butterflies interleave, so the latency is that of ONE reduction
+// (a 64-bit shuffle + add costs ~35 cycles per step on B200, and a trial point needs several norms)
+__device__ __forceinline__ void warp_sum3(double& a, double& b, double& c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ta = __shfl_xor_sync(B200LM_FULL, a, o);
+        const double tb = __shfl_xor_sync(B200LM_FULL, b, o);
+        const double tc = __shfl_xor_sync(B200LM_FULL, c, o);
+        a += ta; b += tb; c += tc;
+    }
+}
+// sum of a and max of m in one pass
+__device__ __forceinline__ void warp_sum_max(double& a, double& m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ta = __shfl_xor_sync(B200LM_FULL, a, o);
+        const double tm = __shfl_xor_sync(B200LM_FULL, m, o);
+        a += ta; m = fmax(m, tm);
+    }
+}
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(B200LM_FULL, v, o));
@@ -1018,9 +1038,16 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
 
         while (status == -2) {
             const double gi = act ? c.g[lane] : 0.0;
-            const double g_norm = warp_max(fabs(gi));
+            // |g|_inf and |x|^2 of the current point in one reduction (x does not change until a step is accepted)
+            double xx = 0.0, g_norm = fabs(gi);
+            {
+                const double pi_ = act ? c.p[lane] : 0.0;
+                xx = pi_ * pi_;
+                warp_sum_max(xx, g_norm);
+            }
             if (g_norm < P.gtol) { status = 1; break; }
             if (nfev >= P.maxit) { status = 0; break; }
+            const double xthr = P.xtol * (P.xtol + sqrt(xx));      // xtol test: |step| < xtol (xtol + |x|)
             const double d = 1.0 / sinv;
             if (act) c.dsc[lane] = d;
             __syncwarp();
@@ -1045,12 +1072,28 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
                 const double step = act ? d * sh : 0.0;
                 if (act) { c.pn[lane] = c.p[lane] + step; c.idg[lane] = step; }
                 __syncwarp();
-                // predicted reduction = -(1/2 step^T A step + g^T step)   (unscaled == scaled)
+                // predicted reduction = -(1/2 step^T A step + g^T step)   (unscaled == scaled); the row sum runs
+                // in four independent chains
                 double As = 0.0;
                 if (act) {
-                    for (int j = 0; j < NP; ++j) As = fma(c.A[lane * LDA + j], c.idg[j], As);
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                    const double* Ar = c.A + lane * LDA;
+#pragma unroll
+                    for (int j = 0; j + 3 < NP; j += 4) {
+                        a0 = fma(Ar[j], c.idg[j], a0);
+                        a1 = fma(Ar[j + 1], c.idg[j + 1], a1);
+                        a2 = fma(Ar[j + 2], c.idg[j + 2], a2);
+                        a3 = fma(Ar[j + 3], c.idg[j + 3], a3);
+                    }
+#pragma unroll
+                    for (int j = NP & ~3; j < NP; ++j) a0 = fma(Ar[j], c.idg[j], a0);
+                    As = (a0 + a1) + (a2 + a3);
                 }
-                const double predicted = -warp_sum(act ? step * (0.5 * As + gi) : 0.0);
+                // predicted reduction, |step|^2 and |sh|^2 in ONE reduction
+                double predicted = act ? -step * (0.5 * As + gi) : 0.0;
+                double step2 = step * step;
+                double sh2 = act ? sh * sh : 0.0;
+                warp_sum3(predicted, step2, sh2);
                 __syncwarp();
                 // Speculative evaluation: residual AND Jacobian / normal equations at the trial
                 // point, into the other buffer.  ~87 % of the trials are accepted, and then no
@@ -1062,25 +1105,31 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
                 pk.eval += clock64() - t_e0;
                 c.A = c.Abuf[cur]; c.g = c.gbuf[cur];
                 ++nfev; ++njev;
-                const double shn = sqrt(warp_sum(act ? sh * sh : 0.0));
-                if (!isfinite(cost_new)) { Delta = 0.25 * shn; continue; }
+                if (!isfinite(cost_new)) { Delta = 0.25 * sqrt(sh2); continue; }
                 actual_reduction = cost - cost_new;
-                double ratio;
-                if (predicted > 0.0) ratio = actual_reduction / predicted;
-                else if (predicted == 0.0 && actual_reduction == 0.0) ratio = 1.0;
-                else ratio = 0.0;
-                double Delta_new = Delta;
-                if (ratio < 0.25) Delta_new = 0.25 * shn;
-                else if (ratio > 0.75 && shn > 0.95 * Delta) Delta_new = 2.0 * Delta;
-                const double step_norm = sqrt(warp_sum(step * step));
-                const double pi_ = act ? c.p[lane] : 0.0;
-                const double x_norm = sqrt(warp_sum(pi_ * pi_));
-                const bool ft = actual_reduction < P.ftol * cost && ratio > 0.25;
-                const bool xt = step_norm < P.xtol * (P.xtol + x_norm);
+                // ratio = actual / predicted enters only through comparisons with 1/4 and 3/4: no division
+                bool lt25, gt25, gt75;
+                if (predicted > 0.0) {
+                    lt25 = actual_reduction < 0.25 * predicted;
+                    gt25 = actual_reduction > 0.25 * predicted;
+                    gt75 = actual_reduction > 0.75 * predicted;
+                } else if (predicted == 0.0 && actual_reduction == 0.0) {
+                    lt25 = false; gt25 = true; gt75 = true;             // ratio = 1
+                } else {
+                    lt25 = true; gt25 = false; gt75 = false;            // ratio = 0
+                }
+                const bool ft = actual_reduction < P.ftol * cost && gt25;
+                const bool xt = step2 < xthr * xthr;
                 if (ft && xt) term = 4; else if (ft) term = 2; else if (xt) term = 3;
                 if (term != -2) break;
-                alpha *= Delta / Delta_new;
-                Delta = Delta_new;
+                if (lt25) {
+                    const double Delta_new = 0.25 * sqrt(sh2);
+                    alpha *= Delta / Delta_new;
+                    Delta = Delta_new;
+                } else if (gt75 && sh2 > (0.95 * 0.95) * Delta * Delta) {
+                    alpha *= 0.5;
+                    Delta = 2.0 * Delta;
+                }
             }
             if (actual_reduction > 0.0) {
                 // accept: the trial buffers become the current ones

@@ -20,7 +20,15 @@
 // which posts "evaluate at p" commands to its helpers; teams synchronise with named barriers, so
 // several teams share one CTA and one staged copy of the weights.
 #pragma once
+#include <cstdio>
 #include "lm_kernel.cuh"
+
+#ifndef B200LM_P2_PIPE
+#define B200LM_P2_PIPE 1
+#endif
+#ifndef B200LM_EVAL_BYREF
+#define B200LM_EVAL_BYREF 0
+#endif
 
 namespace b200lm {
 
@@ -70,6 +78,61 @@ struct ColOut {
     double* p;
     __device__ __forceinline__ double& operator[](int j) const { return p[j * LD]; }
 };
+
+// shared memory of the CTA: [ block weights | x, 1x1 weights | index tables | team 0 | team 1 | ... ]
+struct TeamStage {
+    int wt, x, fw, pw, ints, total;     // offsets in doubles (ints: start of the int tables), total doubles
+};
+__host__ __device__ inline TeamStage team_stage(const FitParams& P) {
+    TeamStage s;
+    s.wt = 0;
+    s.x = (P.wt2_total + 1) & ~1;
+    s.fw = s.x + P.ny * P.nx;
+    s.pw = s.fw + P.nd_fn;
+    s.ints = (s.pw + P.nd_pr + 1) & ~1;
+    const int nints = P.nblk_idx + P.nd_fn + P.nd_pr;
+    s.total = (s.ints + (nints + 1) / 2 + 1) & ~1;
+    return s;
+}
+
+// every pointer of a team's context from its base address (cheap to recompute: the offsets are
+// compile-time constants or kernel parameters, so nothing has to travel through local memory)
+template <class F, int TW>
+__device__ __forceinline__ void team_pointers(TeamCtx<F, TW>& tc, const FitParams& P, double* base, const double* stage) {
+    typedef FitLayout<F> Lay;
+    typedef TeamLayout<F, TW> TL;
+    constexpr int NP = Lay::NP, LDA = Lay::LDA;
+    WarpCtx<F>& c = tc.c;
+    if (P.staged) {
+        const TeamStage st = team_stage(P);
+        const int* si = reinterpret_cast<const int*>(stage + st.ints);
+        c.wt = stage + st.wt;
+        tc.xs = stage + st.x; tc.fw = stage + st.fw; tc.pw = stage + st.pw;
+        tc.bidx = si; tc.fidx = si + P.nblk_idx; tc.pidx = si + P.nblk_idx + P.nd_fn;
+    } else {
+        c.wt = P.blk_wt2;
+        tc.xs = P.x; tc.fw = P.dfn_w; tc.pw = P.dpr_w;
+        tc.bidx = P.blk_idx; tc.fidx = P.dfn_idx; tc.pidx = P.dpr_idx;
+    }
+    c.R = base;
+    c.Abuf[0] = c.R + TL::UNION;
+    c.Abuf[1] = c.Abuf[0] + NP * LDA;
+    c.A = c.Abuf[0];
+    c.L = c.Abuf[1] + NP * LDA;
+    c.p = c.L + NP * LDA;
+    c.pn = c.p + NP;
+    c.g = c.pn + NP;
+    c.sinv = c.g + NP;
+    c.dsc = c.sinv + NP;
+    c.idg = c.dsc + NP;
+    c.gbuf[0] = c.g;
+    c.gbuf[1] = c.idg + NP;
+    c.colb = c.gbuf[1] + NP;                       // column broadcast buffers of the factorisation
+    c.dvec = c.colb + 64;                          // CMD doubles: scratch (4) + command ints
+    tc.cmd = reinterpret_cast<int*>(c.dvec + 4);
+    tc.mean_s = base + TL::FIXED;
+    c.mean = tc.mean_s;
+}
 
 template <class F>
 __device__ __noinline__ void qr_update_rows(const WarpCtx<F>& c_in, double* S, int nrows) {
@@ -172,16 +235,37 @@ __device__ __forceinline__ double team_flush(WarpCtx<F>& c, TeamAcc<F, TW>& na) 
 // A = J^T J, g = J^T r in c.A / c.g and the cost as return value.  mode 1: the leader instead folds
 // all rows into the Householder factor of J.diag(dsc) (final covariance of ill-conditioned fits).
 template <class F, int TW, bool STAGED>
-__device__ __noinline__ double team_eval_impl(const TeamCtx<F, TW>& tc_in, const double* pv, int mode,
+#if B200LM_EVAL_BYREF
+__device__ __noinline__ double team_eval_impl(const TeamCtx<F, TW>& tc_in, int flags, double* fout, double* Jout) {
+#else
+__device__ __noinline__ double team_eval_impl(const FitParams& P, unsigned base_s, unsigned stage_s, int ids, int flags,
                                               double* fout, double* Jout) {
+    // the context arrives as two shared-memory OFFSETS: every pointer is rebuilt from them (constants and
+    // kernel parameters only), so nothing is copied through local memory and the compiler knows the
+    // address space of everything it derives (LDS/STS without __builtin_assume)
+    double* base = reinterpret_cast<double*>(__cvta_shared_to_generic(base_s));
+    const double* stage = reinterpret_cast<const double*>(__cvta_shared_to_generic(stage_s));
+#endif
     typedef FitLayout<F> Lay;
     typedef TeamLayout<F, TW> TL;
     constexpr int NP = Lay::NP, NT = Lay::NT, LDR = Lay::LDR, LDA = Lay::LDA, NCOL = Lay::NCOL;
     constexpr int CH = TL::CH, MT = TL::MT, RW = TL::RW, LDT = TL::LDT, TROWS = TL::TROWS, LPR = TL::LPR;
+    // ids = lane | tw << 8 | bar << 16 ;  flags = mode | pv_sel << 1 | cur << 2
+#if B200LM_EVAL_BYREF
     TeamCtx<F, TW> tc = tc_in;
     WarpCtx<F>& c = tc.c;
     const FitParams& P = c.P;
+#else
+    TeamCtx<F, TW> tc(P);
+    WarpCtx<F>& c = tc.c;
+    team_pointers<F, TW>(tc, P, base, stage);
+    c.lane = ids & 31; tc.tw = (ids >> 8) & 7; tc.bar = ids >> 16;
+#endif
+    const int mode = flags & 1, cur_ = (flags >> 2) & 1;
+    c.A = c.Abuf[cur_]; c.g = c.gbuf[cur_];
+    const double* pv = (flags & 2) ? c.pn : c.p;
     const int lane = c.lane, tw = tc.tw, bar = tc.bar;
+#if B200LM_EVAL_BYREF
     __builtin_assume(__isShared(c.R));
     __builtin_assume(__isShared(c.A));
     __builtin_assume(__isShared(c.g));
@@ -196,14 +280,19 @@ __device__ __noinline__ double team_eval_impl(const TeamCtx<F, TW>& tc_in, const
         __builtin_assume(__isShared(tc.fidx));
         __builtin_assume(__isShared(tc.pidx));
     }
+#endif
     double* Jb = c.R;                       // row-major view  [CH][LDR]  of finished rows [J | r]
     double* T = c.R;                        // transposed view [TROWS][LDT] of a chunk of [G | delta]
     double* Jown = Jb + tw * RW * LDR;      // the rows this warp owns
     TeamAcc<F, TW> na;
     na.clear();
     bool dirty = false;                     // the buffer may still be read by another warp of the team
+#ifdef B200LM_PHASE_TICKS
     long long tk0 = clock64(), tk[5] = {0, 0, 0, 0, 0};
 #define B200LM_TICK(i) do { const long long t_ = clock64(); tk[i] += t_ - tk0; tk0 = t_; } while (0)
+#else
+#define B200LM_TICK(i) do { } while (0)
+#endif
 
     // 1x1 prior rows (leader): J row = w e_j, analytic contribution.  mode 0: added on top of the stored
     // tiles at the end; mode 1: the diagonal matrix that starts the triangular factor.
@@ -280,7 +369,9 @@ __device__ __noinline__ double team_eval_impl(const TeamCtx<F, TW>& tc_in, const
     for (int b = 0; b < P.nblk; ++b) {
         const BlockDesc bd = P.blk[b];
         const double* W = c.wt + bd.wt2_off;
+#if B200LM_EVAL_BYREF
         if constexpr (STAGED) __builtin_assume(__isShared(W));
+#endif
         const int ldw = bd.ldw2;
         for (int g0 = 0; g0 < bd.n_out; g0 += CH) {
             double pc[MT][NT][2];
@@ -340,6 +431,43 @@ __device__ __noinline__ double team_eval_impl(const TeamCtx<F, TW>& tc_in, const
                 // (W is zero padded to whole 64-row groups: no row guards.)
                 const double* wa = W + (size_t)(g0 + 8 * (tw * MT) + r) * ldw + k0 + 2 * q;
                 const double* tb = T + r * LDT + 2 * q;
+#if B200LM_P2_PIPE
+                const double* td = T + NP * LDT + 2 * q;
+                double2 bf[NT], af[MT], dl = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) bf[t] = *reinterpret_cast<const double2*>(tb + 8 * t * LDT);
+#pragma unroll
+                for (int m = 0; m < MT; ++m) af[m] = *reinterpret_cast<const double2*>(wa + (size_t)m * 8 * ldw);
+                if constexpr (!Lay::DELTA_IN_TILE) dl = *reinterpret_cast<const double2*>(td);
+#pragma unroll 2
+                for (int S = 0; S < nk8; S += 8) {
+                    // software pipeline: the fragments of the next slab are in flight while this one is multiplied
+                    // (the last iteration re-reads the current slab: in bounds, unused)
+                    const int Sn = S + 8 < nk8 ? S + 8 : S;
+                    double2 bfn[NT], afn[MT], dln = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) bfn[t] = *reinterpret_cast<const double2*>(tb + 8 * t * LDT + Sn);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) afn[m] = *reinterpret_cast<const double2*>(wa + (size_t)m * 8 * ldw + Sn);
+                    if constexpr (!Lay::DELTA_IN_TILE) dln = *reinterpret_cast<const double2*>(td + Sn);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) dmma(pc[m][t][0], pc[m][t][1], af[m].x, bf[t].x);
+                    }
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) dmma(pc[m][t][0], pc[m][t][1], af[m].y, bf[t].y);
+                        if constexpr (!Lay::DELTA_IN_TILE) pr[m] = fma(af[m].x, dl.x, fma(af[m].y, dl.y, pr[m]));
+                    }
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) bf[t] = bfn[t];
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) af[m] = afn[m];
+                    dl = dln;
+                }
+#else
 #pragma unroll 4
                 for (int S = 0; S < nk8; S += 8) {
                     double2 bf[NT];
@@ -358,6 +486,7 @@ __device__ __noinline__ double team_eval_impl(const TeamCtx<F, TW>& tc_in, const
                         if constexpr (!Lay::DELTA_IN_TILE) pr[m] = fma(af.x, dl.x, fma(af.y, dl.y, pr[m]));
                     }
                 }
+#endif
                 dirty = true;
             }
             team_sync<TW>(bar);                 // every warp has finished reading the chunk
@@ -465,19 +594,35 @@ __device__ __noinline__ double team_eval_impl(const TeamCtx<F, TW>& tc_in, const
     }
     if (tw == 0 && mode == 0) acc += prior_rows();
     B200LM_TICK(4);
+#ifdef B200LM_PHASE_TICKS
     if (tw == 0 && lane == 0 && P.stats) {
 #pragma unroll
         for (int i = 0; i < 5; ++i) atomicAdd(&P.stats[6 + i], (unsigned long long)tk[i]);
     }
+#endif
 #undef B200LM_TICK
+#ifdef B200LM_DEBUG_PRINT
+    if (lane == 0 && blockIdx.x == 0) printf("eval warp %d tw %d mode %d flags %d ids %x acc %g A00 %g g0 %g base %p A %p\n", threadIdx.x >> 5, tw, mode, flags, ids, acc, c.A[0], c.g[0], (void*)base, (void*)c.A);
+#endif
     return tw == 0 ? 0.5 * warp_sum(acc) : 0.0;
 }
 
 template <class F, int TW>
 __device__ __forceinline__ double team_eval(const TeamCtx<F, TW>& tc, const double* pv, int mode,
                                             double* fout, double* Jout) {
-    return tc.c.P.staged ? team_eval_impl<F, TW, true>(tc, pv, mode, fout, Jout)
-                         : team_eval_impl<F, TW, false>(tc, pv, mode, fout, Jout);
+    const WarpCtx<F>& c = tc.c;
+    const int ids = c.lane | (tc.tw << 8) | (tc.bar << 16);
+    const int flags = (mode & 1) | ((pv == c.pn) ? 2 : 0) | ((c.A == c.Abuf[1]) ? 4 : 0);
+#if B200LM_EVAL_BYREF
+    (void)ids;
+    return c.P.staged ? team_eval_impl<F, TW, true>(tc, flags, fout, Jout)
+                      : team_eval_impl<F, TW, false>(tc, flags, fout, Jout);
+#else
+    const unsigned base_s = (unsigned)__cvta_generic_to_shared(c.R);
+    const unsigned stage_s = c.P.staged ? (unsigned)__cvta_generic_to_shared(c.wt) : 0u;
+    return c.P.staged ? team_eval_impl<F, TW, true>(c.P, base_s, stage_s, ids, flags, fout, Jout)
+                      : team_eval_impl<F, TW, false>(c.P, base_s, stage_s, ids, flags, fout, Jout);
+#endif
 }
 
 // leader side of fit_one's evaluator: post the command, then take part in the evaluation
@@ -508,22 +653,6 @@ struct TeamEval {
     }
 };
 
-// shared memory of the CTA: [ block weights | x, 1x1 weights | index tables | team 0 | team 1 | ... ]
-struct TeamStage {
-    int wt, x, fw, pw, ints, total;     // offsets in doubles (ints: start of the int tables), total doubles
-};
-__host__ __device__ inline TeamStage team_stage(const FitParams& P) {
-    TeamStage s;
-    s.wt = 0;
-    s.x = (P.wt2_total + 1) & ~1;
-    s.fw = s.x + P.ny * P.nx;
-    s.pw = s.fw + P.nd_fn;
-    s.ints = (s.pw + P.nd_pr + 1) & ~1;
-    const int nints = P.nblk_idx + P.nd_fn + P.nd_pr;
-    s.total = (s.ints + (nints + 1) / 2 + 1) & ~1;
-    return s;
-}
-
 template <class F, int TW>
 __global__ void __launch_bounds__(TeamLayout<F, TW>::MAX_THREADS, 1)
 fit_team_kernel(const __grid_constant__ FitParams P) {
@@ -552,34 +681,9 @@ fit_team_kernel(const __grid_constant__ FitParams P) {
         for (int i = threadIdx.x; i < P.nd_fn; i += blockDim.x) { smem[st.fw + i] = P.dfn_w[i]; si[P.nblk_idx + i] = P.dfn_idx[i]; }
         for (int i = threadIdx.x; i < P.nd_pr; i += blockDim.x) { smem[st.pw + i] = P.dpr_w[i]; si[P.nblk_idx + P.nd_fn + i] = P.dpr_idx[i]; }
         for (int i = threadIdx.x; i < P.nblk_idx; i += blockDim.x) si[i] = P.blk_idx[i];
-        c.wt = smem + st.wt;
-        tc.xs = smem + st.x; tc.fw = smem + st.fw; tc.pw = smem + st.pw;
-        tc.bidx = si; tc.fidx = si + P.nblk_idx; tc.pidx = si + P.nblk_idx + P.nd_fn;
         region = st.total;
-    } else {
-        c.wt = P.blk_wt2;
-        tc.xs = P.x; tc.fw = P.dfn_w; tc.pw = P.dpr_w;
-        tc.bidx = P.blk_idx; tc.fidx = P.dfn_idx; tc.pidx = P.dpr_idx;
     }
-    double* base = smem + region + (size_t)team * P.team_stride;
-    c.R = base;
-    c.Abuf[0] = c.R + TL::UNION;
-    c.Abuf[1] = c.Abuf[0] + NP * LDA;
-    c.A = c.Abuf[0];
-    c.L = c.Abuf[1] + NP * LDA;
-    c.p = c.L + NP * LDA;
-    c.pn = c.p + NP;
-    c.g = c.pn + NP;
-    c.sinv = c.g + NP;
-    c.dsc = c.sinv + NP;
-    c.idg = c.dsc + NP;
-    c.gbuf[0] = c.g;
-    c.gbuf[1] = c.idg + NP;
-    c.colb = c.gbuf[1] + NP;                       // column broadcast buffers of the factorisation
-    c.dvec = c.colb + 64;                          // CMD doubles: scratch (4) + command ints
-    tc.cmd = reinterpret_cast<int*>(c.dvec + 4);
-    tc.mean_s = base + TL::FIXED;
-    c.mean = tc.mean_s;
+    team_pointers<F, TW>(tc, P, smem + region + (size_t)team * P.team_stride, smem);
     __syncthreads();
     const int lane = c.lane;
 
