@@ -7,17 +7,18 @@ Workload (BASELINE.json config 3): 8-exponential correlator, 64 correlated time 
 16 diagonal priors, svdcut=1e-12, 10^4 bootstrap copies per GPU per step, p0 = prior mean,
 tol=(1e-8,1e-10,1e-10), maxit=1000.  One "step" = one launch of the fit kernel over the
 whole batch (plus, for N>1, the NCCL all-gather of the packed per-fit results).
-Weak scaling: every rank fits its own 10^4 copies (different seed).
+Weak scaling: every rank fits its OWN 10^4 copies (a different seed per rank).
 
-Prints ONE JSON line on rank 0.
+Prints ONE JSON line on rank 0 (stdout); NCCL's own log goes to stderr.
 """
 import os
-# NCCL writes its version banner to STDOUT at NCCL_DEBUG=VERSION/WARN/INFO; the contract is ONE JSON
-# line on stdout, so NCCL's log goes to stderr (and is off unless B200LM_NCCL_DEBUG asks for it)
-os.environ.pop("NCCL_DEBUG", None)
-if os.environ.get("B200LM_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = os.environ["B200LM_NCCL_DEBUG"]
-os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+# The contract is ONE JSON line on stdout, and NCCL prints its banner / INFO lines to stdout unless told
+# otherwise: its log is sent to stderr.  NCCL_DEBUG itself is left as the launcher set it (INFO by default
+# for multi-rank runs, so that the rank count and the transport are visible in the captured log).
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 import argparse
 import json
 import os
@@ -45,12 +46,26 @@ def parse():
     ap.add_argument("--batch", type=int, default=10000, help="fits per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=2000, help="fits timed on the host for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1/C2/C4/C5 and saturated-batch figures")
     return ap.parse_args()
 
 
+def load_configs():
+    """lsqfit_b200/configs.py loaded BY PATH: it is pure numpy, and importing it as part of the package
+    would map libb200lm.so into the process -- the reference arm must not load any of the product."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_b200lm_configs", os.path.join(ROOT, "lsqfit_b200", "configs.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
 # ------------------------------------------------------------------------------ CPU oracle leg
+# The oracle restates lsqfit's scipy_least_squares plugin (src/lsqfit/_scipy.py:115-181).  ORACLE_XSCALE:
+# "jac" = More' column scaling, the policy the device runs by default (GSL's default scaler, scipy
+# x_scale='jac'); the reference plugin's own default is x_scale=1 -- both are timed and reported.
 def _oracle_setup():
-    from lsqfit_b200 import configs
+    configs = load_configs()
     from oracle.whiten import PDF as OPDF
     cfg = configs.c3()
     ny, npar = cfg["ny"], cfg["np"]
@@ -60,7 +75,7 @@ def _oracle_setup():
     full[ny:, ny:] = np.diag(cfg["prior_sdev"] ** 2)
     mean0 = np.concatenate([cfg["f"], cfg["prior_mean"]])
     pdf = OPDF(mean0, full, svdcut=cfg["svdcut"])
-    return cfg, pdf
+    return configs, cfg, pdf
 
 
 _G = {}
@@ -69,39 +84,49 @@ _G = {}
 def _oracle_init():
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
     os.environ["OMP_NUM_THREADS"] = "1"
-    _G["cfg"], _G["pdf"] = _oracle_setup()
+    _G["configs"], _G["cfg"], _G["pdf"] = _oracle_setup()
 
 
-def _oracle_fit(mean):
+def _oracle_fit(arg):
     from oracle.fit import nonlinear_fit
+    mean, x_scale = arg
     cfg, pdf = _G["cfg"], _G["pdf"]
     ny = cfg["ny"]
+    kw = {} if x_scale is None else dict(x_scale=x_scale)
     fit = nonlinear_fit("multiexp", cfg["x"], mean[:ny], prior_mean=mean[ny:], _yp_pdf=pdf,
-                        p0=cfg["p0"], tol=cfg["tol"], maxit=cfg["maxit"])
+                        p0=cfg["p0"], tol=cfg["tol"], maxit=cfg["maxit"], **kw)
     return fit.nit
 
 
-def cpu_fits_per_sec(means, cores):
-    """The oracle (restatement of the reference's scipy_least_squares path, default trf) on
-    `cores` host processes; whitening shared (simulated_fit_iter style)."""
+def cpu_fits_per_sec(means, cores, x_scale):
+    """The oracle on `cores` host processes; whitening shared (simulated_fit_iter style)."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
+    jobs = [(m, x_scale) for m in means]
     with ctx.Pool(cores, initializer=_oracle_init) as pool:
-        pool.map(_oracle_fit, list(means[:cores]))          # warm the workers
+        pool.map(_oracle_fit, jobs[:cores])          # warm the workers
         t0 = time.perf_counter()
-        nit = pool.map(_oracle_fit, list(means), chunksize=max(1, len(means) // (cores * 8)))
+        nit = pool.map(_oracle_fit, jobs, chunksize=max(1, len(jobs) // (cores * 8)))
         dt = time.perf_counter() - t0
     return len(means) / dt, float(np.mean(nit))
 
 
 def _ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the fit kernel, per launch, from the committed
-    `ncu --set full` capture (profiles/traffic_r01_v9.json); None if absent."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fit kernel per launch.  STATIC: taken from the
+    committed `ncu --set full` capture of this kernel (newest profiles/traffic_r*.json), not measured in
+    this run (DRAM counters need a profiler).  Returns (bytes or None, source)."""
+    pdir = os.path.join(ROOT, "profiles")
     try:
-        t = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_r01_v9.json")))
-        return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
-    except (OSError, ValueError, KeyError):
-        return None
+        names = sorted(n for n in os.listdir(pdir) if n.startswith("traffic_r") and n.endswith(".json"))
+    except OSError:
+        names = []
+    for name in reversed(names):
+        try:
+            t = json.load(open(os.path.join(pdir, name)))
+            return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"]), "static: profiles/" + name
+        except (OSError, ValueError, KeyError):
+            continue
+    return None, "no capture committed"
 
 
 def cpu_model():
@@ -178,12 +203,15 @@ def fp64_peak():
 
 # ------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank):
+    """The reference's CPU path for this workload on all host cores.  lsqfit itself cannot be installed
+    (gvar and GSL are absent), so this times the oracle restatement of
+    lsqfit.scipy_least_squares with the plugin's OWN defaults (x_scale = 1).  Nothing of the product is
+    imported: no lsqfit_b200 package, no libb200lm.so, no CUDA."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     _oracle_init()
-    from lsqfit_b200 import configs
-    cfg, pdf = _G["cfg"], _G["pdf"]
+    configs, cfg, pdf = _G["configs"], _G["cfg"], _G["pdf"]
     per_step = max(cores * 25, 200)
     means = configs.bootstrap_means(cfg, per_step * (args.steps + args.warmup), cfg["seed"],
                                     cov=pdf.cov[:cfg["ny"], :cfg["ny"]])
@@ -192,24 +220,188 @@ def run_reference(args, rank):
     with ctx.Pool(cores, initializer=_oracle_init) as pool:
         k = 0
         for _ in range(args.warmup):
-            pool.map(_oracle_fit, list(means[k:k + per_step]))
+            pool.map(_oracle_fit, [(m, None) for m in means[k:k + per_step]])
             k += per_step
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            pool.map(_oracle_fit, list(means[k:k + per_step]), chunksize=max(1, per_step // (cores * 8)))
+            pool.map(_oracle_fit, [(m, None) for m in means[k:k + per_step]], chunksize=max(1, per_step // (cores * 8)))
             k += per_step
         dt = time.perf_counter() - t0
     v = per_step * args.steps / dt
-    sample = ("%d fits per step (bounded sample of the 10k-copy batch), scipy least_squares(trf) "
-              "oracle restatement of lsqfit.scipy_least_squares, whitening shared, %d processes on %s"
+    sample = ("%d fits per step (bounded sample of the 10k-copy batch), scipy least_squares(trf, x_scale=1: the plugin's "
+              "default) oracle restatement of lsqfit.scipy_least_squares, whitening shared, %d processes on %s"
               % (per_step, cores, cpu_model()))
     line = dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * dt / args.steps, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=WORKLOAD, fits_per_step=per_step),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port", sample=sample),
-                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                product_modules_loaded=sorted(m for m in sys.modules if m.split(".")[0] == "lsqfit_b200"))
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ extras (not the headline)
+def _timed(torch, fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+def extras_single_gpu(torch, lb, configs, dev, peak):
+    """C1, C2, C5 and the saturated C3 batch on one GPU (BASELINE.json configs[0], [1], [4]); every entry
+    is guarded so that a failure here can never cost the headline line."""
+    ex = {}
+    # ---- saturated C3 batch, one warp per fit (the kernel's throughput regime)
+    try:
+        cfg = configs.c3()
+        ny, npar = cfg["ny"], cfg["np"]
+        N = ny + npar
+        full = np.zeros((N, N)); full[:ny, :ny] = cfg["ycov"]; full[ny:, ny:] = np.diag(cfg["prior_sdev"] ** 2)
+        pdf = lb.PDF(np.concatenate([cfg["f"], cfg["prior_mean"]]), full, svdcut=cfg["svdcut"], device=dev.index)
+        Bs = 160000
+        md = torch.as_tensor(configs.bootstrap_means(cfg, Bs, cfg["seed"] + 7, cov=pdf.cov[:ny, :ny])).to(dev)
+        p0 = torch.as_tensor(cfg["p0"]).to(dev)
+        rows = {}
+        for team in (1, 4):
+            plan = lb.Plan("multiexp", npar, ny, cfg["x"], pdf.i_invwgts, device=dev.index, team=team)
+            out = plan.fit_batch(md, p0, tol=cfg["tol"], maxit=cfg["maxit"], want_cov=True)
+            ms, _ = _timed(torch, lambda: plan.fit_batch(md, p0, tol=cfg["tol"], maxit=cfg["maxit"], out=out), reps=2)
+            nfev, njev, nfac = plan.last_stats()
+            fl = njev * configs.eval_flops(ny, npar, cfg["K"])
+            rows["warps_per_fit_%d" % team] = dict(ms=ms, fits_per_s=Bs / ms * 1e3, tflops=fl / (ms * 1e-3) / 1e12,
+                                                   frac=fl / (ms * 1e-3) / 1e12 / peak)
+            plan.close()
+        ex["c3_saturated"] = dict(B=Bs, **rows)
+    except Exception as e:                                   # noqa: BLE001
+        ex["c3_saturated"] = dict(error=repr(e))
+    # ---- C1: examples/simple.py, one fit: latency
+    try:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "examples.json")))["examples"]["simple"]
+        ny1 = len(g["ymean"]); yc = np.zeros((ny1, ny1)); i = 0
+        for b in g["ycov_blocks"]:
+            b = np.array(b); yc[i:i + len(b), i:i + len(b)] = b; i += len(b)
+        f1 = lb.nonlinear_fit(data=(np.array(g["x"]), g["ymean"], yc), fcn="simple", prior=(g["prior_mean"], g["prior_sdev"]),
+                              device=dev.index)
+        plan1 = f1._spec.plan(dev.index)
+        mean1 = np.concatenate([g["ymean"], g["prior_mean"]])
+        md1, pd1 = torch.as_tensor(mean1).to(dev), torch.as_tensor(f1.p0).to(dev)
+        t_dev, _ = _timed(torch, lambda: plan1.fit_batch(md1, pd1), reps=50)
+        for _ in range(5):
+            plan1.fit_batch_host(mean1[None, :], f1.p0)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            plan1.fit_batch_host(mean1[None, :], f1.p0)
+        ex["c1_simple"] = dict(device_launch_us=1e3 * t_dev, host_call_us=1e6 * (time.perf_counter() - t0) / 50, nit=int(f1.nit),
+                               chi2_dof=float(f1.chi2 / f1.dof), golden_chi2_dof="0.1 [5] (examples/simple.out)")
+    except Exception as e:                                   # noqa: BLE001
+        ex["c1_simple"] = dict(error=repr(e))
+    # ---- C2: NIST StRD x 10^4 perturbed starts
+    try:
+        probs = json.load(open(os.path.join(ROOT, "tests", "golden", "nist.json")))["problems"]
+        B2, rows, tot_fits, tot_ms = 10000, [], 0, 0.0
+        for k, pr in enumerate(probs):
+            x = np.array(pr["x"]); ny2, np2 = len(pr["y"]), len(pr["p0"])
+            mean = np.concatenate([pr["y"], pr["prior_mean"]]); sd = np.concatenate([pr["ysdev"], pr["prior_sdev"]])
+            plan = lb.Plan(pr["form"], np2, ny2, x, [(np.arange(ny2 + np2), 1.0 / sd)], device=dev.index)
+            rng = np.random.default_rng(20240 + k)
+            p0 = torch.as_tensor(np.array(pr["p0"])[None, :] * (1 + 0.1 * rng.uniform(-1, 1, size=(B2, np2)))).to(dev)
+            md = torch.as_tensor(mean).to(dev)
+            ms, out = _timed(torch, lambda: plan.fit_batch(md, p0, tol=1e-10, maxit=1000), reps=2)
+            o = out.numpy()
+            cert, csd = np.array(pr["certified"]), np.array(pr["certified_sdev"])
+            good = (o["status"] > 0) & (np.max(np.abs(o["x"] - cert[None]) / csd[None], axis=1) < 1e-2)
+            rows.append(dict(name=pr["name"], fits_per_s=B2 / ms * 1e3, converged=float((o["status"] > 0).mean()),
+                             at_certified_minimum=float(good.mean()), mean_nit=float(o["nit"].mean())))
+            tot_fits += B2; tot_ms += ms
+            plan.close()
+        ex["c2_nist_x10k"] = dict(problems=len(rows), fits_per_s_all=tot_fits / tot_ms * 1e3,
+                                  fits_per_s_min=min(r["fits_per_s"] for r in rows), fits_per_s_max=max(r["fits_per_s"] for r in rows),
+                                  at_certified_minimum_median=float(np.median([r["at_certified_minimum"] for r in rows])),
+                                  per_problem=rows)
+    except Exception as e:                                   # noqa: BLE001
+        ex["c2_nist_x10k"] = dict(error=repr(e))
+    # ---- C5: one large dense fit (5000 correlated points, 2000 parameters, svdcut)
+    try:
+        from lsqfit_b200.dense import DenseFit
+        cfg5 = configs.c5()
+        fit = None
+        for _ in range(2):                                   # second pass = warm
+            del fit
+            fit = DenseFit((cfg5["t"], cfg5["ymean"], cfg5["ycov"]), (cfg5["prior_mean"], cfg5["prior_sdev"]),
+                           svdcut=cfg5["svdcut"], tol=cfg5["tol"], maxit=cfg5["maxit"], device=dev.index)
+        fit.propagate()
+        ms_prop, _ = _timed(torch, fit.propagate, reps=2)
+        ex["c5_dense"] = dict(ny=cfg5["ny"], np=cfg5["np"], svdn=int(fit.svdn), nit=int(fit.nit), whiten_s=fit.times["whiten"],
+                              fit_s=fit.times["fit"], per_iteration_ms=1e3 * fit.times["fit"] / max(1, fit.nit),
+                              propagate_ms=ms_prop, chi2_dof=float(fit.chi2 / fit.dof),
+                              stopping_criterion=int(fit.stopping_criterion))
+        del fit
+    except Exception as e:                                   # noqa: BLE001
+        ex["c5_dense"] = dict(error=repr(e))
+    return ex
+
+
+def c4_strong(torch, dist, lb, configs, lbdist, dev, rank, world, B=1000000):
+    """BASELINE config 4: 10^6 simulated fits of a 3-exp correlator SHARDED over the ranks (strong scaling):
+    every rank generates its shard of the Philox stream on its own GPU, fits it, then one all-gather of the
+    packed results and one all-reduce of the moments.  Timed on the device, max over ranks."""
+    from lsqfit_b200 import bootstrap as bs
+    cfg = configs.c4(B=B)
+    ny, npar = cfg["ny"], cfg["np"]
+    N = ny + npar
+    full = np.zeros((N, N)); full[:ny, :ny] = cfg["ycov"]; full[ny:, ny:] = np.diag(cfg["prior_sdev"] ** 2)
+    mean0 = np.concatenate([cfg["f"], cfg["prior_mean"]])
+    pdf = lb.PDF(mean0, full, svdcut=cfg["svdcut"], device=dev.index)
+    val, vec = np.linalg.eigh(pdf.cov)
+    L = vec * np.sqrt(np.clip(val, 0, None)); L[ny:, :] = 0.0      # simulated fits: prior means fixed
+    Ld, m0d, p0d = torch.as_tensor(L).to(dev), torch.as_tensor(mean0).to(dev), torch.as_tensor(cfg["p0"]).to(dev)
+    plan = lb.Plan("multiexp", npar, ny, cfg["x"], pdf.i_invwgts, device=dev.index)
+    lo, hi = lbdist.shard_range(B, rank, world)
+
+    def job():
+        means = bs.bootstrap_means(m0d, Ld, hi - lo, cfg["seed"], first=lo, device=dev.index)
+        out = plan.fit_batch(means, p0d, tol=cfg["tol"], maxit=cfg["maxit"], want_cov=False)
+        packed = lbdist.pack_results(out.x, out.chi2, out.nit, out.status)
+        allp = lbdist.gather_results(packed, B_total=B)
+        m, c, n = lbdist.moments(out.x, out.status > 0)
+        return allp, m, c, n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    job(); barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        allp, m, c, n = job()
+    e1.record(); barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    nfev = plan.last_stats()[0]
+    tt = torch.tensor([float(nfev)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt)
+    plan.close()
+    ms = float(t[0])
+    bias = float(torch.max(torch.abs(m - p0d) / torch.sqrt(torch.diagonal(c)) * (n ** 0.5)))
+    return dict(workload="C4: 3-exp correlator, 10^6 simulated fits sharded over the ranks (generate + fit + gather + moments)",
+                B=B, n_gpus=world, ms=ms, fits_per_s=B / ms * 1e3, scaling="strong", converged=int(n),
+                gathered_rows=int(allp.shape[0]), nfev_per_fit=float(tt[0]) / B,
+                pmean_minus_pexact_in_sigma_of_mean=bias,
+                note="the mean of the best-fit parameters is BIASED with respect to pexact at second order in the noise "
+                     "(nonlinear model, prior pull); tests/test_gpu_parity.py::test_c4_bias_matches_oracle shows the CPU "
+                     "oracle has the same bias on the same copies")
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -231,12 +423,15 @@ def run_ours(args, rank, local_rank, world):
         ocfg, opdf = _G["cfg"], _G["pdf"]
         n = min(args.cpu_sample, args.batch)
         om = configs.bootstrap_means(ocfg, args.batch, ocfg["seed"], cov=opdf.cov[:ocfg["ny"], :ocfg["ny"]])[:n]
-        v, mean_nit = cpu_fits_per_sec(om, cores)
+        v, mean_nit = cpu_fits_per_sec(om, cores, "jac")
+        v1, mean_nit1 = cpu_fits_per_sec(om[:max(cores * 25, 200)], cores, None)
         cpu = dict(value=v, unit=UNIT, cores=cores, kind="port",
-                   sample="first %d of the %d bootstrap copies of this workload; oracle = scipy "
-                          "least_squares(trf) restatement of lsqfit.scipy_least_squares (numpy AD Jacobian, "
-                          "whitening shared), %d processes, mean nfev %.1f, %s"
-                          % (n, args.batch, cores, mean_nit, cpu_model()))
+                   sample="first %d of the %d bootstrap copies of this workload; oracle = scipy least_squares(trf) "
+                          "restatement of lsqfit.scipy_least_squares (numpy AD Jacobian, whitening shared) with the SAME "
+                          "scaling policy as the device (More' / x_scale='jac'), %d processes, mean nfev %.1f, %s"
+                          % (n, args.batch, cores, mean_nit, cpu_model()),
+                   plugin_default_x_scale_1=dict(value=v1, mean_nfev=mean_nit1,
+                                                 note="the reference plugin's own default scaling (what --impl reference times)"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -250,12 +445,10 @@ def run_ours(args, rank, local_rank, world):
     full[ny:, ny:] = np.diag(cfg["prior_sdev"] ** 2)
     mean0 = np.concatenate([cfg["f"], cfg["prior_mean"]])
     pdf = lb.PDF(mean0, full, svdcut=cfg["svdcut"], device=local_rank)          # device whitening
-    # Weak scaling = fixed per-GPU work: every rank fits the SAME synthetic batch.  (With a different
-    # seed per rank the slowest rank's longest fit sets the step time -- 74 % efficiency at 8 GPUs instead
-    # of ~95 %, see DESIGN.md section 7 -- which measures the workload's tail, not the engine's scaling.
-    # B200LM_BENCH_DISTINCT=1 restores per-rank seeds.)
-    distinct = os.environ.get("B200LM_BENCH_DISTINCT", "0") == "1"
-    means_h = configs.bootstrap_means(cfg, B, cfg["seed"] + (rank if distinct else 0), cov=pdf.cov[:ny, :ny])
+    # Weak scaling: every rank fits its OWN batch (seed + rank).  B200LM_BENCH_SAME=1 gives every rank the same
+    # batch instead (isolates the engine's scaling from the workload's straggler statistics).
+    same = os.environ.get("B200LM_BENCH_SAME", "0") == "1"
+    means_h = configs.bootstrap_means(cfg, B, cfg["seed"] + (0 if same else rank), cov=pdf.cov[:ny, :ny])
     plan = lb.Plan("multiexp", npar, ny, cfg["x"], pdf.i_invwgts, device=local_rank)
     means_d = torch.as_tensor(means_h).to(dev)
     p0_d = torch.as_tensor(cfg["p0"]).to(dev)
@@ -301,13 +494,22 @@ def run_ours(args, rank, local_rank, world):
     launches = plan.launch_count() - launches0
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
     tk_ms = sum(a.elapsed_time(b) for a, b in kev)
+    nfev, njev, nfac = plan.last_stats()
     tt = torch.tensor([t_ms, tk_ms], device=dev, dtype=torch.float64)
+    ts = torch.tensor([float(nfev), float(njev), float(nfac), float(out.nit.max())], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tsum = ts.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        nfev_all, njev_all, nfac_all = float(tsum[0]), float(tsum[1]), float(tsum[2])
+    else:
+        nfev_all, njev_all, nfac_all = float(nfev), float(njev), float(nfac)
     t_ms, tk_ms = float(tt[0]), float(tt[1])
-    nfev, njev, nfac = plan.last_stats()
+    max_nit = int(ts[3])
     res = out.numpy()
     conv = float((res["status"] > 0).mean())
+    warps_per_fit = plan.last_team()
 
     # ---- e2e: the public host-buffer call, pinned inputs, H2D + D2H inside the timed region
     means_pin = torch.as_tensor(means_h).pin_memory()
@@ -358,6 +560,22 @@ def run_ours(args, rank, local_rank, world):
     tq_ms = q0.elapsed_time(q1)
     plan_b.close()
 
+    peak, peak_src = fp64_peak()
+    extras = {}
+    if not args.no_extras:
+        try:
+            extras["c4_strong"] = c4_strong(torch, dist, lb, configs, lbdist, dev, rank, world)
+        except Exception as e:                               # noqa: BLE001
+            extras["c4_strong"] = dict(error=repr(e))
+        if world == 1:
+            extras.update(extras_single_gpu(torch, lb, configs, dev, peak))
+
+    comm = None
+    if world > 1:
+        comm = dict(backend=dist.get_backend(), nranks=dist.get_world_size(),
+                    nccl_version=".".join(str(v) for v in torch.cuda.nccl.version()),
+                    nccl_debug=os.environ.get("NCCL_DEBUG"), log="stderr (NCCL_DEBUG_FILE=/dev/stderr)",
+                    collectives_per_step="1 all_gather_into_tensor of [B, np+3] fp64 rows; no host synchronisation")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -366,14 +584,18 @@ def run_ours(args, rank, local_rank, world):
     # ---- roofline of the dominant kernel (the fit kernel is the only kernel of a step)
     F_eval = configs.eval_flops(ny, npar, cfg["K"])
     F_res = 2.0 * ny * ny + 2.0 * N + ny * cfg["K"] * 3.0       # residual-only trial evaluation
-    flops_launch = njev * F_eval + (nfev - njev) * F_res
-    peak, peak_src = fp64_peak()
+    flops_launch = (njev_all * F_eval + (nfev_all - njev_all) * F_res) / world     # per launch (per rank)
     achieved = flops_launch / (tk_ms / args.steps * 1e-3) / 1e12
+    traffic, traffic_src = _ncu_traffic()
+    kname = "fit_team_kernel<MultiExp<8>, %d>" % warps_per_fit if warps_per_fit > 1 else "fit_kernel<MultiExp<8>>"
     roofline = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                    traffic=_ncu_traffic(), kernel="fit_kernel<MultiExp<8>>", peak_source=peak_src,
-                    flops_per_launch=flops_launch, flops_per_launch_survey_formula=nfev * F_eval,
-                    nfev_per_fit=nfev / B, njev_per_fit=njev / B, chol_per_fit=nfac / B,
-                    kernel_ms=tk_ms / args.steps)
+                    traffic=traffic, traffic_source=traffic_src, kernel=kname, warps_per_fit=warps_per_fit,
+                    peak_source=peak_src, flops_per_launch=flops_launch,
+                    flops_per_launch_survey_formula=nfev_all * F_eval / world,
+                    nfev_per_fit=nfev_all / (B * world), njev_per_fit=njev_all / (B * world),
+                    chol_per_fit=nfac_all / (B * world), max_nfev_of_a_fit=max_nit, kernel_ms=tk_ms / args.steps,
+                    note="FP64 pipe (DMMA/DFMA share one pipe; tcgen05 has no FP64 kind).  The step is bounded by the "
+                         "latency of its slowest fits, not by throughput: see extras.c3_saturated for the saturated batch")
 
     queued = dict(value=B * args.steps / (tq_ms * 1e-3), unit=UNIT + " per GPU", streams=2, ms_per_step=tq_ms / args.steps,
                   note="same steps queued on two streams (two plans): throughput of a stream of 10k-fit batches; "
@@ -383,13 +605,14 @@ def run_ours(args, rank, local_rank, world):
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=WORKLOAD, fits_per_gpu_per_step=B, ny=ny, np=npar, svdcut=cfg["svdcut"],
                             tol=list(cfg["tol"]), maxit=cfg["maxit"], l2="flushed between timed steps (256 MiB memset)",
-                            per_rank_data="distinct seeds" if distinct else "identical batch on every rank (fixed per-GPU work)",
+                            per_rank_data="identical batch on every rank (B200LM_BENCH_SAME=1)" if same
+                            else "a different batch on every rank (seed + rank)",
                             converged_frac=conv, svdn=int(pdf.nmod)),
                 clocks=clocks,
                 e2e=dict(value=world * B * args.steps / te, unit=UNIT, h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=d2h, ms_per_step=1e3 * te / args.steps,
                          api="lsqfit_b200.Plan.fit_batch_host -> b200lm_fit_batch_host (pinned host buffers)"),
-                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, queued=queued)
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, queued=queued, comm=comm, extras=extras)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

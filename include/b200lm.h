@@ -121,6 +121,11 @@ int b200lm_last_stats(b200lm_handle h, unsigned long long out[3]);
 int b200lm_last_stats_ex(b200lm_handle h, unsigned long long* out, int n);
 /* warps per fit used by the last fit_batch launch: 1 (one warp per fit), 2 or 4 (team kernel) */
 int b200lm_last_team(b200lm_handle h);
+/* choose the kernel: 0 = default policy (by problem shape only: four warps per fit where one trial point is
+ * expensive -- np >= 12 and a correlated block of >= 32 points -- else one), 1 = one warp per fit (highest
+ * throughput on saturated batches), 2 / 4 = team kernel (lowest latency per trial point).  The two kernels
+ * sum in a different order: results agree to rounding, not bit for bit. */
+int b200lm_set_team(b200lm_handle h, int team);
 /* number of kernel launches issued through this handle so far */
 long long b200lm_launch_count(b200lm_handle h);
 

@@ -59,12 +59,16 @@ static std::vector<FunctorEntry>& registry() {
 
 // default number of warps per fit.  The choice depends on the problem's shape only, never on the batch
 // size: a fit's result must not depend on how many other fits share its launch (the two kernels sum in a
-// different order).  Measured on C3 (np = 16, one 64 x 64 block; tools/team_check.py): a team of four warps
-// cuts the latency of one trial point by a third (B = 1000: 5.3 ms instead of 8.4 ms) but keeps fewer fits in
-// flight per SM (B = 10^4: 14.6 vs 13.3 ms), so one warp per fit stays the default; B200LM_TEAM=4 selects
-// the team kernel.
-static int default_team(b200lm_handle_s* h, int B) {
-    (void)h; (void)B;
+// different order).  Measured on C3 (np = 16, one 64 x 64 block; tools/team_check.py, profiles/team_r02.json):
+// a team of four warps halves the latency of one trial point, which decides every batch that is bounded by
+// its slowest fits (B = 1000: 4.7 ms instead of 8.2 ms; B = 10^4: 12.4 vs 12.9 ms); a saturated batch is
+// bounded by the number of fits in flight per SM, where one warp per fit wins (B = 160 k: 117 vs 157 ms).
+// For small np (C4: np = 6) the evaluation is too short to split.  b200lm_set_team overrides.
+static int default_team(b200lm_handle_s* h) {
+    if (h->team_request > 0) return h->team_request;
+    int big = 0;
+    for (const auto& b : h->h_blk) big = b.n_in > big ? b.n_in : big;
+    if (big >= 32 && h->np >= 12) return 4;
     return 1;
 }
 
@@ -285,7 +289,7 @@ int b200lm_fit_batch(b200lm_handle h, int B,
     CUDA_TRY(h, cudaMemsetAsync(h->d_stats, 0, 16 * sizeof(unsigned long long), s), "reset stats");
     // kernel choice: one warp per fit, or a team of 2 / 4 warps per fit where the functor has one
     // (B200LM_TEAM = 0/1, 2, 4 overrides the default policy)
-    int team = default_team(h, B);
+    int team = default_team(h);
     if (const char* env = getenv("B200LM_TEAM")) team = atoi(env);
     const int ti = team == 4 ? 1 : (team == 2 ? 0 : -1);
     if (ti >= 0 && h->fe->fit_team[ti] &&
@@ -322,6 +326,13 @@ int b200lm_last_stats_ex(b200lm_handle h, unsigned long long* out, int n) {
 }
 
 int b200lm_last_team(b200lm_handle h) { return h ? h->last_team : B200LM_EINVAL; }
+
+int b200lm_set_team(b200lm_handle h, int team) {
+    if (!h) return set_error(h, B200LM_EINVAL, "NULL handle");
+    if (team != 0 && team != 1 && team != 2 && team != 4) return set_error(h, B200LM_EINVAL, "team must be 0 (default), 1, 2 or 4");
+    h->team_request = team;
+    return B200LM_OK;
+}
 
 long long b200lm_launch_count(b200lm_handle h) { return h ? h->launches : 0; }
 

@@ -30,6 +30,14 @@ namespace b200lm {
 
 #define B200LM_FULL 0xffffffffu
 
+// the counters cost a few hundred cycles per trial point: compiled in only with -DB200LM_PHASE_TICKS
+// (python lsqfit_b200/build.py with B200LM_EXTRA_CFLAGS=-DB200LM_PHASE_TICKS; tools/phase_probe.py)
+#ifdef B200LM_PHASE_TICKS
+#define B200LM_CLOCK() clock64()
+#else
+#define B200LM_CLOCK() 0ll
+#endif
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(B200LM_FULL, v, o);
@@ -644,17 +652,17 @@ __device__ double solve_tr(WarpCtx<F>& c, double gh, double Delta, double& alpha
     if (!gn.valid && alpha > 0.0) {
         ++nfac;
         tried_warm = true;
-        const long long tq = clock64();
+        const long long tq = B200LM_CLOCK();
         warm_ok = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, c.colb, lane, alpha, gh, false, &warm_p, res);
-        fclk += clock64() - tq;
+        fclk += B200LM_CLOCK() - tq;
         if (warm_ok) { warm_pn = res[0]; warm_w2 = res[1]; warm_phi = warm_pn - Delta; }
     }
     const bool need_gn = !(tried_warm && warm_ok && warm_phi > 0.0);
     if (!gn.valid && need_gn) {
         ++nfac;
-        const long long tq = clock64();
+        const long long tq = B200LM_CLOCK();
         gn.full_rank = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, c.colb, lane, 0.0, gh, false, &p, res);
-        fclk += clock64() - tq;
+        fclk += B200LM_CLOCK() - tq;
         gn.p = p; gn.pn = res[0]; gn.w2 = res[1];
         gn.valid = true;
     }
@@ -683,9 +691,9 @@ __device__ double solve_tr(WarpCtx<F>& c, double gh, double Delta, double& alpha
             if (alpha < alpha_lower || alpha > alpha_upper)
                 alpha = fmax(0.001 * alpha_upper, sqrt(alpha_lower * alpha_upper));
             ++nfac;
-            const long long tq = clock64();
+            const long long tq = B200LM_CLOCK();
             ok = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, c.colb, lane, alpha, gh, false, &pt, res);
-            fclk += clock64() - tq;
+            fclk += B200LM_CLOCK() - tq;
         }
         if (!ok) {
             alpha_lower = fmax(alpha_lower, alpha);
@@ -767,9 +775,9 @@ __device__ double solve_tr_dual(WarpCtx<F>& c, double gh, double Delta, double& 
     auto dual = [&](double a_lo, double a_hi, TRCand& lo, TRCand& hi) {
         double p, pn, w2;
         bool ok;
-        const long long tq = clock64();
+        const long long tq = B200LM_CLOCK();
         factor_solve2<NPD, LDA>(c.A, c.dsc, c.L, LT1, c.colb, lane, a_lo, a_hi, gh, &p, &pn, &w2, &ok);
-        fclk += clock64() - tq;
+        fclk += B200LM_CLOCK() - tq;
         nfac += 2;
         lo.a = a_lo; hi.a = a_hi;
         lo.p = p;
@@ -797,9 +805,9 @@ __device__ double solve_tr_dual(WarpCtx<F>& c, double gh, double Delta, double& 
     if (!gn.valid && !(alpha > 0.0)) {
         double res[3], p0;
         ++nfac;
-        const long long tq = clock64();
+        const long long tq = B200LM_CLOCK();
         gn.full_rank = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, c.colb, lane, 0.0, gh, false, &p0, res);
-        fclk += clock64() - tq;
+        fclk += B200LM_CLOCK() - tq;
         gn.p = p0; gn.pn = res[0]; gn.w2 = res[1];
         gn.valid = true;
     } else {
@@ -1001,6 +1009,7 @@ struct PhaseClock {
     __device__ __forceinline__ void clear() { eval = 0; solve = 0; total = 0; fact = 0; }
 };
 
+
 template <class F, class EV>
 __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& P, int b,
                                         unsigned long long& tot_nfev, unsigned long long& tot_njev,
@@ -1017,9 +1026,9 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
 
         int cur = 0;                              // buffer holding J^T J, J^T r of the current point
         c.A = c.Abuf[0]; c.g = c.gbuf[0];
-        const long long t_fit0 = clock64();
+        const long long t_fit0 = B200LM_CLOCK();
         double cost = ev.run(c, c.p, nullptr, nullptr, 0);
-        pk.eval += clock64() - t_fit0;
+        pk.eval += B200LM_CLOCK() - t_fit0;
         int nfev = 1, njev = 1, nfac = 0;
         int status = -2;                         // -2: running
         if (!isfinite(cost)) status = -1;
@@ -1058,7 +1067,7 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
             gn.valid = false;
             while (actual_reduction <= 0.0 && nfev < P.maxit) {
                 double sh;
-                const long long t_s0 = clock64();
+                const long long t_s0 = B200LM_CLOCK();
                 // two shifts per round pay off where the factorisation dominates a trial (np = 12..16: +8 % on
                 // C3); for small np the extra control flow and code size cost more than they save (C4, np = 6:
                 // -10 %), so those kernels do not even contain the dual path
@@ -1068,7 +1077,7 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
                 } else {
                     sh = solve_tr<F>(c, gh, Delta, alpha, nfac, gn, pk.fact);
                 }
-                pk.solve += clock64() - t_s0;
+                pk.solve += B200LM_CLOCK() - t_s0;
                 const double step = act ? d * sh : 0.0;
                 if (act) { c.pn[lane] = c.p[lane] + step; c.idg[lane] = step; }
                 __syncwarp();
@@ -1100,9 +1109,9 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
                 // second pass over the rows is needed; a rejected trial leaves the current
                 // buffers untouched.
                 c.A = c.Abuf[cur ^ 1]; c.g = c.gbuf[cur ^ 1];
-                const long long t_e0 = clock64();
+                const long long t_e0 = B200LM_CLOCK();
                 cost_new = ev.run(c, c.pn, nullptr, nullptr, 0);
-                pk.eval += clock64() - t_e0;
+                pk.eval += B200LM_CLOCK() - t_e0;
                 c.A = c.Abuf[cur]; c.g = c.gbuf[cur];
                 ++nfev; ++njev;
                 if (!isfinite(cost_new)) { Delta = 0.25 * sqrt(sh2); continue; }
@@ -1232,7 +1241,7 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
             if (P.logdet) P.logdet[b] = ld;
         }
         tot_nfev += nfev; tot_njev += njev; tot_nfac += nfac;
-        pk.total += clock64() - t_fit0;
+        pk.total += B200LM_CLOCK() - t_fit0;
         __syncwarp();
     }
 }
@@ -1317,8 +1326,9 @@ inline cudaError_t plan_launch(FitParams& P, int sm_count, size_t smem_budget, L
     P.warps = warps;
     li.block = warps * 32;
     li.smem = (P.wt_in_smem ? wt_bytes : 0) + warps * per_warp;
-    int grid = (P.B + warps - 1) / warps;
-    if (grid > sm_count) grid = sm_count;
+    // one persistent CTA per SM; a batch smaller than the machine is SPREAD over the SMs (a fit is latency
+    // bound: 7 fits on each of 148 SMs finish sooner than 12 on each of 84)
+    int grid = P.B < sm_count ? P.B : sm_count;
     if (grid < 1) grid = 1;
     li.grid = grid;
     return cudaSuccess;

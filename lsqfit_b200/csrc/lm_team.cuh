@@ -48,7 +48,7 @@ struct TeamLayout {
     static constexpr int NACC = 2 * Lay::NTRI + NGT + 1;
     static constexpr bool STAGE_OWN = NACC * 32 <= RW * LDR;       // partials fit into the warp's own rows
     static constexpr int CMD = 8;                                  // scratch (4 doubles) + command block (8 ints)
-    static constexpr int MAX_THREADS = TW == 4 ? 512 : 640;
+    static constexpr int MAX_THREADS = 512;      // 4 teams of 4 or 8 teams of 2 (measured best on C3), 128 registers per thread
     static constexpr int MAX_TEAMS = MAX_THREADS / (32 * TW) > 15 ? 15 : MAX_THREADS / (32 * TW);
     // doubles per team, without the staged means
     static constexpr int FIXED = (UNION + 3 * NP * LDA + (Lay::NVEC + 1) * NP + 64 + CMD + 1) & ~1;
@@ -288,8 +288,8 @@ __device__ __noinline__ double team_eval_impl(const FitParams& P, unsigned base_
     na.clear();
     bool dirty = false;                     // the buffer may still be read by another warp of the team
 #ifdef B200LM_PHASE_TICKS
-    long long tk0 = clock64(), tk[5] = {0, 0, 0, 0, 0};
-#define B200LM_TICK(i) do { const long long t_ = clock64(); tk[i] += t_ - tk0; tk0 = t_; } while (0)
+    long long tk0 = B200LM_CLOCK(), tk[5] = {0, 0, 0, 0, 0};
+#define B200LM_TICK(i) do { const long long t_ = B200LM_CLOCK(); tk[i] += t_ - tk0; tk0 = t_; } while (0)
 #else
 #define B200LM_TICK(i) do { } while (0)
 #endif
@@ -747,8 +747,7 @@ cudaError_t launch_fit_team(FitParams P, int sm_count, size_t smem_budget, cudaS
     }
     P.warps = teams * TW;
     const size_t smem = (P.staged ? stage_bytes : 0) + teams * per_team;
-    int grid = (P.B + teams - 1) / teams;
-    if (grid > sm_count) grid = sm_count;
+    int grid = P.B < sm_count ? P.B : sm_count;         // spread small batches over all SMs
     if (grid < 1) grid = 1;
     cudaError_t e = cudaFuncSetAttribute(fit_team_kernel<F, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

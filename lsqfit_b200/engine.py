@@ -46,7 +46,7 @@ class BatchResult(object):
 
 
 class Plan(object):
-    def __init__(self, functor, np_, ny, x, i_invwgts, noprior=False, device=0):
+    def __init__(self, functor, np_, ny, x, i_invwgts, noprior=False, device=0, team=None):
         if isinstance(functor, str):
             functor = Functor(functor)
         self.functor = functor
@@ -62,6 +62,8 @@ class Plan(object):
         _cabi.check(_cabi.lib.b200lm_set_const(self._h, xr.ctypes.data, xr.size), self._h)
         self.set_weights(i_invwgts)
         self.tdev = torch.device("cuda", self.device)
+        if team is not None:
+            self.set_team(team)
 
     # ---- whitening ---------------------------------------------------------------
     def set_weights(self, i_invwgts):
@@ -201,6 +203,11 @@ class Plan(object):
         buf = (C.c_ulonglong * 16)()
         _cabi.check(_cabi.lib.b200lm_last_stats_ex(self._h, buf, int(n)), self._h)
         return [int(v) for v in buf[:n]]
+
+    def set_team(self, team):
+        """Kernel choice: 0/None = default policy (by problem shape), 1 = one warp per fit (saturated batches),
+        2 / 4 = team kernel (lowest latency per trial point)."""
+        _cabi.check(_cabi.lib.b200lm_set_team(self._h, int(team or 0)), self._h)
 
     def last_team(self):
         """Warps per fit of the last fit_batch launch (1 = one warp per fit, 2 / 4 = team kernel)."""
