@@ -69,3 +69,102 @@ Y_NOERR_OUT = {      # examples/y-noerr.out: chi2/dof, dof, Q, logGBF, svdcut/n,
     4: ("0.21", 9, "0.99", "83.212", 3, ["0.4009(10)", "0.424(22)", "0.469(61)", "0.426(94)"],
         ["0.90036(44)", "1.819(19)", "2.83(11)", "3.83(15)"]),
 }
+
+
+# ------------------------------------------------------------------------------------------------
+# Oracle fits in a process pool (spawned: the parent may hold a CUDA context).  Every worker rebuilds the
+# problem from the same seeded recipe, so inputs are identical to the device's.
+# ------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _load_configs():
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_b200lm_configs", os.path.join(root, "lsqfit_b200", "configs.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def correlator_problem(K, svdcut=1e-12):
+    """(cfg, oracle PDF) of the C3 / C4 lattice with K exponentials (lsqfit_b200/configs.py::correlator)."""
+    from oracle.whiten import PDF as OPDF
+    cfg = _load_configs().correlator(K)
+    ny, npar = cfg["ny"], cfg["np"]
+    N = ny + npar
+    full = np.zeros((N, N))
+    full[:ny, :ny] = cfg["ycov"]
+    full[ny:, ny:] = np.diag(cfg["prior_sdev"] ** 2)
+    pdf = OPDF(np.concatenate([cfg["f"], cfg["prior_mean"]]), full, svdcut=svdcut)
+    return cfg, pdf
+
+
+def _corr_init(K):
+    import os
+    import warnings
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["OMP_NUM_THREADS"] = "1"
+    warnings.simplefilter("ignore")
+    _W["cfg"], _W["pdf"] = correlator_problem(K)
+
+
+def _corr_job(arg):
+    """One oracle fit of a correlator copy: arg = (mean, p0, tol, maxit, refine)."""
+    from oracle.fit import nonlinear_fit
+    mean, p0, tol, maxit, refine = arg
+    cfg, pdf = _W["cfg"], _W["pdf"]
+    ny = cfg["ny"]
+    fo = nonlinear_fit("multiexp", cfg["x"], mean[:ny], prior_mean=mean[ny:], _yp_pdf=pdf, p0=p0, tol=tol,
+                       maxit=maxit, x_scale="jac")
+    out = dict(x=fo.pmean, cov=fo.cov, chi2=fo.chi2, nit=fo.nit, crit=fo.stopping_criterion)
+    if refine and fo.stopping_criterion != 0:
+        xe, fe, Je, cove = exact_minimum(fo, iters=3000)
+        # undamped Gauss-Newton only converges from a point that is already close: keep the refined point when it
+        # is finite and within 1e-3 sdev of where the reference's solver stopped, otherwise the copy is skipped
+        gap = np.max(np.abs(fo.pmean - xe) / np.sqrt(np.abs(np.diag(cove)))) if np.all(np.isfinite(xe)) else np.inf
+        if np.isfinite(gap) and gap <= 1e-3:
+            # how converged the refinement itself is: one more Gauss-Newton step, in sdev
+            last = np.max(np.abs(np.linalg.lstsq(Je, -fe, rcond=None)[0]) / np.sqrt(np.diag(cove)))
+            out.update(xe=xe, cove=cove, chi2e=float(fe @ fe), logdete=float(np.linalg.slogdet(Je.T @ Je)[1]),
+                       refine_last_step=float(last))
+    return out
+
+
+def oracle_correlator_fits(K, means, p0, tol, maxit=1000, refine=False, nproc=None):
+    import multiprocessing as mp
+    import os
+    nproc = nproc or min(os.cpu_count() or 1, 32)
+    jobs = [(m, p0, tol, maxit, refine) for m in means]
+    with mp.get_context("spawn").Pool(nproc, initializer=_corr_init, initargs=(K,)) as pool:
+        return pool.map(_corr_job, jobs, chunksize=max(1, len(jobs) // (nproc * 8)))
+
+
+def _nist_init():
+    import json
+    import os
+    import warnings
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    warnings.simplefilter("ignore")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "nist.json")) as f:
+        _W["nist"] = json.load(f)["problems"]
+
+
+def _nist_job(arg):
+    from oracle.fit import nonlinear_fit
+    k, p0, tol, maxit = arg
+    pr = _W["nist"][k]
+    fo = nonlinear_fit(pr["form"], np.array(pr["x"]), pr["y"], pr["ysdev"], prior_mean=pr["prior_mean"],
+                       prior_cov=pr["prior_sdev"], p0=p0, tol=tol, maxit=maxit, x_scale="jac")
+    return dict(x=fo.pmean, chi2=fo.chi2, nit=fo.nit, crit=fo.stopping_criterion, sd=fo.psdev)
+
+
+def oracle_nist_fits(jobs, nproc=None):
+    """jobs = [(problem index, p0, tol, maxit)]"""
+    import multiprocessing as mp
+    import os
+    nproc = nproc or min(os.cpu_count() or 1, 32)
+    with mp.get_context("spawn").Pool(nproc, initializer=_nist_init) as pool:
+        return pool.map(_nist_job, jobs, chunksize=max(1, len(jobs) // (nproc * 8)))
