@@ -26,13 +26,35 @@ class _ChivProxy(object):
 
 
 def _find_functor(flatfcn):
+    """(functor, x, pperm) behind the reference's flatfcn (a functools.partial whose keywords hold fcn, x and the
+    parameter / data buffers, src/lsqfit/__init__.py:1997-2012), or (None, None, None).  A MultiFitter closure
+    (``_multifitfcn``, _extras.py:1816-1829) whose models are all device-backed maps onto one composite functor."""
+    from .multifit import composite
     f = flatfcn
     while isinstance(f, functools.partial):
         kw = f.keywords or {}
-        if isinstance(kw.get("fcn"), Functor):
-            return kw["fcn"], kw.get("x", False)
+        fcn = kw.get("fcn")
+        if isinstance(fcn, Functor):
+            return fcn, kw.get("x", False), None
+        if hasattr(fcn, "flatmodels") and "po" in kw and "yo" in kw:
+            c = composite(fcn, kw["po"], kw["yo"])
+            if c is not None:
+                return c
         f = f.func
-    return None, None
+    return None, None, None
+
+
+def _prior_size(prior):
+    """number of prior entries: a GVar array / BufferDict (``.size`` / ``.flat``), or the (mean, cov) pair of the
+    array-form test double"""
+    if isinstance(prior, tuple):
+        m = prior[0]
+        if isinstance(m, dict):
+            return int(sum(np.size(v) for v in m.values()))
+        return int(np.size(m))
+    if hasattr(prior, "size"):
+        return int(prior.size)
+    return int(np.size(getattr(prior, "flat", prior)[:]))
 
 
 def install(lsqfit):
@@ -42,16 +64,16 @@ def install(lsqfit):
 
     def _build_chiv_chivw(yp_pdf, fcn, prior):
         cv, cvw = reference_build(yp_pdf=yp_pdf, fcn=fcn, prior=prior)
-        functor, x = _find_functor(fcn)
+        functor, x, pperm = _find_functor(fcn)
         if functor is None:
             return cv, cvw                      # ordinary Python fcn: CPU fitters only
         noprior = prior is None
         N = len(yp_pdf.mean)
-        npar = 0 if noprior else int(np.size(getattr(prior, "flat", prior)[:]))
+        npar = 0 if noprior else _prior_size(prior)
         ny = N - npar
         if noprior:
             npar = None                         # taken from p0 by the fitter
-        spec = ChivSpec(functor, x, yp_pdf, noprior, ny, npar if npar is not None else -1)
+        spec = ChivSpec(functor, x, yp_pdf, noprior, ny, npar if npar is not None else -1, pperm=pperm)
         return _ChivProxy(cv, spec), cvw
 
     class b200_lm_plugin(b200_lm):

@@ -53,6 +53,7 @@ static std::vector<FunctorEntry>& registry() {
         e = registry_nist_a(&n);   r.insert(r.end(), e, e + n);
         e = registry_nist_b(&n);   r.insert(r.end(), e, e + n);
         e = registry_misc(&n);     r.insert(r.end(), e, e + n);
+        e = registry_misc_b(&n);   r.insert(r.end(), e, e + n);
     }
     return r;
 }

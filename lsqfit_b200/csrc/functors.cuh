@@ -31,7 +31,7 @@ namespace b200lm {
 // family ids (stable ABI; mirrored in lsqfit_b200/functors.py)
 enum FunctorFamily : int {
     F_MULTIEXP = 0, F_MULTIEXP_DE = 1, F_SIMPLE = 2, F_OFFSET_EXP = 3, F_POLY = 4,
-    F_EXP_POLY = 5, F_XERR_LOGISTIC = 6, F_GATHER = 7,
+    F_EXP_POLY = 5, F_XERR_LOGISTIC = 6, F_GATHER = 7, F_MULTIEXP_SHARED2 = 8, F_MULTIEXP_SHARED3 = 9,
     F_MISRA1A = 10, F_CHWIRUT = 11, F_LANCZOS = 12, F_GAUSS = 13, F_DANWOOD = 14,
     F_MISRA1B = 15, F_MISRA1C = 16, F_MISRA1D = 17, F_KIRBY2 = 18, F_HAHN1 = 19,
     F_NELSON = 20, F_MGH17 = 21, F_ROSZMAN1 = 22, F_ENSO = 23, F_MGH09 = 24,
@@ -123,6 +123,42 @@ struct MultiExp {
 
 // number of lanes this functor can spread one row's value_grad over (value_grad_part); primary template: lm_kernel.cuh
 template <int K> struct SplitOf<MultiExp<K>> { static constexpr int value = K >= 2 ? 2 : 1; };
+
+// M data sets that share their energies: set m is sum_k a^(m)_k exp(-E_k t); params [a^(0)(K), ..., a^(M-1)(K), E(K)],
+// x row = (t, m).  The composite model of a simultaneous (lsqfit.MultiFitter) fit of several correlators, whose
+// fit function is a Python closure over per-data-set models in the reference (src/lsqfit/_extras.py:1816-1829).
+template <int K, int M>
+struct MultiExpShared {
+    static constexpr int NP = (M + 1) * K;
+    static constexpr int NX = 2;
+    __device__ __forceinline__ static double value(const double* __restrict__ x, int, const double* p) {
+        const double t = x[0];
+        const int m = (int)x[1];
+        double f = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) f = fma(p[m * K + k], ::exp(-p[M * K + k] * t), f);
+        return f;
+    }
+    template <class G>
+    __device__ __forceinline__ static double value_grad(const double* __restrict__ x, int,
+                                                        const double* p, double w, G g) {
+        const double t = x[0];
+        const int m = (int)x[1];
+        const double wt = -w * t;
+#pragma unroll
+        for (int j = 0; j < M * K; ++j) g[j] = 0.0;
+        double f = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+            const double e = ::exp(-p[M * K + k] * t);
+            const double a = p[m * K + k];
+            g[m * K + k] = w * e;
+            g[M * K + k] = wt * (a * e);
+            f = fma(a, e, f);
+        }
+        return f;
+    }
+};
 
 // E_k = dE_0 + ... + dE_k ; params [a_0..a_K-1, dE_0..dE_K-1]
 template <int K>

@@ -1,0 +1,21 @@
+// Kernel instantiations: larger polynomials (tests/test_lsqfit.py:878-880 fits 25 coefficients) and the
+// shared-energy composite models of simultaneous (MultiFitter) correlator fits.
+#define B200LM_DEFINE_ENTRIES
+#include "registry.h"
+namespace b200lm {
+static const FunctorEntry kEntries[] = {
+    B200LM_ENTRY(F_POLY, "poly", Poly<8>),
+    B200LM_ENTRY(F_POLY, "poly", Poly<10>),
+    B200LM_ENTRY(F_POLY, "poly", Poly<12>),
+    B200LM_ENTRY(F_POLY, "poly", Poly<16>),
+    B200LM_ENTRY(F_POLY, "poly", Poly<20>),
+    B200LM_ENTRY(F_POLY, "poly", Poly<25>),
+    B200LM_ENTRY(F_MULTIEXP_SHARED2, "multiexp_shared2", MultiExpShared<1, 2>),
+    B200LM_ENTRY(F_MULTIEXP_SHARED2, "multiexp_shared2", MultiExpShared<2, 2>),
+    B200LM_ENTRY(F_MULTIEXP_SHARED2, "multiexp_shared2", MultiExpShared<3, 2>),
+    B200LM_ENTRY(F_MULTIEXP_SHARED2, "multiexp_shared2", MultiExpShared<4, 2>),
+    B200LM_ENTRY(F_MULTIEXP_SHARED3, "multiexp_shared3", MultiExpShared<2, 3>),
+    B200LM_ENTRY(F_MULTIEXP_SHARED3, "multiexp_shared3", MultiExpShared<3, 3>),
+};
+const FunctorEntry* registry_misc_b(int* n) { *n = sizeof(kEntries) / sizeof(kEntries[0]); return kEntries; }
+}  // namespace b200lm

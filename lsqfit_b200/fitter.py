@@ -19,22 +19,107 @@ import numpy as np
 from .engine import Plan, STOPPING_CRITERION, normalize_tol
 
 
+class PlanCache(object):
+    """Plans shared between fits that differ only in their means.
+
+    The reference's iterators construct one ``nonlinear_fit`` per bootstrap copy (src/lsqfit/__init__.py:1612-1624)
+    and each of them rebuilds chiv -- but model, x and whitening are the same for every copy, only the means move.
+    A plan (device handle, uploaded x and weights, workspaces, stream) is therefore keyed by a digest of
+    (functor, np, ny, x, i_invwgts, noprior, device): a copy then costs one launch, not a ``b200lm_create``."""
+
+    def __init__(self, capacity=16):
+        import collections
+        self.capacity = int(capacity)
+        self.plans = collections.OrderedDict()
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def key(functor, np_, ny, x, i_invwgts, noprior, device):
+        import hashlib
+        h = hashlib.blake2b(digest_size=16)
+        h.update(("%s|%d|%d|%d|%d|%d" % (functor.name, functor.family, int(np_), int(ny), int(bool(noprior)), int(device))).encode())
+        h.update(np.ascontiguousarray(functor.xrows(x, int(ny)), dtype=np.float64).tobytes())
+        for idx, w in i_invwgts:
+            h.update(np.ascontiguousarray(idx, dtype=np.int64).tobytes())
+            h.update(np.ascontiguousarray(w, dtype=np.float64).tobytes())
+        return h.hexdigest()
+
+    def get(self, functor, np_, ny, x, i_invwgts, noprior, device):
+        k = self.key(functor, np_, ny, x, i_invwgts, noprior, device)
+        plan = self.plans.get(k)
+        if plan is not None:
+            self.hits += 1
+            self.plans.move_to_end(k)
+            return plan
+        self.misses += 1
+        plan = Plan(functor, np_, ny, x, i_invwgts, noprior=noprior, device=device)
+        self.plans[k] = plan
+        while len(self.plans) > self.capacity:
+            _, old = self.plans.popitem(last=False)
+            old.close()
+        return plan
+
+    def clear(self):
+        for p in self.plans.values():
+            p.close()
+        self.plans.clear()
+        self.hits = self.misses = 0
+
+
+PLAN_CACHE = PlanCache()
+
+
 class ChivSpec(object):
     """Everything the device needs to evaluate chiv: functor, x, whitening, means."""
 
-    def __init__(self, functor, x, pdf, noprior, ny, np_):
+    def __init__(self, functor, x, pdf, noprior, ny, np_, pperm=None):
         self.functor, self.x, self.pdf, self.noprior = functor, x, pdf, bool(noprior)
         self.ny, self.np = int(ny), int(np_)
+        # pperm[k] = position in the CALLER's flat parameter buffer of device parameter k (composite functors fix
+        # their own parameter order; lsqfit's buffer follows the prior dictionary); None = identical
+        self.pperm = None if pperm is None else np.asarray(pperm, dtype=np.int64)
         self._plans = {}
+
+    def _inv(self):
+        inv = np.empty_like(self.pperm)
+        inv[self.pperm] = np.arange(self.pperm.size)
+        return inv
 
     @property
     def mean(self):
-        return np.asarray(self.pdf.mean, dtype=float)
+        """means of y (+) prior in DEVICE order"""
+        m = np.asarray(self.pdf.mean, dtype=float)
+        if self.pperm is None or self.noprior:
+            return m
+        return np.concatenate([m[:self.ny], m[self.ny:][self.pperm]])
+
+    @property
+    def i_invwgts(self):
+        """the whitening with prior indices renumbered to the device's parameter order"""
+        if self.pperm is None or self.noprior:
+            return self.pdf.i_invwgts
+        inv, ny = self._inv(), self.ny
+        out = []
+        for idx, w in self.pdf.i_invwgts:
+            idx = np.asarray(idx, dtype=np.int64)
+            out.append((np.where(idx >= ny, ny + inv[np.maximum(idx - ny, 0)], idx), w))
+        return out
+
+    def to_device(self, p):
+        return np.asarray(p, dtype=float) if self.pperm is None else np.asarray(p, dtype=float)[..., self.pperm]
+
+    def from_device(self, x=None, cov=None, J=None):
+        """results in the caller's parameter order"""
+        if self.pperm is None:
+            return x, cov, J
+        inv = self._inv()
+        return (None if x is None else x[..., inv], None if cov is None else cov[..., inv, :][..., :, inv],
+                None if J is None else J[..., inv])
 
     def plan(self, device=0):
         if device not in self._plans:
-            self._plans[device] = Plan(self.functor, self.np, self.ny, self.x, self.pdf.i_invwgts,
-                                       noprior=self.noprior, device=device)
+            self._plans[device] = PLAN_CACHE.get(self.functor, self.np, self.ny, self.x, self.i_invwgts,
+                                                 self.noprior, device)
         return self._plans[device]
 
 
@@ -47,13 +132,13 @@ class DeviceChiv(object):
 
     def __call__(self, p):
         plan = self.b200.plan(self.device)
-        f, _, _ = plan.residual_jacobian(np.asarray(p, dtype=float).reshape(1, -1), self.b200.mean)
+        f, _, _ = plan.residual_jacobian(self.b200.to_device(p).reshape(1, -1), self.b200.mean)
         return f[0].cpu().numpy()
 
     def jacobian(self, p):
         plan = self.b200.plan(self.device)
-        _, J, _ = plan.residual_jacobian(np.asarray(p, dtype=float).reshape(1, -1), self.b200.mean)
-        return J[0].cpu().numpy()
+        _, J, _ = plan.residual_jacobian(self.b200.to_device(p).reshape(1, -1), self.b200.mean)
+        return self.b200.from_device(J=J[0].cpu().numpy())[2]
 
 
 class b200_lm(object):
@@ -83,12 +168,10 @@ class b200_lm(object):
         plan = spec.plan(device)
         if n != plan.nchiv:
             raise ValueError("b200_lm: n=%d does not match the whitening (%d residuals)" % (n, plan.nchiv))
-        out = plan.fit_batch_host(spec.mean, self.x0.reshape(1, -1), tol=self.tol, maxit=maxit,
+        out = plan.fit_batch_host(spec.mean, spec.to_device(self.x0).reshape(1, -1), tol=self.tol, maxit=maxit,
                                   scaler=scaler, want_cov=True, want_fJ=True, polish=polish)
-        self.x = out["x"][0].copy()
-        self.cov = out["cov"][0].copy()
+        self.x, self.cov, self.J = spec.from_device(out["x"][0].copy(), out["cov"][0].copy(), out["J"][0].copy())
         self.f = out["f"][0].copy()
-        self.J = out["J"][0].copy()
         self.nit = int(out["nit"][0])
         self.logdet_JtJ = float(out["logdet"][0])
         status = int(out["status"][0])

@@ -13,11 +13,12 @@ import numpy as np
 # family ids == enum FunctorFamily in csrc/functors.cuh
 FAMILY = dict(
     multiexp=0, multiexp_de=1, simple=2, offset_exp=3, poly=4, exp_poly=5, xerr_logistic=6, gather=7,
+    multiexp_shared2=8, multiexp_shared3=9,
     misra1a=10, chwirut=11, lanczos=12, gauss=13, danwood=14, misra1b=15, misra1c=16,
     misra1d=17, kirby2=18, hahn1=19, nelson=20, mgh17=21, roszman1=22, enso=23, mgh09=24,
     rat42=25, mgh10=26, eckerle4=27, rat43=28, bennett5=29,
 )
-NX = dict(simple=2, nelson=2)          # every other family reads one x column
+NX = dict(simple=2, nelson=2, multiexp_shared2=2, multiexp_shared3=2)          # every other family reads one x column
 
 # NIST StRD problem name -> functor family (examples/nist.py)
 NIST_FORM = dict(
@@ -49,6 +50,18 @@ def _multiexp_de(x, p):
     K = len(p) // 2
     E = np.cumsum(p[K:])
     return sum(p[k] * np.exp(-E[k] * t) for k in range(K))
+
+
+def _multiexp_shared(M):
+    """M data sets with shared energies: x rows (t, m); p = [a^(0)(K), ..., a^(M-1)(K), E(K)]"""
+    def f(x, p):
+        x = np.asarray(x)
+        t, m = x[:, 0], x[:, 1].astype(int)
+        p = np.asarray(p)
+        K = len(p) // (M + 1)
+        a = p[:M * K].reshape(M, K)
+        return sum(a[m, k] * np.exp(-p[M * K + k] * t) for k in range(K))
+    return f
 
 
 def _simple(x, p):
@@ -83,6 +96,8 @@ def _gauss(x, b):
 _HOST = dict(
     multiexp=_multiexp,
     multiexp_de=_multiexp_de,
+    multiexp_shared2=_multiexp_shared(2),
+    multiexp_shared3=_multiexp_shared(3),
     simple=_simple,
     offset_exp=lambda x, p: p[0] + p[1] * np.exp(-p[2] * _col(x)),
     poly=_poly,

@@ -38,6 +38,23 @@ def multiexp(x, p):
     return ans
 
 
+def _multiexp_shared(M):
+    """M data sets with shared energies (a simultaneous MultiFitter fit; src/lsqfit/_extras.py:1816-1829 evaluates the
+    per-data-set models one after the other): x rows (t, m); p = [a^(0)(K), ..., a^(M-1)(K), E(K)]"""
+    def f(x, p):
+        x = np.asarray(x, dtype=float)
+        t, mm = x[:, 0], x[:, 1].astype(int)
+        K = len(p) // (M + 1)
+        parts = []
+        for i in range(len(t)):
+            ans = 0.0
+            for k in range(K):
+                ans = ans + p[mm[i] * K + k] * exp(-p[M * K + k] * t[i])
+            parts.append(ans)
+        return D.stack(parts) if isinstance(parts[0], D.Dual) else np.array(parts)
+    return f
+
+
 def multiexp_de(x, p):
     t = _x(x)
     K = len(p) // 2
@@ -192,6 +209,7 @@ def bennett5(x, b):         # :1291
 
 MODELS = dict(
     multiexp=multiexp, multiexp_de=multiexp_de, simple=simple,
+    multiexp_shared2=_multiexp_shared(2), multiexp_shared3=_multiexp_shared(3),
     offset_exp=offset_exp, poly=poly, exp_poly=exp_poly,
     xerr_logistic=xerr_logistic, gather=gather,
     misra1a=misra1a, chwirut=chwirut, lanczos=lanczos, gauss=gauss,

@@ -63,13 +63,16 @@ def test_model_jacobians_fd():
                 "lanczos": 6, "gauss": 8, "danwood": 2, "misra1b": 2, "misra1c": 2,
                 "misra1d": 2, "kirby2": 5, "hahn1": 7, "nelson": 3, "mgh17": 5,
                 "roszman1": 4, "enso": 9, "mgh09": 4, "rat42": 3, "mgh10": 3,
-                "eckerle4": 3, "rat43": 4, "bennett5": 3, "gather": 3}[name]
+                "eckerle4": 3, "rat43": 4, "bennett5": 3, "gather": 3,
+                "multiexp_shared2": 6, "multiexp_shared3": 8}[name]
         ny = 7
         x = rng.uniform(0.5, 2.0, size=(ny, 2))
         if name == "simple":
             x[:, 1] = [0, 0, 0, 1, 0, 1, 0]
         if name == "gather":
             x[:, 0] = [0, 1, 2, 2, 0, 1, 0]
+        if name.startswith("multiexp_shared"):
+            x[:, 1] = [0, 1, 1, 0, 1, 0, int(name[-1]) - 1]
         p = rng.uniform(0.5, 1.5, size=npar)
         f, G = M.value_and_jacobian(name, x, p)
         for j in range(npar):
