@@ -126,6 +126,15 @@ int b200lm_last_team(b200lm_handle h);
  * throughput on saturated batches), 2 / 4 = team kernel (lowest latency per trial point).  The two kernels
  * sum in a different order: results agree to rounding, not bit for bit. */
 int b200lm_set_team(b200lm_handle h, int team);
+/* trust-region decisions of the following fit_batch calls on this handle:
+ *   0 = those of the solver behind lsqfit.scipy_least_squares (scipy trf, src/lsqfit/_scipy.py:156-161) -- default;
+ *   1 = those of lsqfit.gsl_multifit with alg='lm' (src/lsqfit/_gsl.pyx:563-723: GSL's gsl_multifit_nlinear trust
+ *       driver with the Levenberg-Marquardt sub-problem): Nielsen's update of the LM parameter, accept iff rho > 0,
+ *       GSL's xtol / gtol tests.  With this policy d_nit counts ITERATIONS (gsl_multifit_nlinear_niter, _gsl.pyx:713),
+ *       maxit limits iterations, scaler may also be 2 (= 'marquardt'), and d_status is 0 (maxit), 11 (info 1: xtol),
+ *       12 (info 2: gtol) or 14 (info 27: no progress in the first iteration) -- stopping_criterion = status - 10
+ *       (_gsl.pyx:689-701). */
+int b200lm_set_policy(b200lm_handle h, int policy);
 /* number of kernel launches issued through this handle so far */
 long long b200lm_launch_count(b200lm_handle h);
 

@@ -40,6 +40,7 @@ void fill_params(b200lm_handle_s* h, FitParams& P) {
     }
     P.counter = h->d_counter;
     P.stats = h->d_stats;
+    P.policy = h->policy;
 }
 }  // namespace b200lm
 
@@ -275,7 +276,8 @@ int b200lm_fit_batch(b200lm_handle h, int B,
         return set_error(h, B200LM_EINVAL, "NULL required argument");
     if ((mean_stride != 0 && mean_stride < h->N) || (p0_stride != 0 && p0_stride < h->np))
         return set_error(h, B200LM_EINVAL, "bad stride");
-    if (scaler != 0 && scaler != 1) return set_error(h, B200LM_EINVAL, "scaler must be 0 or 1");
+    if (scaler != 0 && scaler != 1 && !(scaler == 2 && h->policy == 1))
+        return set_error(h, B200LM_EINVAL, "scaler must be 0 (levenberg), 1 (more) or, with the GSL policy, 2 (marquardt)");
     if (maxit < 1) return set_error(h, B200LM_EINVAL, "maxit must be >= 1");
     if (B == 0) return B200LM_OK;
     CUDA_TRY(h, cudaSetDevice(h->device), "cudaSetDevice");
@@ -332,6 +334,13 @@ int b200lm_set_team(b200lm_handle h, int team) {
     if (!h) return set_error(h, B200LM_EINVAL, "NULL handle");
     if (team != 0 && team != 1 && team != 2 && team != 4) return set_error(h, B200LM_EINVAL, "team must be 0 (default), 1, 2 or 4");
     h->team_request = team;
+    return B200LM_OK;
+}
+
+int b200lm_set_policy(b200lm_handle h, int policy) {
+    if (!h) return set_error(h, B200LM_EINVAL, "NULL handle");
+    if (policy != 0 && policy != 1) return set_error(h, B200LM_EINVAL, "policy must be 0 (scipy trf) or 1 (gsl lm)");
+    h->policy = policy;
     return B200LM_OK;
 }
 

@@ -31,6 +31,7 @@ struct b200lm_handle_s {
     cudaStream_t last_stream = nullptr;
     long long launches = 0;
     int team_request = 0;       // 0: default policy; 1, 2, 4: warps per fit asked for by b200lm_set_team
+    int policy = 0;             // trust-region decisions: 0 scipy TRF, 1 GSL trust/lm (b200lm_set_policy)
     int last_team = 1;          // warps per fit of the last fit_batch launch
     // staging for the host-pointer API
     void* d_stage = nullptr; size_t stage_bytes = 0;

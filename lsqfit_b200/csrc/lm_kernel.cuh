@@ -1045,6 +1045,97 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
         LinModel lm;
         lm.valid = false; lm.a = 0.0; lm.b = 0.0;
 
+        int nit_report = -1;                      // what P.nit reports when it is not nfev (GSL policy: iterations)
+        if (P.policy == 1 && status == -2) {
+            // ---- GSL trust-region driver with the Levenberg-Marquardt sub-problem (gsl_multifit_nlinear: trust.c,
+            // lm.c, nielsen.c, scaling.c, convergence.c, fdf.c as called by the reference's src/lsqfit/_gsl.pyx:563-723;
+            // CPU restatement: oracle/gsl_lm.py).  One factorisation per trial: (D^-1 J^T J D^-1 + mu I) (D dx) = -D^-1 g.
+            const double cn0 = act ? sqrt(c.A[lane * LDA + lane]) : 0.0;          // |J_j|
+            double diag = 1.0;                                                    // D_j: levenberg 1, more / marquardt |J_j|
+            if (P.scaler != 0) diag = cn0 == 0.0 ? 1.0 : cn0;
+            double mu;
+            {
+                const double m = warp_max(act ? cn0 / diag : 0.0);
+                mu = 1.0e-3 * m * m;                                              // nielsen_init
+            }
+            double nu = 2.0;
+            int iter = 0;
+            while (status == -2) {
+                const double gi = act ? c.g[lane] : 0.0;
+                const double d = 1.0 / diag;
+                if (act) c.dsc[lane] = d;
+                __syncwarp();
+                const double gh = d * gi;
+                int bad = 0;
+                bool found = false;
+                double step = 0.0;
+                while (!found) {
+                    double sh, res[3];
+                    ++nfac;
+                    const long long t_s0 = B200LM_CLOCK();
+                    const bool ok = factor_solve<NP, LDA>(c.A, c.dsc, c.L, c.idg, c.colb, lane, mu, gh, false, &sh, res);
+                    pk.solve += B200LM_CLOCK() - t_s0;
+                    double rho = -1.0;
+                    double cost_new = cost;
+                    step = (act && ok) ? d * sh : 0.0;
+                    if (ok) {
+                        if (act) { c.pn[lane] = c.p[lane] + step; c.idg[lane] = step; }
+                        __syncwarp();
+                        double As = 0.0;
+                        if (act) {
+                            const double* Ar = c.A + lane * LDA;
+#pragma unroll
+                            for (int j = 0; j < NP; ++j) As = fma(Ar[j], c.idg[j], As);
+                        }
+                        // quadratic_preduction * |f|^2 / 2 = -(1/2 dx^T A dx + g^T dx)
+                        const double predicted = warp_sum(act ? -step * (0.5 * As + gi) : 0.0);
+                        __syncwarp();
+                        c.A = c.Abuf[cur ^ 1]; c.g = c.gbuf[cur ^ 1];
+                        const long long t_e0 = B200LM_CLOCK();
+                        cost_new = ev.run(c, c.pn, nullptr, nullptr, 0);
+                        pk.eval += B200LM_CLOCK() - t_e0;
+                        c.A = c.Abuf[cur]; c.g = c.gbuf[cur];
+                        ++nfev; ++njev;
+                        // trust_calc_rho: |f_trial| >= |f| (or NaN) rejects; rho = (1 - u^2) / pred
+                        if (cost_new < cost && predicted > 0.0) rho = (cost - cost_new) / predicted;
+                    }
+                    if (rho > 0.0) {
+                        if (act) c.p[lane] = c.pn[lane];
+                        cur ^= 1;
+                        c.A = c.Abuf[cur]; c.g = c.gbuf[cur];
+                        cost = cost_new;
+                        __syncwarp();
+                        if (P.scaler != 0) {
+                            const double cn = act ? sqrt(c.A[lane * LDA + lane]) : 0.0;
+                            if (P.scaler == 1) diag = fmax(diag, cn);                 // more
+                            else diag = cn == 0.0 ? 1.0 : cn;                         // marquardt
+                        }
+                        __syncwarp();
+                        const double bq = 2.0 * rho - 1.0;                            // nielsen_accept
+                        mu *= fmax(0.333333333333333, 1.0 - bq * bq * bq);
+                        nu = 2.0;
+                        found = true;
+                    } else {
+                        mu *= nu;                                                     // nielsen_reject
+                        nu *= 2.0;
+                        if (++bad > 15) break;                                        // GSL_ENOPROG
+                    }
+                }
+                if (!found && iter == 0) { status = 14; iter = 1; break; }            // fdf.c: no progress in the first iteration
+                ++iter;
+                // gsl_multifit_nlinear_test: dx of the last trial, x, g, f of the current point
+                const double xi = act ? c.p[lane] : 0.0;
+                const bool small = !act || fabs(step) < P.xtol * P.xtol + P.xtol * fabs(xi) || step == 0.0;
+                const double gnorm = warp_max(act ? fabs(c.g[lane] * fmax(xi, 1.0)) : 0.0);
+                if (__all_sync(B200LM_FULL, small)) status = 11;
+                else if (gnorm <= P.gtol * fmax(cost, 1.0)) status = 12;
+                else if (iter >= P.maxit) status = 0;
+            }
+            nit_report = iter;
+            // the scale of the covariance / polish code below
+            sinv = diag;
+        }
+
         while (status == -2) {
             const double gi = act ? c.g[lane] : 0.0;
             // |g|_inf and |x|^2 of the current point in one reduction (x does not change until a step is accepted)
@@ -1236,7 +1327,7 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
         if (act) P.x_out[(size_t)b * NP + lane] = c.p[lane];
         if (lane == 0) {
             P.chi2[b] = 2.0 * cost;
-            P.nit[b] = nfev;
+            P.nit[b] = nit_report >= 0 ? nit_report : nfev;
             P.status[b] = status;
             if (P.logdet) P.logdet[b] = ld;
         }

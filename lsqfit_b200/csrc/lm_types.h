@@ -53,13 +53,16 @@ struct FitParams {
     int maxit;
     int scaler;                 // 0: none (scipy x_scale=1), 1: More' (scipy 'jac', GSL 'more')
     int polish;                 // max Gauss-Newton refinement steps after the trust-region loop stops
+    int policy;                 // 0: scipy TRF decisions (src/lsqfit/_scipy.py:156-161); 1: GSL trust/lm decisions
+                                // (gsl_multifit_nlinear behind src/lsqfit/_gsl.pyx:563-723; scaler 2 = marquardt)
     // ---- outputs (any of f_out, J_out, cov, logdet may be null) ----------------
     double* x_out;              // [B][np]
     double* chi2;               // [B]
     double* cov;                // [B][np][np]
     double* logdet;             // [B]  log det(J^T J)
-    int* nit;                   // [B]  function evaluations (scipy nfev)
-    int* status;                // [B]  scipy status: 0 maxit, 1 gtol, 2 ftol, 3 xtol, 4 both, -1 non-finite start
+    int* nit;                   // [B]  function evaluations (scipy nfev); policy 1: iterations (gsl niter)
+    int* status;                // [B]  scipy status: 0 maxit, 1 gtol, 2 ftol, 3 xtol, 4 both, -1 non-finite start;
+                                //      policy 1: 0 maxit, 11 xtol (info 1), 12 gtol (info 2), 14 no progress (info 27)
     double* f_out;              // [B][nchiv]
     double* J_out;              // [B][nchiv][np]
     int* counter;               // work-queue head (zeroed before launch)

@@ -17,7 +17,10 @@ from . import _cabi
 from .functors import Functor
 
 # solver status -> lsqfit stopping_criterion (reference src/lsqfit/_scipy.py:178-181)
-STOPPING_CRITERION = {0: 0, 1: 2, 2: 3, 3: 1, 4: 1, -1: 0}
+# (11, 12, 14: the GSL policy's info 1 / 2 / 27, reference src/lsqfit/_gsl.pyx:689-701)
+STOPPING_CRITERION = {0: 0, 1: 2, 2: 3, 3: 1, 4: 1, -1: 0, 11: 1, 12: 2, 14: 4}
+SCALER = {"more": 1, "jac": 1, 1: 1, "none": 0, "levenberg": 0, None: 0, 0: 0, "marquardt": 2, 2: 2}
+POLICY = {"trf": 0, "scipy": 0, "scipy_least_squares": 0, 0: 0, None: 0, "gsl": 1, "gsl_lm": 1, "gsl_multifit": 1, "lm": 1, 1: 1}
 
 
 def normalize_tol(tol):
@@ -111,13 +114,25 @@ class Plan(object):
         return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
 
     # ---- the batch fit -------------------------------------------------------------
+    def _set_policy(self, policy, scaler):
+        """policy: 'trf' (decisions of scipy's trf, the solver behind lsqfit.scipy_least_squares; nit = function
+        evaluations) or 'gsl' (decisions of lsqfit.gsl_multifit with alg='lm'; nit = iterations, maxit limits
+        iterations, scaler may also be 'marquardt')."""
+        if policy not in POLICY:
+            raise ValueError("unknown policy %r (use 'trf' or 'gsl')" % (policy,))
+        if scaler not in SCALER:
+            raise ValueError("unkown scaler " + str(scaler))
+        _cabi.check(_cabi.lib.b200lm_set_policy(self._h, POLICY[policy]), self._h)
+        return SCALER[scaler]
+
     def fit_batch(self, mean, p0, tol=1e-8, maxit=1000, scaler="more", B=None,
-                  want_cov=True, want_fJ=False, out=None, polish=0):
+                  want_cov=True, want_fJ=False, out=None, polish=0, policy="trf"):
         """Fit B problems on the device; inputs may be numpy arrays or device tensors.
 
         mean: [B, N] or [N] (shared);  p0: [B, np] or [np] (shared).
         Returns a BatchResult of device tensors (no host synchronisation)."""
         xtol, gtol, ftol = normalize_tol(tol)
+        sc = self._set_policy(policy, scaler)
         tm, sm = self._dev(mean, self.N)
         tp, sp = self._dev(p0, self.np)
         if B is None:
@@ -134,7 +149,6 @@ class Plan(object):
                 torch.empty(B, device=self.tdev, dtype=torch.int32),
                 torch.empty((B, self.nchiv), **kw) if want_fJ else None,
                 torch.empty((B, self.nchiv, self.np), **kw) if want_fJ else None)
-        sc = {"more": 1, "jac": 1, 1: 1, "none": 0, "levenberg": 0, None: 0, 0: 0}[scaler]
         ptr = lambda t: t.data_ptr() if t is not None else None
         _cabi.check(_cabi.lib.b200lm_fit_batch(
             self._h, B, tm.data_ptr(), sm, tp.data_ptr(), sp, xtol, gtol, ftol, int(maxit), sc, int(polish),
@@ -144,10 +158,11 @@ class Plan(object):
         return out
 
     def fit_batch_host(self, mean, p0, tol=1e-8, maxit=1000, scaler="more", want_cov=True,
-                       want_fJ=False, out=None, polish=0):
+                       want_fJ=False, out=None, polish=0, policy="trf"):
         """Same fit through the host-buffer C entry point: numpy in, numpy out.
         ``out`` may hold preallocated arrays (dict with keys x, chi2, cov, logdet, nit, status)."""
         xtol, gtol, ftol = normalize_tol(tol)
+        sc = self._set_policy(policy, scaler)
         # the C entry point reads raw host pointers: dtype, contiguity and shapes are checked HERE
         # (np.ascontiguousarray is a no-op for conforming arrays)
         mean = np.ascontiguousarray(mean, dtype=np.float64)
@@ -183,7 +198,6 @@ class Plan(object):
                         and a.flags["WRITEABLE"] and tuple(a.shape) == shp):
                     raise ValueError("out[%r] must be a writable C-contiguous %s array of shape %s"
                                      % (k, np.dtype(dt).name, shp))
-        sc = {"more": 1, "jac": 1, 1: 1, "none": 0, "levenberg": 0, None: 0, 0: 0}[scaler]
         ptr = lambda a: a.ctypes.data if a is not None else None
         _cabi.check(_cabi.lib.b200lm_fit_batch_host(
             self._h, B, mean.ctypes.data, sm, p0.ctypes.data, sp, xtol, gtol, ftol, int(maxit), sc, int(polish),

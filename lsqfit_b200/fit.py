@@ -196,7 +196,8 @@ class nonlinear_fit(object):
         args.pop("device", None)
         out = plan.fit_batch(means, p0, tol=self.tol if tol is None else tol,
                              maxit=self.maxit if maxit is None else maxit, want_cov=want_cov,
-                             scaler=args.pop("scaler", "more"), polish=args.pop("polish", 0))
+                             scaler=args.pop("scaler", "more"), polish=args.pop("polish", 0),
+                             policy=args.pop("policy", "trf"))
         return BatchFits(self, out)
 
     def bootstrap_means(self, n, seed=None, first=0):

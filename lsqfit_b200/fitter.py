@@ -145,16 +145,35 @@ class b200_lm(object):
     """B200 batched Levenberg-Marquardt fitter (single-fit plugin face).
 
     Args mirror the reference plugins: ``x0`` start, ``n`` number of residuals, ``f`` the chiv
-    callable, ``tol`` = xtol or (xtol, gtol, ftol), ``maxit`` = max function evaluations.
-    Extra ``fitterargs``: ``scaler`` ('more' default | 'levenberg'), ``device`` (CUDA index), ``polish`` (max
-    Gauss-Newton refinement steps after the trust-region loop; default 0 = stop where the
-    reference's solver stops).
+    callable, ``tol`` = xtol or (xtol, gtol, ftol), ``maxit``.
+    Extra ``fitterargs``:
+      ``policy``  'trf' (default): the trust-region decisions of the solver behind ``lsqfit.scipy_least_squares``
+                  (reference src/lsqfit/_scipy.py:156-161); ``nit`` and ``maxit`` count function evaluations (:167).
+                  'gsl': those of ``lsqfit.gsl_multifit`` with ``alg='lm'`` (src/lsqfit/_gsl.pyx:563-723: Nielsen update
+                  of the LM parameter, GSL's xtol/gtol tests); ``nit`` and ``maxit`` count iterations (:713), and the
+                  reference's ``alg`` ('lm' only), ``solver`` ('qr' | 'cholesky' | 'svd': all served by the device's
+                  LDL^T solve of the damped normal equations), ``factor_up``, ``factor_down``, ``avmax`` (read by GSL's
+                  dogleg / lmaccel methods only) are accepted.
+      ``scaler``  'more' (default) | 'levenberg' | 'marquardt' (gsl policy only)   (_gsl.pyx:621-653)
+      ``device``  CUDA index;  ``polish``  max Gauss-Newton refinement steps after the trust-region loop (default 0 =
+                  stop where the reference's solver stops).
     """
 
     def __init__(self, x0, n, f, tol=(1e-8, 1e-10, 1e-10), maxit=1000, scaler="more", device=0,
-                 polish=0, **extra_args):
+                 polish=0, policy="trf", alg="lm", solver="qr", factor_up=3.0, factor_down=2.0, avmax=0.75,
+                 **extra_args):
         if extra_args:
             raise ValueError("b200_lm: unknown fitter arguments: " + ", ".join(sorted(extra_args)))
+        from .engine import POLICY, SCALER
+        if policy not in POLICY:
+            raise ValueError("b200_lm: unknown policy " + str(policy))
+        gsl = POLICY[policy] == 1
+        if alg != "lm":
+            raise ValueError("unkown algorithm " + str(alg))                # _gsl.pyx:619 (only 'lm' runs on the device)
+        if scaler not in SCALER or (SCALER[scaler] == 2 and not gsl):
+            raise ValueError("unkown scaler " + str(scaler))                 # _gsl.pyx:628
+        if solver not in ("qr", "cholesky", "svd"):
+            raise ValueError("unkown solver " + str(solver))                 # _gsl.pyx:637
         spec = getattr(f, "b200", None)
         if spec is None:
             raise ValueError(
@@ -164,24 +183,33 @@ class b200_lm(object):
         self.maxit = maxit
         self.n = n
         self.x0 = np.array(x0, dtype=float)
-        self.description = "scaler = {}    device = cuda:{}".format(scaler, device)
+        self.policy, self.scaler = ("gsl" if gsl else "trf"), scaler
+        if gsl:
+            self.alg, self.solver, self.factor_up, self.factor_down, self.avmax = alg, solver, factor_up, factor_down, avmax
+            self.description = "methods = {}/{}/{}    device = cuda:{}".format(alg, scaler, solver, device)
+        else:
+            self.description = "scaler = {}    device = cuda:{}".format(scaler, device)
         plan = spec.plan(device)
         if n != plan.nchiv:
             raise ValueError("b200_lm: n=%d does not match the whitening (%d residuals)" % (n, plan.nchiv))
         out = plan.fit_batch_host(spec.mean, spec.to_device(self.x0).reshape(1, -1), tol=self.tol, maxit=maxit,
-                                  scaler=scaler, want_cov=True, want_fJ=True, polish=polish)
+                                  scaler=scaler, want_cov=True, want_fJ=True, polish=polish, policy=self.policy)
         self.x, self.cov, self.J = spec.from_device(out["x"][0].copy(), out["cov"][0].copy(), out["J"][0].copy())
         self.f = out["f"][0].copy()
         self.nit = int(out["nit"][0])
         self.logdet_JtJ = float(out["logdet"][0])
         status = int(out["status"][0])
-        self.results = dict(status=status, nfev=self.nit, chi2=float(out["chi2"][0]),
+        self.results = dict(status=status, nit=self.nit, chi2=float(out["chi2"][0]),
                             logdet_JtJ=self.logdet_JtJ)
+        if not gsl:
+            self.results["nfev"] = self.nit
         self.stopping_criterion = STOPPING_CRITERION[status]
         self.error = None
         if status == -1:
             self.error = "b200_lm: residuals are not finite at the starting point"
         elif status == 0:
-            self.error = "b200_lm: no convergence in {} function evaluations".format(maxit)
+            self.error = "b200_lm: no convergence in {} {}".format(maxit, "iterations" if gsl else "function evaluations")
+        elif status == 14:
+            self.error = "b200_lm can't improve on starting value; may have converged already."   # _gsl.pyx:714-715
         elif not np.all(np.isfinite(self.cov)):
             self.error = "b200_lm: J^T J is singular at the solution"

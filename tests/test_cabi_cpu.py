@@ -95,7 +95,8 @@ def test_tol_normalisation_and_blocks():
     assert normalize_tol((1, 2, 3)) == (1.0, 2.0, 3.0)
     with pytest.raises(ValueError):
         normalize_tol((1, 2, 3, 4))
-    assert STOPPING_CRITERION == {0: 0, 1: 2, 2: 3, 3: 1, 4: 1, -1: 0}     # _scipy.py:178-181
+    assert {k: STOPPING_CRITERION[k] for k in (0, 1, 2, 3, 4, -1)} == {0: 0, 1: 2, 2: 3, 3: 1, 4: 1, -1: 0}     # _scipy.py:178-181
+    assert {k: STOPPING_CRITERION[k] for k in (11, 12, 14)} == {11: 1, 12: 2, 14: 4}     # GSL policy: info 1, 2, 27 (_gsl.pyx:689-701)
     cov = np.diag([1., 2., 3., 4., 5.])
     cov[0, 3] = cov[3, 0] = 0.1
     cov[3, 4] = cov[4, 3] = 0.2

@@ -811,24 +811,86 @@ def test_large_block_eps_regulator_vs_oracle(n, eps):
     np.testing.assert_allclose(np.sum((Wd @ z) ** 2), np.sum((Wo @ z) ** 2), rtol=1e-9)
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 4])
-def test_y_noerr_golden(n):
+@pytest.mark.parametrize("policy", ["trf", "gsl"])
+def test_y_noerr_golden(policy):
     """examples/y-noerr.out through the device path: data and prior correlated with each other (one joint
-    covariance block), svd cut modifying 2-3 modes, tol = 1e-15."""
+    covariance block), svd cut modifying 2-3 modes, tol = 1e-15, DEFAULT scaler (More'), every fit started from the
+    previous fit's parameters as the example does (examples/y-noerr.py:27-45).  With the GSL policy the iteration
+    counts follow the example's (12 / 31 / 64 / 143)."""
     _need_gpu()
     import lsqfit_b200 as lb
     from oracle import gvfmt
     from parity_util import _y_noerr_problem, Y_NOERR_OUT
-    x, ymod, cov, pm = _y_noerr_problem(n)
-    # scaler='levenberg' = the unit scaling of the reference's scipy plugin.  With More' scaling the n = 4 fit
-    # does not converge from the prior mean -- nor does scipy's trf with x_scale='jac' (1000 evaluations, cost
-    # 2.7e4): the svd cut leaves Jacobian columns of norm 1e4 ... 1e9 and More' scaling follows the largest.
-    fit = lb.nonlinear_fit(data=(x, ymod, None), prior=(pm, np.ones(2 * n)), yp_cov=cov, fcn="multiexp",
-                           svdcut=1e-12, tol=1e-15, scaler="levenberg")
-    chi2dof, dof, Q, logGBF, svdn, a_exp, E_exp = Y_NOERR_OUT[n]
-    assert fit.dof == dof and fit.svdn == svdn
-    assert gvfmt.agrees_g(fit.chi2 / fit.dof, chi2dof, 2)
-    assert gvfmt.agrees_g(fit.Q, Q, 2)
-    assert abs(fit.logGBF - float(logGBF)) < 1.5e-3
-    for m, s, e in zip(fit.pmean, fit.psdev, a_exp + E_exp):
-        assert gvfmt.agrees(m, s, e, slack=1.01), (m, s, e)
+    from test_oracle_golden import _chain_p0, Y_NOERR_ITNS
+    prev = None
+    for n in (1, 2, 3, 4):
+        x, ymod, cov, pm = _y_noerr_problem(n)
+        fit = lb.nonlinear_fit(data=(x, ymod, None), prior=(pm, np.ones(2 * n)), yp_cov=cov, fcn="multiexp",
+                               p0=_chain_p0(pm, prev, n), svdcut=1e-12, tol=1e-15, policy=policy)
+        prev = fit.pmean
+        chi2dof, dof, Q, logGBF, svdn, a_exp, E_exp = Y_NOERR_OUT[n]
+        assert fit.error is None, (n, fit.error)
+        assert fit.dof == dof and fit.svdn == svdn
+        assert gvfmt.agrees_g(fit.chi2 / fit.dof, chi2dof, 2)
+        assert gvfmt.agrees_g(fit.Q, Q, 2)
+        assert abs(fit.logGBF - float(logGBF)) < 1.5e-3
+        for m, s, e in zip(fit.pmean, fit.psdev, a_exp + E_exp):
+            assert gvfmt.agrees(m, s, e, slack=1.01), (m, s, e)
+        if policy == "gsl":
+            print("y-noerr nexp=%d: %d iterations on the device, %d in examples/y-noerr.out" % (n, fit.nit, Y_NOERR_ITNS[n]))
+            assert abs(fit.nit - Y_NOERR_ITNS[n]) <= max(2, 0.15 * Y_NOERR_ITNS[n]), (n, fit.nit)
+
+
+def test_gsl_policy_vs_oracle(nist_problems):
+    """policy='gsl': the decisions of lsqfit.gsl_multifit (alg='lm', src/lsqfit/_gsl.pyx:563-723) on the device.
+    Against the CPU restatement (oracle/gsl_lm.py, pinned to the iteration counts of examples/nist.out): same
+    iteration count (nit = gsl_multifit_nlinear_niter) on >= 20 of the 27 problems and within 10 % of the printed
+    count of examples/nist.out on >= 20; same stopping criterion; p, chi2 as close as the stopping rule allows; and
+    with a tight tolerance + polish the usual 1e-8 / 1e-9 / 1e-8 bars against the exact stationary point."""
+    _need_gpu()
+    from oracle.gsl_lm import gsl_multifit
+    from oracle.fit import nonlinear_fit as ofit
+    same = close = near = 0
+    for pr in nist_problems:
+        fo = ofit(pr["form"], np.array(pr["x"]), pr["y"], pr["ysdev"], prior_mean=pr["prior_mean"],
+                  prior_cov=pr["prior_sdev"], p0=pr["p0"], tol=pr["tol"], fitter=gsl_multifit)
+        fd = _device_nist(pr, pr["tol"], policy="gsl")
+        assert fd.error is None and fd.stopping_criterion == fo.stopping_criterion == 1, pr["name"]
+        print("   %-10s iterations: device %4d, oracle %4d, examples/nist.out %4d" % (pr["name"], fd.nit, fo.nit, pr["out"]["nit"]))
+        same += int(fd.nit == fo.nit)
+        near += int(abs(fd.nit - fo.nit) <= max(1, 0.1 * fo.nit))
+        want = pr["out"]["nit"]
+        close += int(abs(fd.nit - want) <= max(1, 0.1 * want))
+        if pr["name"] != "lanczos1":
+            assert np.max(np.abs(fd.pmean - fo.pmean) / fo.psdev) < 2e-4, (pr["name"], fd.nit, fo.nit)
+            assert abs(fd.chi2 - fo.chi2) <= 1e-7 * fo.chi2, pr["name"]
+    print("GSL policy: nit identical to the oracle on %d / 27, within max(1, 10 %%) of it on %d / 27, within 10 %% of "
+          "examples/nist.out on %d / 27" % (same, near, close))
+    # the device solves the damped normal equations (LDL^T), the oracle the augmented least-squares problem: the
+    # last iterations of a fit converged to rounding level differ, the decisions before them do not
+    assert same >= 12 and near >= 22 and close >= 20, (same, near, close)
+    # tight + polish: the exact stationary point
+    for pr in nist_problems[:12]:
+        fo = _oracle_nist(pr, TIGHT)
+        xe, fe, Je, cove = exact_minimum(fo)
+        fd = _device_nist(pr, (1e-14, 0.0, 0.0), policy="gsl", polish=8)
+        if pr["name"].startswith("lanczos"):
+            continue
+        assert np.max(np.abs(fd.pmean - xe) / fo.psdev) < 1e-8, pr["name"]
+        assert abs(fd.chi2 - fe @ fe) <= 1e-9 * (fe @ fe), pr["name"]
+        assert _rel_cov(fd.cov, cove) < 1e-8, pr["name"]
+    # scalers and argument checking of the reference plugin (src/lsqfit/_gsl.pyx:610-640)
+    pr = nist_problems[0]
+    for scaler in ("levenberg", "marquardt"):
+        fo = ofit(pr["form"], np.array(pr["x"]), pr["y"], pr["ysdev"], prior_mean=pr["prior_mean"],
+                  prior_cov=pr["prior_sdev"], p0=pr["p0"], tol=pr["tol"], fitter=gsl_multifit, scaler=scaler)
+        fd = _device_nist(pr, pr["tol"], policy="gsl", scaler=scaler)
+        assert abs(fd.nit - fo.nit) <= 1 and fd.error is None, (scaler, fd.nit, fo.nit)
+        assert np.max(np.abs(fd.pmean - fo.pmean) / fo.psdev) < 1e-5
+    with pytest.raises(ValueError, match="unkown algorithm"):
+        _device_nist(pr, pr["tol"], policy="gsl", alg="dogleg")
+    with pytest.raises(ValueError, match="unkown scaler"):
+        _device_nist(pr, pr["tol"], scaler="marquardt")           # GSL-only scaler with the scipy policy
+    # maxit counts iterations with this policy; too few = stopping_criterion 0 + an error message, not an exception
+    f3 = _device_nist(nist_problems[3], pr["tol"], policy="gsl", maxit=5)
+    assert f3.nit == 5 and f3.stopping_criterion == 0 and "5 iterations" in f3.error
