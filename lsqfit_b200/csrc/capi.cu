@@ -74,6 +74,15 @@ static int default_team(b200lm_handle_s* h) {
     return 1;
 }
 
+// shapes the wave kernel takes (lm_wave.cuh): one correlated block of <= 64 points, every other entry a 1x1 prior
+// row, np <= 16, the scipy policy
+static bool wave_ok(b200lm_handle_s* h) {
+    if (!h->fe->fit_wave || h->policy != 0 || h->np > 16 || h->nblk != 1 || h->nd_fn != 0) return false;
+    const auto& b = h->h_blk[0];
+    if (b.n_in > 64 || b.n_out > 64 || b.n_out < 1) return false;
+    return h->fe->wave_bytes(h->wt_total) <= h->smem_budget;
+}
+
 #define CUDA_TRY(h, call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(h, e_, what); } while (0)
 
 template <class T>
@@ -295,7 +304,17 @@ int b200lm_fit_batch(b200lm_handle h, int B,
     int team = default_team(h);
     if (const char* env = getenv("B200LM_TEAM")) team = atoi(env);
     const int ti = team == 4 ? 1 : (team == 2 ? 0 : -1);
-    if (ti >= 0 && h->fe->fit_team[ti] &&
+    if (team == 32 && wave_ok(h)) {
+        // wave kernel: the trust-region loops of 32 fits per CTA in lock step, then covariance / log det / f / J
+        // (and polish) of every fit by the one-warp kernel in finalize_only mode
+        P.team = 32;
+        CUDA_TRY(h, h->fe->fit_wave(P, h->sm_count, h->smem_budget, s), "wave kernel launch");
+        CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s), "reset work queue");
+        FitParams Q = P;
+        Q.finalize_only = 1; Q.p0 = d_x; Q.p0_stride = h->np; Q.team = 1;
+        CUDA_TRY(h, h->fe->fit(Q, h->sm_count, h->smem_budget, s), "finalize kernel launch");
+        h->launches += 1;
+    } else if (ti >= 0 && h->fe->fit_team[ti] &&
         h->fe->team_bytes[ti](h->N) <= h->smem_budget) {
         P.team = team;
         CUDA_TRY(h, h->fe->fit_team[ti](P, h->sm_count, h->smem_budget, s), "fit kernel launch");
@@ -332,7 +351,8 @@ int b200lm_last_team(b200lm_handle h) { return h ? h->last_team : B200LM_EINVAL;
 
 int b200lm_set_team(b200lm_handle h, int team) {
     if (!h) return set_error(h, B200LM_EINVAL, "NULL handle");
-    if (team != 0 && team != 1 && team != 2 && team != 4) return set_error(h, B200LM_EINVAL, "team must be 0 (default), 1, 2 or 4");
+    if (team != 0 && team != 1 && team != 2 && team != 4 && team != 32)
+        return set_error(h, B200LM_EINVAL, "team must be 0 (default), 1, 2, 4 or 32 (wave kernel)");
     h->team_request = team;
     return B200LM_OK;
 }

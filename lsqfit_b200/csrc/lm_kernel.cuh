@@ -1032,6 +1032,7 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
         int nfev = 1, njev = 1, nfac = 0;
         int status = -2;                         // -2: running
         if (!isfinite(cost)) status = -1;
+        else if (P.finalize_only) status = P.status[b];      // the wave kernel has done the trust-region loop (lm_wave.cuh)
         // scale_inv_j = |J_j| = sqrt(A_jj)   (More': running max; scaler 0: 1)
         double sinv = 1.0;
         if (act && P.scaler == 1) {
@@ -1327,10 +1328,15 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
         if (act) P.x_out[(size_t)b * NP + lane] = c.p[lane];
         if (lane == 0) {
             P.chi2[b] = 2.0 * cost;
-            P.nit[b] = nit_report >= 0 ? nit_report : nfev;
-            P.status[b] = status;
+            if (!P.finalize_only) {
+                P.nit[b] = nit_report >= 0 ? nit_report : nfev;
+                P.status[b] = status;
+            } else if (nfev > 1) {
+                P.nit[b] += nfev - 1;                        // polish steps
+            }
             if (P.logdet) P.logdet[b] = ld;
         }
+        if (P.finalize_only) { --nfev; --njev; }
         tot_nfev += nfev; tot_njev += njev; tot_nfac += nfac;
         pk.total += B200LM_CLOCK() - t_fit0;
         __syncwarp();

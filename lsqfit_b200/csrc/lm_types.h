@@ -53,6 +53,7 @@ struct FitParams {
     int maxit;
     int scaler;                 // 0: none (scipy x_scale=1), 1: More' (scipy 'jac', GSL 'more')
     int polish;                 // max Gauss-Newton refinement steps after the trust-region loop stops
+    int finalize_only;          // 1: the fits are done (d_x = solutions, status given): only covariance, log det, f / J, polish
     int policy;                 // 0: scipy TRF decisions (src/lsqfit/_scipy.py:156-161); 1: GSL trust/lm decisions
                                 // (gsl_multifit_nlinear behind src/lsqfit/_gsl.pyx:563-723; scaler 2 = marquardt)
     // ---- outputs (any of f_out, J_out, cov, logdet may be null) ----------------

@@ -17,6 +17,9 @@ struct FunctorEntry {
     // NULL where the functor has no team instantiation
     cudaError_t (*fit_team[2])(FitParams, int sm_count, size_t smem_budget, cudaStream_t);
     size_t (*team_bytes[2])(int N);
+    // wave kernel (lm_wave.cuh: 32 fits per CTA in lock-step phases); NULL where the functor has none
+    cudaError_t (*fit_wave)(FitParams, int sm_count, size_t smem_budget, cudaStream_t);
+    size_t (*wave_bytes)(int wt_total);
 };
 
 const FunctorEntry* registry_multiexp(int* n);
@@ -31,17 +34,19 @@ const FunctorEntry* registry_misc_b(int* n);
 #ifdef B200LM_DEFINE_ENTRIES
 #include "lm_kernel.cuh"
 #include "lm_team.cuh"
+#include "lm_wave.cuh"
 #include "functors.cuh"
 namespace b200lm {
 template <class F>
 size_t per_warp_bytes_of(int rb) { return (size_t)FitLayout<F>::per_warp_doubles(rb) * sizeof(double); }
 #define B200LM_ENTRY(family, name, ...) \
     { family, __VA_ARGS__::NP, __VA_ARGS__::NX, name, &launch_fit<__VA_ARGS__>, &launch_resjac<__VA_ARGS__>, \
-      &per_warp_bytes_of<__VA_ARGS__>, {nullptr, nullptr}, {nullptr, nullptr} }
+      &per_warp_bytes_of<__VA_ARGS__>, {nullptr, nullptr}, {nullptr, nullptr}, nullptr, nullptr }
 // entry with team kernels (2 and 4 warps per fit)
 #define B200LM_ENTRY_TEAM(family, name, ...) \
     { family, __VA_ARGS__::NP, __VA_ARGS__::NX, name, &launch_fit<__VA_ARGS__>, &launch_resjac<__VA_ARGS__>, \
       &per_warp_bytes_of<__VA_ARGS__>, {&launch_fit_team<__VA_ARGS__, 2>, &launch_fit_team<__VA_ARGS__, 4>}, \
-      {&team_bytes_of<__VA_ARGS__, 2>, &team_bytes_of<__VA_ARGS__, 4>} }
+      {&team_bytes_of<__VA_ARGS__, 2>, &team_bytes_of<__VA_ARGS__, 4>}, &launch_fit_wave<__VA_ARGS__>, \
+      &wave_bytes_of<__VA_ARGS__> }
 }  // namespace b200lm
 #endif

@@ -27,8 +27,20 @@ def _copies(cfg, pdf, B, seed, vary_prior):
     return configs.bootstrap_means(cfg, B, seed, cov=pdf.cov[:ny, :ny], vary_prior=vary_prior)
 
 
+_ORACLE_CACHE = {}
+
+
+def _oracle_cached(K, means, p0, tol, **kw):
+    """the oracle's 2000 fits are the expensive part of this test: run them once per (K, settings), for every kernel"""
+    key = (K, tuple(tol), tuple(sorted(kw.items())))
+    if key not in _ORACLE_CACHE:
+        _ORACLE_CACHE[key] = oracle_correlator_fits(K, means, p0, tol, **kw)
+    return _ORACLE_CACHE[key]
+
+
+@pytest.mark.parametrize("team", [None, 32], ids=["default-kernel", "wave-kernel"])
 @pytest.mark.parametrize("K,vary_prior,p0kind", [(8, True, "prior"), (3, False, "exact")])
-def test_correlator_2000_copies_at_bench_settings(K, vary_prior, p0kind):
+def test_correlator_2000_copies_at_bench_settings(K, vary_prior, p0kind, team):
     """C3 (K=8: bootstrap copies, p0 = prior mean) and C4 (K=3: simulated copies, prior means fixed, p0 = pexact) on
     2000 copies.
 
@@ -39,6 +51,8 @@ def test_correlator_2000_copies_at_bench_settings(K, vary_prior, p0kind):
     case in brackets): chi2 to 1e-8 relative, second order in that distance [7e-10]; p within 1e-3 sdev for every
     copy [2.9e-4], 2e-4 for 99 % of them [5.7e-5], 1e-5 for half of them [3e-7]; covariance to 1e-3 [4.3e-4]; the same
     copies converge; evaluation counts equal on >= 75 % of the copies [81 %; mean 23.47 vs 23.45].
+    Run for the default kernel (team of four warps per fit for K = 8, one warp for K = 3) and for the wave kernel
+    (lm_wave.cuh: 32 fits per CTA in lock-step phases, thread-level factorisations, chunk GEMM on the tensor path).
     (2) THE NORTH-STAR BARS -- both sides at tight tolerance, device with polish, against the exact stationary
     point of the oracle's chi2 (oracle result refined by Gauss-Newton until its own step is below 1e-10 sdev; at
     least 99 % of the copies): p 1e-8 sdev, chi2 1e-9, covariance 1e-8, log det 1e-8."""
@@ -49,10 +63,12 @@ def test_correlator_2000_copies_at_bench_settings(K, vary_prior, p0kind):
     ny, npar = cfg["ny"], cfg["np"]
     p0 = cfg["prior_mean"].copy() if p0kind == "prior" else cfg["ptrue"].copy()
     means = _copies(cfg, opdf, B, 4242 + K, vary_prior)
-    plan = lb.Plan("multiexp", npar, ny, cfg["x"], opdf.i_invwgts)            # the ORACLE's whitening: identical inputs
+    plan = lb.Plan("multiexp", npar, ny, cfg["x"], opdf.i_invwgts, team=team)   # the ORACLE's whitening: identical inputs
     # ---- (1) bench settings
     out = plan.fit_batch(means, p0, tol=BENCH_TOL, maxit=1000).numpy()
-    ref = oracle_correlator_fits(K, means, p0, BENCH_TOL, maxit=1000)
+    ref = _oracle_cached(K, means, p0, BENCH_TOL, maxit=1000)
+    if team is not None:
+        assert plan.last_team() == team
     conv_d = out["status"] > 0
     conv_o = np.array([r["crit"] != 0 for r in ref])
     assert np.array_equal(conv_d, conv_o), (int(conv_d.sum()), int(conv_o.sum()))
@@ -74,7 +90,7 @@ def test_correlator_2000_copies_at_bench_settings(K, vary_prior, p0kind):
     assert nit_eq >= 0.75
     # ---- (2) tight tolerance + polish vs the exact stationary point
     outp = plan.fit_batch(means, p0, tol=TIGHT, maxit=2000, polish=3000).numpy()
-    refe = oracle_correlator_fits(K, means, p0, TIGHT, maxit=2000, refine=True)
+    refe = _oracle_cached(K, means, p0, TIGHT, maxit=2000, refine=True)
     worst = dict(p=0.0, chi2=0.0, cov=0.0, logdet=0.0, ref_gap=0.0)
     n = 0
     dps, lasts = [], []
