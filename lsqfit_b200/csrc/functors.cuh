@@ -36,6 +36,7 @@ enum FunctorFamily : int {
     F_MISRA1B = 15, F_MISRA1C = 16, F_MISRA1D = 17, F_KIRBY2 = 18, F_HAHN1 = 19,
     F_NELSON = 20, F_MGH17 = 21, F_ROSZMAN1 = 22, F_ENSO = 23, F_MGH09 = 24,
     F_RAT42 = 25, F_MGH10 = 26, F_ECKERLE4 = 27, F_RAT43 = 28, F_BENNETT5 = 29,
+    F_SPLINE_POLY = 30,
 };
 
 // ---------------------------------------------------------------------------
@@ -364,5 +365,67 @@ B200LM_BODY(Rat43Body) { return b[0] / pow(1.0 + exp(b[1] - b[2] * x[0]), 1.0 / 
 B200LM_BODY(Bennett5Body) { return b[0] * pow(b[1] + x[0], -1.0 / b[2]); } };
 
 #undef B200LM_BODY
+
+// ---------------------------------------------------------------------------
+// Monotonic cubic spline (Steffen 1990) through FITTED knots + even powers: the model of examples/spline.py:50-60,
+//     f(m, am) = CSpline(mknot, fknot)(m) + sum_i c_i am^(2 + 2 i),     params [mknot(NK), fknot(NK), c(NCF)],  x = (m, am).
+// gvar.cspline.CSpline (third party, not vendored) defaults to Steffen's algorithm with Steffen's own end slopes and
+// continues the end cubics outside the knots (extrap_order = 3); restated in oracle/models.py and PINNED there by
+// examples/spline.out (logGBF = 9.2202 and every printed parameter).  Knots are parameters, so slopes, interval
+// search and the min/sign selections are differentiated through by the dual numbers (selections by value).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double valof(double a) { return a; }
+template <int N> __device__ __forceinline__ double valof(const Dual<N>& a) { return a.v; }
+template <class T> __device__ __forceinline__ T abs_sel(const T& a) { return valof(a) < 0.0 ? -a : a; }
+template <class T> __device__ __forceinline__ T min_sel(const T& a, const T& b) { return valof(a) <= valof(b) ? a : b; }
+__device__ __forceinline__ double sign_of(double v) { return v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0); }
+
+template <int NK, int NCF>
+struct SplinePolyBody {
+    static_assert(NK >= 3, "Steffen's end slopes need three knots");
+    // end slope from the parabola through the three outermost knots, limited as in Steffen's paper
+    template <class T>
+    __device__ __forceinline__ static T end_slope(const T& s0, const T& s1, const T& h0, const T& h1) {
+        const T r = h0 / (h0 + h1);
+        const T pe = s0 * (1.0 + r) - s1 * r;
+        if (valof(pe) * valof(s0) <= 0.0) return pe * 0.0;
+        if (fabs(valof(pe)) > 2.0 * fabs(valof(s0))) return s0 * 2.0;
+        return pe;
+    }
+    template <class T>
+    __device__ __forceinline__ static T eval(const double* __restrict__ x, const T* p) {
+        T h[NK - 1], sl[NK - 1], yp[NK];
+#pragma unroll
+        for (int j = 0; j < NK - 1; ++j) { h[j] = p[j + 1] - p[j]; sl[j] = (p[NK + j + 1] - p[NK + j]) / h[j]; }
+#pragma unroll
+        for (int j = 1; j < NK - 1; ++j) {
+            const T pj = (sl[j - 1] * h[j] + sl[j] * h[j - 1]) / (h[j - 1] + h[j]);
+            const T m = min_sel(min_sel(abs_sel(sl[j - 1]), abs_sel(sl[j])), abs_sel(pj) * 0.5);
+            yp[j] = m * (sign_of(valof(sl[j - 1])) + sign_of(valof(sl[j])));
+        }
+        yp[0] = end_slope(sl[0], sl[1], h[0], h[1]);
+        yp[NK - 1] = end_slope(sl[NK - 2], sl[NK - 3], h[NK - 2], h[NK - 3]);
+        const double xv = x[0];
+        int iv = 0;
+#pragma unroll
+        for (int k = 1; k < NK - 1; ++k) iv = (xv > valof(p[k])) ? k : iv;
+        T f = p[NK] * 0.0;
+#pragma unroll
+        for (int j = 0; j < NK - 1; ++j) {
+            if (iv == j) {
+                const T t = xv - p[j];
+                const T a = (yp[j] + yp[j + 1] - sl[j] * 2.0) / (h[j] * h[j]);
+                const T b = (sl[j] * 3.0 - yp[j] * 2.0 - yp[j + 1]) / h[j];
+                f = ((a * t + b) * t + yp[j]) * t + p[NK + j];
+            }
+        }
+        const double am2 = x[1] * x[1];
+        double pw = am2;
+#pragma unroll
+        for (int i = 0; i < NCF; ++i) { f = f + p[2 * NK + i] * pw; pw *= am2; }
+        return f;
+    }
+};
+template <int NK, int NCF> using SplinePoly = ADFunctor<SplinePolyBody<NK, NCF>, 2 * NK + NCF, 2>;
 
 }  // namespace b200lm

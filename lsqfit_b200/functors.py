@@ -16,9 +16,9 @@ FAMILY = dict(
     multiexp_shared2=8, multiexp_shared3=9,
     misra1a=10, chwirut=11, lanczos=12, gauss=13, danwood=14, misra1b=15, misra1c=16,
     misra1d=17, kirby2=18, hahn1=19, nelson=20, mgh17=21, roszman1=22, enso=23, mgh09=24,
-    rat42=25, mgh10=26, eckerle4=27, rat43=28, bennett5=29,
+    rat42=25, mgh10=26, eckerle4=27, rat43=28, bennett5=29, spline_poly=30,
 )
-NX = dict(simple=2, nelson=2, multiexp_shared2=2, multiexp_shared3=2)          # every other family reads one x column
+NX = dict(simple=2, nelson=2, multiexp_shared2=2, multiexp_shared3=2, spline_poly=2)          # every other family reads one x column
 
 # NIST StRD problem name -> functor family (examples/nist.py)
 NIST_FORM = dict(
@@ -93,6 +93,38 @@ def _gauss(x, b):
             + b[5] * np.exp(-(t - b[6]) ** 2 / b[7] ** 2))
 
 
+SPLINE_SHAPES = {13: (4, 5), 8: (4, 0), 12: (6, 0)}      # np -> (knots, polynomial coefficients): csrc/inst_misc_b.cu
+
+
+def _spline_poly(x, p):
+    """host mirror of csrc/functors.cuh: SplinePolyBody (Steffen's monotonic spline through the knots p[:NK], p[NK:2NK],
+    end cubics continued outside, plus sum_i p[2NK+i] am^(2+2i); the model of reference examples/spline.py:50-60)"""
+    x = np.asarray(x, dtype=float)
+    p = np.asarray(p, dtype=float)
+    nk, ncf = SPLINE_SHAPES[len(p)]
+    xk, yk = p[:nk], p[nk:2 * nk]
+    h = np.diff(xk)
+    s = np.diff(yk) / h
+    yp = np.zeros(nk)
+    pi = (s[:-1] * h[1:] + s[1:] * h[:-1]) / (h[:-1] + h[1:])
+    yp[1:-1] = (np.sign(s[:-1]) + np.sign(s[1:])) * np.minimum(np.minimum(np.abs(s[:-1]), np.abs(s[1:])), 0.5 * np.abs(pi))
+
+    def end(s0, s1, h0, h1):
+        r = h0 / (h0 + h1)
+        pe = s0 * (1 + r) - s1 * r
+        return 0.0 if pe * s0 <= 0 else (2 * s0 if abs(pe) > 2 * abs(s0) else pe)
+    yp[0], yp[-1] = end(s[0], s[1], h[0], h[1]), end(s[-1], s[-2], h[-1], h[-2])
+    m = x[:, 0]
+    i = np.clip(np.searchsorted(xk[1:-1], m, side="left"), 0, nk - 2)
+    t = m - xk[i]
+    a = (yp[i] + yp[i + 1] - 2 * s[i]) / h[i] ** 2
+    b = (3 * s[i] - 2 * yp[i] - yp[i + 1]) / h[i]
+    f = ((a * t + b) * t + yp[i]) * t + yk[i]
+    for k in range(ncf):
+        f = f + p[2 * nk + k] * x[:, 1] ** (2 + 2 * k)
+    return f
+
+
 _HOST = dict(
     multiexp=_multiexp,
     multiexp_de=_multiexp_de,
@@ -104,6 +136,7 @@ _HOST = dict(
     exp_poly=lambda x, p: np.exp(-_poly(x, p)),
     xerr_logistic=_xerr,
     gather=lambda x, p: np.asarray(p)[np.asarray(_col(x)).astype(int)],
+    spline_poly=_spline_poly,
     misra1a=lambda x, b: b[0] * (1 - np.exp(-b[1] * _col(x))),
     chwirut=lambda x, b: np.exp(-b[0] * _col(x)) / (b[1] + b[2] * _col(x)),
     lanczos=lambda x, b: (b[0] * np.exp(-b[1] * _col(x)) + b[2] * np.exp(-b[3] * _col(x))

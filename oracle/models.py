@@ -207,11 +207,78 @@ def bennett5(x, b):         # :1291
     return b[0] * (b[1] + _x(x)) ** (-1 / b[2])
 
 
+
+# ---- monotonic cubic spline through fitted knots + even powers (examples/spline.py:50-60) --------------------------
+SPLINE_SHAPES = {13: (4, 5), 8: (4, 0), 12: (6, 0)}          # np -> (knots, polynomial coefficients) compiled on the device
+
+
+def _sel_abs(a):
+    return -a if D.value(a) < 0 else a
+
+
+def _sel_min(a, b):
+    return a if D.value(a) <= D.value(b) else b
+
+
+def _sgn(a):
+    v = float(D.value(a))
+    return 1.0 if v > 0 else (-1.0 if v < 0 else 0.0)
+
+
+def steffen_spline(xk, yk, xs):
+    """gvar.cspline.CSpline(xk, yk)(xs) with gvar's defaults (third party, not vendored; gvar >= 13.1.5 pinned by the
+    reference's setup): ``alg='steffen'`` -- Steffen's monotonic cubic Hermite spline, A&A 239 (1990) 443: interior slopes
+    (sign(s_i-1) + sign(s_i)) min(|s_i-1|, |s_i|, |p_i| / 2), end slopes from the parabola through the three outermost
+    knots limited to [0, 2 s] -- and ``extrap_order=3`` (the end cubics continue outside the knots).  Knots may be dual
+    numbers.  PINNED by examples/spline.out: tests/test_oracle_golden.py::test_spline_golden."""
+    n = len(xk)
+    h = [xk[i + 1] - xk[i] for i in range(n - 1)]
+    s = [(yk[i + 1] - yk[i]) / h[i] for i in range(n - 1)]
+    yp = [None] * n
+    for i in range(1, n - 1):
+        pi = (s[i - 1] * h[i] + s[i] * h[i - 1]) / (h[i - 1] + h[i])
+        yp[i] = _sel_min(_sel_min(_sel_abs(s[i - 1]), _sel_abs(s[i])), 0.5 * _sel_abs(pi)) * (_sgn(s[i - 1]) + _sgn(s[i]))
+
+    def end(s0, s1, h0, h1):
+        r = h0 / (h0 + h1)
+        pe = s0 * (1.0 + r) - s1 * r
+        if float(D.value(pe)) * float(D.value(s0)) <= 0:
+            return pe * 0.0
+        if abs(float(D.value(pe))) > 2 * abs(float(D.value(s0))):
+            return s0 * 2.0
+        return pe
+    yp[0] = end(s[0], s[1], h[0], h[1])
+    yp[-1] = end(s[-1], s[-2], h[-1], h[-2])
+    out = []
+    for xv in xs:
+        i = 0
+        for k in range(1, n - 1):
+            if xv > float(D.value(xk[k])):
+                i = k
+        t = xv - xk[i]
+        a = (yp[i] + yp[i + 1] - s[i] * 2.0) / (h[i] * h[i])
+        b = (s[i] * 3.0 - yp[i] * 2.0 - yp[i + 1]) / h[i]
+        out.append(((a * t + b) * t + yp[i]) * t + yk[i])
+    return out
+
+
+def spline_poly(x, p):
+    """x rows (m, am); p = [mknot(NK), fknot(NK), c(NCF)]:  CSpline(mknot, fknot)(m) + sum_i c_i am^(2 + 2 i)"""
+    x = np.asarray(x, dtype=float)
+    nk, ncf = SPLINE_SHAPES[len(p)]
+    vals = steffen_spline([p[i] for i in range(nk)], [p[nk + i] for i in range(nk)], x[:, 0])
+    res = []
+    for r, v in enumerate(vals):
+        for i in range(ncf):
+            v = v + p[2 * nk + i] * x[r, 1] ** (2 + 2 * i)
+        res.append(v)
+    return D.stack(res) if any(isinstance(v, D.Dual) for v in res) else np.array([float(v) for v in res])
+
 MODELS = dict(
     multiexp=multiexp, multiexp_de=multiexp_de, simple=simple,
     multiexp_shared2=_multiexp_shared(2), multiexp_shared3=_multiexp_shared(3),
     offset_exp=offset_exp, poly=poly, exp_poly=exp_poly,
-    xerr_logistic=xerr_logistic, gather=gather,
+    xerr_logistic=xerr_logistic, gather=gather, spline_poly=spline_poly,
     misra1a=misra1a, chwirut=chwirut, lanczos=lanczos, gauss=gauss,
     danwood=danwood, misra1b=misra1b, misra1c=misra1c, misra1d=misra1d,
     kirby2=kirby2, hahn1=hahn1, nelson=nelson, mgh17=mgh17,

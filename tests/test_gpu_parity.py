@@ -894,3 +894,45 @@ def test_gsl_policy_vs_oracle(nist_problems):
     # maxit counts iterations with this policy; too few = stopping_criterion 0 + an error message, not an exception
     f3 = _device_nist(nist_problems[3], pr["tol"], policy="gsl", maxit=5)
     assert f3.nit == 5 and f3.stopping_criterion == 0 and "5 iterations" in f3.error
+
+
+@pytest.mark.parametrize("policy", ["trf", "gsl"])
+def test_spline_golden(policy):
+    """examples/spline.py on the device: the `spline_poly` functor (Steffen's monotonic spline through FITTED knots, the
+    default of gvar.cspline.CSpline, + even powers; 13 parameters, 12 correlated points).  Printed values of
+    examples/spline.out, the oracle at tight tolerance, residuals and Jacobian element-wise."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from oracle import gvfmt, dual as D
+    from oracle.fit import nonlinear_fit as ofit
+    from test_oracle_golden import _spline_problem
+    g, x = _spline_problem()
+    ycov, o = np.array(g["ycov"]), g["out"]
+    fit = lb.nonlinear_fit(data=(x, g["ymean"], ycov), prior=(g["prior_mean"], g["prior_sdev"]), fcn="spline_poly", policy=policy)
+    assert fit.error is None and fit.dof == o["dof"]
+    assert gvfmt.agrees_g(fit.chi2 / fit.dof, o["chi2_dof"], 2)
+    assert gvfmt.agrees_g(fit.Q, o["Q"], 2)
+    assert gvfmt.agrees_g(fit.logGBF, o["logGBF"], 5)
+    for mu, sd, e in zip(fit.pmean, fit.p_sdev, o["params"]):
+        assert gvfmt.agrees(mu, sd, e, slack=1.01), (mu, sd, e)
+    if policy == "gsl":
+        assert abs(fit.nit - o["nit"]) <= 1, fit.nit
+    fo = ofit("spline_poly", x, g["ymean"], ycov, prior_mean=g["prior_mean"], prior_cov=g["prior_sdev"], tol=TIGHT, x_scale="jac")
+    xe, fe, Je, cove = exact_minimum(fo)
+    fd = lb.nonlinear_fit(data=(x, g["ymean"], ycov), prior=(g["prior_mean"], g["prior_sdev"]), fcn="spline_poly",
+                          tol=(1e-14, 0.0, 0.0), polish=8, policy=policy)
+    assert np.max(np.abs(fd.pmean - xe) / fo.psdev) < 1e-8
+    assert abs(fd.chi2 - fe @ fe) <= 1e-9 * (fe @ fe)
+    assert _rel_cov(fd.cov, cove) < 1e-8
+    # chiv and its Jacobian at the solution and at the prior mean (knots are parameters: the interval search, the
+    # min / sign selections of the slopes and the end conditions are all differentiated through)
+    plan = fd._spec.plan(0)
+    P = np.array([xe, g["prior_mean"]])
+    f, J, _ = plan.residual_jacobian(P, fo.yp_pdf.mean)
+    for b in range(2):
+        fo_b = np.asarray(fo._chiv(P[b]))
+        Jo_b = D.deriv(fo._chiv(D.Dual.variables(P[b])), 13)
+        # (the device whitening is its own eigen-decomposition: compare chi2 and J^T J, which do not depend on the basis)
+        np.testing.assert_allclose(f[b].cpu().numpy() @ f[b].cpu().numpy(), fo_b @ fo_b, rtol=1e-10)
+        Jd = J[b].cpu().numpy()
+        np.testing.assert_allclose(Jd.T @ Jd, Jo_b.T @ Jo_b, rtol=1e-9, atol=1e-9 * np.max(np.abs(Jo_b.T @ Jo_b)))

@@ -64,7 +64,7 @@ def test_model_jacobians_fd():
                 "misra1d": 2, "kirby2": 5, "hahn1": 7, "nelson": 3, "mgh17": 5,
                 "roszman1": 4, "enso": 9, "mgh09": 4, "rat42": 3, "mgh10": 3,
                 "eckerle4": 3, "rat43": 4, "bennett5": 3, "gather": 3,
-                "multiexp_shared2": 6, "multiexp_shared3": 8}[name]
+                "multiexp_shared2": 6, "multiexp_shared3": 8, "spline_poly": 13}[name]
         ny = 7
         x = rng.uniform(0.5, 2.0, size=(ny, 2))
         if name == "simple":
@@ -74,6 +74,8 @@ def test_model_jacobians_fd():
         if name.startswith("multiexp_shared"):
             x[:, 1] = [0, 1, 1, 0, 1, 0, int(name[-1]) - 1]
         p = rng.uniform(0.5, 1.5, size=npar)
+        if name == "spline_poly":
+            p[:4] = [0.6, 1.0, 1.4, 1.9]                  # knots in increasing order, data on both sides of them
         f, G = M.value_and_jacobian(name, x, p)
         for j in range(npar):
             h = 1e-6 * max(1.0, abs(p[j]))
@@ -366,3 +368,32 @@ def test_gsl_lm_iteration_counts(nist_problems):
         if pr["name"] != "lanczos1":
             assert gvfmt.agrees_g(fit.logGBF, o["logGBF"], 5), pr["name"]
     assert exact >= 18 and close >= 23, (exact, close)
+
+
+def _spline_problem():
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spline.json")))
+    m = np.concatenate([g["param"][k][0] * np.array(g["param"][k][1]) for k in "ABC"])
+    am = np.concatenate([np.array(g["param"][k][1]) for k in "ABC"])
+    return g, np.stack([m, am], axis=1)
+
+
+@pytest.mark.parametrize("fitter", ["scipy", "gsl"])
+def test_spline_golden(fitter):
+    """examples/spline.out: 12 correlated points, 13 parameters of which 8 are the knots of a gvar.cspline.CSpline.
+    PINS the restatement of gvar's default spline (Steffen's monotonic cubic, oracle/models.py: steffen_spline):
+    chi2/dof, Q, logGBF = 9.2202 and all printed parameters; with the GSL restatement also the 9 iterations."""
+    from oracle.gsl_lm import gsl_multifit
+    from oracle.fitter import scipy_least_squares
+    g, x = _spline_problem()
+    fit = nonlinear_fit("spline_poly", x, g["ymean"], np.array(g["ycov"]), prior_mean=g["prior_mean"], prior_cov=g["prior_sdev"],
+                        fitter=gsl_multifit if fitter == "gsl" else scipy_least_squares)
+    o = g["out"]
+    assert fit.dof == o["dof"] and fit.error is None
+    assert gvfmt.agrees_g(fit.chi2 / fit.dof, o["chi2_dof"], 2)
+    assert gvfmt.agrees_g(fit.Q, o["Q"], 2)
+    assert gvfmt.agrees_g(fit.logGBF, o["logGBF"], 5)
+    for mu, sd, e in zip(fit.pmean, fit.p_sdev, o["params"]):
+        assert gvfmt.agrees(mu, sd, e, slack=1.01), (mu, sd, e)
+    if fitter == "gsl":
+        assert abs(fit.nit - o["nit"]) <= 1, fit.nit
