@@ -184,6 +184,20 @@ int b200lm_dgemm(int device, int transA, int transB, int batch, int M, int N, in
                  const double* d_A, long long sA, int lda, const double* d_B, long long sB, int ldb,
                  double beta, double* d_C, long long sC, int ldc, void* stream);
 
+/* ---- single-fit row kernels: ONE fit, parallel over its data rows ----------------------------
+ * Un-whitened model rows of the handle's functor at d_p[np]:  d_G (ny x np, leading dimension ld >= np; NULL for a
+ * residual-only evaluation) = df/dp,  d_delta[ny] = f(p) - d_y.  Replaces fcn(x, p) on GVars and the delta of
+ * src/lsqfit/_utilities.pyx:76-77 for any registered functor; the dense path multiplies by the whitening with
+ * b200lm_dgemm.  Needs b200lm_set_const only. */
+int b200lm_model_rows(b200lm_handle h, const double* d_p, const double* d_y, double* d_G, int ld, double* d_delta,
+                      void* stream);
+/* Uncorrelated data (1x1 weights d_w[ny] = 1/sigma, src/lsqfit/_utilities.pyx:85-89), np <= 8: one pass over the rows
+ * gives d_out = [ packed upper triangle of J^T J (row-major, i <= j) | J^T r (np) | r^T r ] for r = w (f(p) - y) --
+ * the normal equations of a fit with millions of points and a handful of parameters (examples/uncorrelated.py:30-41).
+ * HBM bound (x, y, w are read once); deterministic (fixed-order reduction). */
+int b200lm_normal_diag(b200lm_handle h, const double* d_p, const double* d_y, const double* d_w, double* d_out,
+                       void* stream);
+
 /* ---- dense single-fit path (config 5: np in the thousands) ------------------------------
  * Multi-exponential correlator with K exponentials: un-whitened model rows at parameters
  * d_p = [a_0..a_K-1, E_0..E_K-1]:  d_G (ny x 2K, leading dimension ld >= 2K; may be NULL for a

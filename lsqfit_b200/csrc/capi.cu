@@ -44,6 +44,17 @@ void fill_params(b200lm_handle_s* h, FitParams& P) {
 }
 }  // namespace b200lm
 
+namespace b200lm {
+// fixed-order sum of the per-CTA partial rows of normal_diag_kernel (lm_rows.cuh): deterministic results
+__global__ void sum_partials_kernel(int nparts, int nacc, const double* __restrict__ partial, double* __restrict__ out) {
+    for (int k = threadIdx.x; k < nacc; k += blockDim.x) {
+        double v = 0.0;
+        for (int q = 0; q < nparts; ++q) v += partial[(size_t)q * nacc + k];
+        out[k] = v;
+    }
+}
+}  // namespace b200lm
+
 static std::vector<FunctorEntry>& registry() {
     static std::vector<FunctorEntry> r;
     if (r.empty()) {
@@ -361,6 +372,43 @@ int b200lm_set_policy(b200lm_handle h, int policy) {
     if (!h) return set_error(h, B200LM_EINVAL, "NULL handle");
     if (policy != 0 && policy != 1) return set_error(h, B200LM_EINVAL, "policy must be 0 (scipy trf) or 1 (gsl lm)");
     h->policy = policy;
+    return B200LM_OK;
+}
+
+// ---- single-fit row kernels (lm_rows.cuh) -------------------------------------------------------------------
+int b200lm_model_rows(b200lm_handle h, const double* d_p, const double* d_y, double* d_G, int ld, double* d_delta,
+                      void* stream) {
+    if (!h) return set_error(h, B200LM_EINVAL, "NULL handle");
+    if (!h->have_const) return set_error(h, B200LM_EINVAL, "b200lm_set_const has not been called");
+    if (!d_p || !d_y || !d_delta || (d_G && ld < h->np)) return set_error(h, B200LM_EINVAL, "bad model_rows argument");
+    CUDA_TRY(h, cudaSetDevice(h->device), "cudaSetDevice");
+    CUDA_TRY(h, h->fe->model_rows(h->ny, h->nx, h->d_x, d_p, d_y, d_G, ld, d_delta, h->sm_count, (cudaStream_t)stream),
+             "model_rows kernel launch");
+    h->last_stream = (cudaStream_t)stream;
+    h->launches += 1;
+    return B200LM_OK;
+}
+
+int b200lm_normal_diag(b200lm_handle h, const double* d_p, const double* d_y, const double* d_w, double* d_out,
+                       void* stream) {
+    if (!h) return set_error(h, B200LM_EINVAL, "NULL handle");
+    if (!h->have_const) return set_error(h, B200LM_EINVAL, "b200lm_set_const has not been called");
+    if (!d_p || !d_y || !d_w || !d_out) return set_error(h, B200LM_EINVAL, "NULL argument");
+    if (!h->fe->normal_diag) return set_error(h, B200LM_ESIZE, "normal_diag needs np <= 8 (use b200lm_model_rows + b200lm_dgemm)");
+    CUDA_TRY(h, cudaSetDevice(h->device), "cudaSetDevice");
+    const int nacc = h->np * (h->np + 1) / 2 + h->np + 1;
+    const int max_parts = 4 * h->sm_count;
+    const size_t need = (size_t)max_parts * nacc * sizeof(double);
+    if (need > h->scratch_bytes) {
+        if (h->d_scratch) cudaFree(h->d_scratch);
+        h->d_scratch = nullptr; h->scratch_bytes = 0;
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_scratch, need), "scratch allocation");
+        h->scratch_bytes = need;
+    }
+    CUDA_TRY(h, h->fe->normal_diag(h->ny, h->nx, h->d_x, d_p, d_y, d_w, h->d_scratch, max_parts, d_out, h->sm_count,
+                                   (cudaStream_t)stream), "normal_diag kernel launch");
+    h->last_stream = (cudaStream_t)stream;
+    h->launches += 2;
     return B200LM_OK;
 }
 

@@ -9,7 +9,8 @@ unbounded TRF (the solver behind src/lsqfit/_scipy.py:156-161) -> covariance and
 on our own kernels through the C ABI:
 
     whitening              b200lm_whiten      (block-Jacobi eigensolver, csrc/whiten_large.cu)
-    model rows [G|delta]   b200lm_multiexp_dense
+    model rows [G|delta]   b200lm_model_rows (any registered functor) / b200lm_multiexp_dense (any number of terms)
+    uncorrelated data      b200lm_normal_diag (J^T J, J^T r, r^T r in one pass over millions of rows)
     W.G, J^T J, J^T f, ... b200lm_dgemm       (FP64 DMMA GEMM)
     chol(d J^T J d + aI)   b200lm_potrf       (blocked, DMMA trailing updates)
     secular-equation solves, (J^T J)^-1        b200lm_trsm
@@ -80,40 +81,78 @@ class _LA(object):
         return X
 
 
-class DenseFit(object):
-    """Least-squares fit of one large multi-exponential model ``f(t) = sum_k a_k exp(-E_k t)``,
-    parameters ``p = [a_0..a_{K-1}, E_0..E_{K-1}]``, to correlated data with Gaussian priors.
+def _dense_weights(pdf, n):
+    """the whitening of a PDF (``i_invwgts``: 1x1 weights + block matrices) as ONE dense [nchiv, n] matrix"""
+    W = np.zeros((pdf.nchiv, n))
+    idx0, w0 = pdf.i_invwgts[0]
+    W[np.arange(len(idx0)), idx0] = w0
+    r = len(idx0)
+    for idx, Wk in pdf.i_invwgts[1:]:
+        W[r:r + Wk.shape[0], idx] = Wk
+        r += Wk.shape[0]
+    return W
 
-    ``data = (t, ymean, ycov)``; ``prior = (pmean, psdev)`` (independent priors).  Attributes follow
-    the reference's ``nonlinear_fit`` (src/lsqfit/__init__.py:665-725): ``pmean psdev cov chi2 dof Q
-    logGBF nit stopping_criterion error svdcut svdn time``; ``p_cov`` / ``D`` are the propagated
-    covariance and derivative matrix of ``fit.p`` (``_getp``, :897-922).
+
+class DenseFit(object):
+    """Least-squares fit of ONE large problem: a model from the device registry (``fcn``: functor name, default
+    ``'multiexp'`` with any number of terms), data with a dense covariance, a block structure or plain standard
+    deviations, Gaussian priors that may be correlated with each other.
+
+    ``data = (x, ymean, ycov)`` with ``ycov`` a matrix, a vector of standard deviations (uncorrelated data: millions of
+    points are fine, nothing of size ny x ny is ever formed -- reference examples/uncorrelated.py:30-41) or None (see
+    ``pdf``); ``prior = (pmean, psdev)`` or ``(pmean, pcov)`` with a covariance MATRIX (reference examples/p-corr.py:44-61).
+    Attributes follow the reference's ``nonlinear_fit`` (src/lsqfit/__init__.py:665-725): ``pmean psdev cov chi2 dof Q
+    logGBF nit stopping_criterion error svdcut svdn time``; ``p_cov`` / ``D`` are the propagated covariance and
+    derivative matrix of ``fit.p`` (``_getp``, :897-922).
     """
 
     def __init__(self, data, prior, p0=None, svdcut=False, eps=False, tol=1e-8, maxit=1000, scaler="more",
-                 polish=0, device=0, pdf=None):
+                 polish=0, device=0, pdf=None, fcn="multiexp"):
         from .fit import resolve_svdcut_eps
+        from .functors import Functor
         svdcut, eps = resolve_svdcut_eps(svdcut, eps)
         t, ymean, ycov = data
-        pm, psd = prior
+        pm, pcov = prior
         la = self.la = _LA(device)
-        self.t = np.asarray(t, dtype=float).reshape(-1)
         ymean = np.asarray(ymean, dtype=float).reshape(-1)
         pm = np.asarray(pm, dtype=float).reshape(-1)
-        psd = np.asarray(psd, dtype=float).reshape(-1)
+        pcov = np.asarray(pcov, dtype=float)
         self.ny, self.np = ymean.size, pm.size
-        if self.np % 2:
-            raise ValueError("multiexp needs an even number of parameters [a..., E...]")
-        self.K = self.np // 2
+        self.functor = fcn if isinstance(fcn, Functor) else Functor(fcn)
         self.tol = normalize_tol(tol)
         self.maxit = int(maxit)
         self.scaler = scaler
         self.times = {}
-        t0 = time.perf_counter()
-        # ---- whitening of the data block(s) on the device (a-1) ----
         dev = la.tdev
+        # ---- the model evaluator: a compiled functor of this size, or the any-size multi-exponential kernel ----
+        self._h = None
+        self.xrows = self.functor.xrows(t, self.ny)
+        compiled = any(f == self.functor.family and n == self.np for f, n, _, _ in _cabi.functor_table())
+        if compiled:
+            self._h = _cabi.handle_t()
+            _cabi.check(_cabi.lib.b200lm_create(self.functor.family, self.ny, self.np, self.functor.nx, 0, la.device,
+                                                C.byref(self._h)))
+            _cabi.check(_cabi.lib.b200lm_set_const(self._h, self.xrows.ctypes.data, self.xrows.size), self._h)
+        elif self.functor.name == "multiexp":
+            if self.np % 2:
+                raise ValueError("multiexp needs an even number of parameters [a..., E...]")
+            self.K = self.np // 2
+            self.t = self.xrows[:, 0].copy()
+        else:
+            raise ValueError("no device functor for %s with np=%d (lsqfit_b200.available() lists the compiled ones)"
+                             % (self.functor.name, self.np))
+        t0 = time.perf_counter()
+        # ---- whitening of the data on the device (a-1): dense block / general block structure / 1x1 weights ----
         ycov = None if ycov is None else np.asarray(ycov, dtype=float)
-        if pdf is None and ycov.ndim == 2 and np.count_nonzero(ycov) == ycov.size:
+        self.Wd = self.wdiag = None
+        if pdf is None and ycov is not None and ycov.ndim <= 1:
+            # uncorrelated data: 1x1 weights (src/lsqfit/_utilities.pyx:85-89), never a matrix
+            sd = np.full(self.ny, float(ycov)) if ycov.ndim == 0 else ycov.reshape(-1)
+            self.wdiag = torch.as_tensor(1.0 / sd).to(dev)
+            self._Cd = torch.as_tensor(sd ** 2).to(dev)          # (diagonal of the data covariance)
+            self.svdcut, self.eps, self.svdn = svdcut, eps, 0
+            nd, data_logdet, data_mean = self.ny, 2.0 * float(np.sum(np.log(sd))), ymean
+        elif pdf is None and ycov.ndim == 2 and np.count_nonzero(ycov) == ycov.size:
             # one fully correlated block: W and the corrected covariance never leave the device
             from .whiten import whiten_blocks
             if svdcut is not None:
@@ -130,39 +169,51 @@ class DenseFit(object):
                 pdf = PDF(ymean, ycov, svdcut=svdcut, eps=eps, device=device)
             self.svdcut, self.eps, self.svdn = pdf.svdcut, pdf.eps, pdf.nmod
             nd = pdf.nchiv
-            Wd = np.zeros((nd, self.ny))
-            idx0, w0 = pdf.i_invwgts[0]
-            Wd[np.arange(len(idx0)), idx0] = w0
-            r = len(idx0)
-            for idx, Wk in pdf.i_invwgts[1:]:
-                Wd[r:r + Wk.shape[0], idx] = Wk
-                r += Wk.shape[0]
-            self.Wd = torch.as_tensor(Wd).to(dev)
+            self.Wd = torch.as_tensor(_dense_weights(pdf, self.ny)).to(dev)
             self._Cd = torch.as_tensor(pdf.cov).to(dev)
             data_logdet = pdf.logdet
             data_mean = pdf.mean
+        # ---- prior: independent (1x1 weights) or correlated (its own whitening, same svdcut / eps) ----
+        self.Wp = self._Cp = None
+        if pcov.ndim <= 1:
+            psd = np.full(self.np, float(pcov)) if pcov.ndim == 0 else pcov.reshape(-1)
+            prior_logdet = 2.0 * float(np.sum(np.log(psd)))
+            npr = self.np
+        else:
+            ppdf = PDF(pm, pcov, svdcut=svdcut, eps=eps, device=device)
+            psd = np.sqrt(np.diag(pcov))
+            self.Wp = torch.as_tensor(_dense_weights(ppdf, self.np)).to(dev)
+            self._Cp = torch.as_tensor(ppdf.cov).to(dev)
+            self.PtP = la.mm(self.Wp, self.Wp, transA=True)
+            self.svdn += ppdf.nmod
+            prior_logdet = ppdf.logdet
+            npr = ppdf.nchiv
         torch.cuda.synchronize(dev)
         self.times["whiten"] = time.perf_counter() - t0
         self.pdf = pdf
         self.nd = nd
-        self.d_t = torch.as_tensor(self.t).to(dev)
+        self.d_x = torch.as_tensor(self.xrows).to(dev)
+        self.d_t = self.d_x[:, 0].contiguous()
         self.d_y = torch.as_tensor(np.ascontiguousarray(data_mean)).to(dev)
         self.d_pm = torch.as_tensor(pm).to(dev)
         self.d_wp = torch.as_tensor(1.0 / psd).to(dev)
         self.prior_mean, self.prior_sdev = pm, psd
-        self.logdet_pdf = data_logdet + 2.0 * float(np.sum(np.log(psd)))
-        self.nchiv = nd + self.np
+        self.logdet_pdf = data_logdet + prior_logdet
+        self.nchiv = nd + npr
         self.dof = self.nchiv - self.np
         # ---- workspaces ----
         n = self.np
+        self.fused = self.wdiag is not None and self._h is not None and n <= 8      # b200lm_normal_diag in the loop
         self.G = la.empty(self.ny, n)
         self.delta = la.empty(self.ny)
-        self.J = la.empty(nd, n)
+        self.J = self.G if self.wdiag is not None else la.empty(nd, n)             # (uncorrelated: J = diag(w) G in place)
         self.A = la.empty(n, n)
         self.As = la.empty(n, n)
         self.L = la.empty(n, n)
         self.linv = la.empty((n + 63) // 64, 64, 64)
         self.info = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.nacc = la.empty(n * (n + 1) // 2 + n + 1)
+        self._triu = torch.triu_indices(n, n, device=dev)
         self.polish = int(polish)
         x0 = pm.copy() if p0 is None else np.asarray(p0, dtype=float).reshape(-1)
         t0 = time.perf_counter()
@@ -171,33 +222,76 @@ class DenseFit(object):
         self.times["fit"] = time.perf_counter() - t0
         self._p_cov = self._D = None
 
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _cabi.lib.b200lm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     # ---- residuals and Jacobian (a-2) -------------------------------------------------------
     def _model(self, p, with_G):
         la = self.la
-        _cabi.check(_cabi.lib.b200lm_multiexp_dense(
-            la.device, self.ny, self.K, self.d_t.data_ptr(), p.data_ptr(), self.d_y.data_ptr(),
-            self.G.data_ptr() if with_G else None, self.G.stride(0), self.delta.data_ptr(), la.stream()))
+        if self._h is not None:
+            _cabi.check(_cabi.lib.b200lm_model_rows(
+                self._h, p.data_ptr(), self.d_y.data_ptr(), self.G.data_ptr() if with_G else None, self.G.stride(0),
+                self.delta.data_ptr(), la.stream()), self._h)
+        else:
+            _cabi.check(_cabi.lib.b200lm_multiexp_dense(
+                la.device, self.ny, self.K, self.d_t.data_ptr(), p.data_ptr(), self.d_y.data_ptr(),
+                self.G.data_ptr() if with_G else None, self.G.stride(0), self.delta.data_ptr(), la.stream()))
         la.launches += 1
 
-    def residual(self, p):
-        """(f_data [nd], f_prior [np]) = whitened residuals at p."""
-        self._model(p, False)
-        fd = self.la.mm(self.Wd, self.delta)
-        fp = (p - self.d_pm) * self.d_wp
-        return fd, fp
+    def _prior_residual(self, p):
+        dp = p - self.d_pm
+        return dp * self.d_wp if self.Wp is None else self.la.mm(self.Wp, dp)
 
-    def jacobian(self, p):
-        """Evaluates J_data = W.G into self.J, the normal matrix into self.A; returns (fd, fp, g)."""
+    def residual(self, p):
+        """(f_data [nd], f_prior) = whitened residuals at p."""
+        self._model(p, False)
+        fd = self.delta * self.wdiag if self.wdiag is not None else self.la.mm(self.Wd, self.delta)
+        return fd, self._prior_residual(p)
+
+    def _add_prior(self, fp, g):
+        if self.Wp is None:
+            self.A.diagonal().add_(self.d_wp ** 2)
+            return g + self.d_wp * fp
+        self.A.add_(self.PtP)
+        return g + self.la.mm(self.Wp, fp, transA=True)
+
+    def jacobian(self, p, materialize=False):
+        """Normal matrix into self.A (and J_data = W.G into self.J unless the fused one-pass kernel is used);
+        returns (fd, fp, g).  In fused mode fd is None and self.cost_data holds f_data . f_data."""
         la = self.la
-        self._model(p, True)
-        fd = la.mm(self.Wd, self.delta)
-        la.mm(self.Wd, self.G, out=self.J)
-        la.mm(self.J, self.J, transA=True, out=self.A)
-        self.A.diagonal().add_(self.d_wp ** 2)
-        fp = (p - self.d_pm) * self.d_wp
-        g = la.mm(self.J, fd, transA=True) + self.d_wp * fp
+        fp = self._prior_residual(p)
         self.nfev_jac += 1
-        return fd, fp, g
+        if self.fused and not materialize:
+            _cabi.check(_cabi.lib.b200lm_normal_diag(self._h, p.data_ptr(), self.d_y.data_ptr(), self.wdiag.data_ptr(),
+                                                     self.nacc.data_ptr(), la.stream()), self._h)
+            la.launches += 2
+            n = self.np
+            nt = n * (n + 1) // 2
+            self.A.zero_()
+            self.A[self._triu[0], self._triu[1]] = self.nacc[:nt]
+            self.A.copy_(self.A + self.A.T - torch.diag(self.A.diagonal()))
+            g = self.nacc[nt:nt + n].clone()
+            self.cost_data = self.nacc[nt + n].clone()
+            return None, fp, self._add_prior(fp, g)
+        self._model(p, True)
+        if self.wdiag is not None:
+            fd = self.delta * self.wdiag
+            self.J.mul_(self.wdiag[:, None])                    # J = diag(w) G, in place (self.J is self.G)
+        else:
+            fd = la.mm(self.Wd, self.delta)
+            la.mm(self.Wd, self.G, out=self.J)
+        la.mm(self.J, self.J, transA=True, out=self.A)
+        g = la.mm(self.J, fd, transA=True)
+        self.cost_data = fd @ fd
+        return fd, fp, self._add_prior(fp, g)
 
     # ---- trust-region sub-problem -------------------------------------------------------------
     def _factor_solve(self, alpha, gs):
@@ -260,11 +354,11 @@ class DenseFit(object):
         self.nfev_jac = self.nfac = 0
         fd, fp, g = self.jacobian(x)
         nfev = 1
-        cost = 0.5 * float(fd @ fd + fp @ fp)
+        cost = 0.5 * float(self.cost_data + fp @ fp)
         more = self.scaler == "more"
 
         def colnorm():
-            return torch.sqrt(torch.sum(self.J * self.J, dim=0) + self.d_wp ** 2)
+            return torch.sqrt(self.A.diagonal())                 # |J_j| over data and prior rows
         if more:
             scale_inv = colnorm()
             scale_inv[scale_inv == 0] = 1.0
@@ -355,6 +449,8 @@ class DenseFit(object):
                     break
                 sh, dec = sh2, dec2
         # ---- results (a-5; src/lsqfit/__init__.py:665-682, 706-725) ----
+        if fd is None:                                           # fused loop: one materialised pass for f, J, covariance
+            fd, fp, g = self.jacobian(x, materialize=True)
         self.nit = nfev
         self.status = status
         self.stopping_criterion = STOPPING_CRITERION[status]
@@ -383,8 +479,12 @@ class DenseFit(object):
         del Js
         A2 = la.mm(Q1, Q1, transA=True)
         del Q1
-        Xp = X * (self.d_wp * d)[None, :]                                # prior rows: diag(wp d) X^T
-        la.mm(Xp, Xp, transB=True, out=A2, beta=1.0)
+        if self.Wp is None:
+            Xp = X * (self.d_wp * d)[None, :]                            # prior rows: diag(wp d) X^T
+            la.mm(Xp, Xp, transB=True, out=A2, beta=1.0)
+        else:
+            Q1p = la.mm(self.Wp * d[None, :], X, transB=True)            # prior rows of Q1
+            la.mm(Q1p, Q1p, transA=True, out=A2, beta=1.0)
         if la.potrf(A2, 0.0, self.L, self.linv, self.info):
             eye = torch.eye(n, dtype=torch.float64, device=la.tdev)
             X2 = la.trsm(self.L, self.linv, 0, eye, la.empty(n, n))
@@ -404,13 +504,20 @@ class DenseFit(object):
         t0 = time.perf_counter()
         n, ny = self.np, self.ny
         M = la.mm(self.d_cov, self.J, transB=True)               # np x nd   = cov . J_data^T
-        Dd = la.mm(M, self.Wd)                                   # np x ny
-        Dp = self.d_cov * self.d_wp[None, :] ** 2                # cov . diag(wp) . diag(wp)
-        Cd = self._Cd                                            # svd-corrected data covariance
-        T = la.mm(Dd, Cd)
-        covp = la.mm(T, Dd, transB=True)
-        Dps = Dp * torch.as_tensor(self.prior_sdev).to(la.tdev)[None, :]
-        la.mm(Dps, Dps, transB=True, out=covp, beta=1.0)
+        if self.wdiag is not None:
+            Dd = M * self.wdiag[None, :]                         # uncorrelated data: W and C are diagonal
+            covp = la.mm(Dd * self._Cd[None, :], Dd, transB=True)
+        else:
+            Dd = la.mm(M, self.Wd)                               # np x ny
+            T = la.mm(Dd, self._Cd)                              # svd-corrected data covariance
+            covp = la.mm(T, Dd, transB=True)
+        if self.Wp is None:
+            Dp = self.d_cov * self.d_wp[None, :] ** 2            # cov . diag(wp) . diag(wp)
+            Dps = Dp * torch.as_tensor(self.prior_sdev).to(la.tdev)[None, :]
+            la.mm(Dps, Dps, transB=True, out=covp, beta=1.0)
+        else:
+            Dp = la.mm(self.d_cov, self.PtP)                     # cov . Wp^T Wp
+            la.mm(la.mm(Dp, self._Cp), Dp, transB=True, out=covp, beta=1.0)
         torch.cuda.synchronize(la.tdev)
         self.times["propagate"] = time.perf_counter() - t0
         self._D = torch.cat([Dd, Dp], dim=1)

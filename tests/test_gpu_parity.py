@@ -936,3 +936,91 @@ def test_spline_golden(policy):
         np.testing.assert_allclose(f[b].cpu().numpy() @ f[b].cpu().numpy(), fo_b @ fo_b, rtol=1e-10)
         Jd = J[b].cpu().numpy()
         np.testing.assert_allclose(Jd.T @ Jd, Jo_b.T @ Jo_b, rtol=1e-9, atol=1e-9 * np.max(np.abs(Jo_b.T @ Jo_b)))
+
+
+def test_dense_fit_generic(golden_examples):
+    """DenseFit beyond the multi-exponential / diagonal-prior case (single-fit path, lsqfit_b200/dense.py):
+    (a) examples/p-corr.out through the dense path: a registry functor (mgh09) + a CORRELATED prior block;
+    (b) the shape of examples/uncorrelated.py (3 parameters, 1e5 uncorrelated points; the reference needs 2 minutes for
+        2e6 of them): the one-pass normal-equation kernel b200lm_normal_diag against the oracle and against the
+        materialised-Jacobian path;
+    (c) 25 polynomial coefficients on 5 points (tests/test_lsqfit.py:878-880): dense path == batched kernel == oracle;
+    (d) the spline model of examples/spline.py with its 12 x 12 data block."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from lsqfit_b200.dense import DenseFit
+    from oracle import gvfmt
+    from oracle.fit import nonlinear_fit as ofit
+    # ---- (a)
+    ex = golden_examples["p-corr"]
+    y = np.array([gvfmt.parse(s)[:2] for s in ex["y"]])
+    fit = DenseFit((np.array(ex["x"]), y[:, 0], y[:, 1]), (ex["prior_mean"], np.array(ex["prior_cov"])), fcn="mgh09")
+    o = ex["out"]
+    assert fit.error is None and fit.dof == o["dof"] and fit.svdn == o["svdn"]
+    assert gvfmt.agrees_g(fit.chi2 / fit.dof, o["chi2_dof"], 2)
+    assert gvfmt.agrees_g(fit.logGBF, o["logGBF"], 5)
+    for m, sd, e in zip(fit.pmean, np.sqrt(np.diag(fit.p_cov)), o["p"]):
+        assert gvfmt.agrees(m, sd, e)
+    C = fit.p_cov
+    assert "%.4f" % (C[0, 1] / np.sqrt(C[0, 0] * C[1, 1])) == o["corr_p0_p1"]
+    fb = lb.nonlinear_fit(data=(np.array(ex["x"]), y[:, 0], y[:, 1]), fcn="mgh09", prior=(ex["prior_mean"], np.array(ex["prior_cov"])))
+    np.testing.assert_allclose(fit.pmean, fb.pmean, rtol=0, atol=1e-4 * np.min(fb.psdev))      # (both at the default tolerances)
+    assert _rel_cov(fit.cov, fb.cov) < 1e-4
+    # ---- (b)
+    rng = np.random.default_rng(12)
+    N = 100000
+    x = np.linspace(0.2, 2.0, N)
+    ptrue = np.array([0.5, 0.4, 0.7])
+    sd = np.full(N, 1e-3)
+    ymean = ptrue[0] + ptrue[1] * np.exp(-ptrue[2] * x) + sd * rng.standard_normal(N)
+    prior = (np.zeros(3), np.ones(3))
+    # the oracle's chiv with 1x1 weights only (src/lsqfit/_utilities.pyx:85-89); oracle.fit.nonlinear_fit would build the
+    # N x N covariance matrix, which is exactly what this path exists to avoid
+    import types
+    from oracle.chiv import Chiv
+    from oracle.fitter import scipy_least_squares
+    from oracle import models as OM
+    opdf = types.SimpleNamespace(mean=np.concatenate([ymean, prior[0]]),
+                                 i_invwgts=[(np.arange(N + 3), 1.0 / np.concatenate([sd, prior[1]]))])
+    chiv = Chiv(opdf, lambda p: OM.MODELS["offset_exp"](x[:, None], p), False)
+    fo = scipy_least_squares(np.array([0.1, 0.1, 0.1]), N + 3, chiv, tol=1e-10, x_scale="jac")
+    o_chi2 = float(fo.f @ fo.f)
+    o_psdev = np.sqrt(np.diag(fo.cov))
+    o_logGBF = 0.5 * (-np.linalg.slogdet(fo.J.T @ fo.J)[1] - 2.0 * np.sum(np.log(np.concatenate([sd, prior[1]]))) - o_chi2
+                      - N * np.log(2 * np.pi))
+    fd = DenseFit((x, ymean, sd), prior, p0=[0.1, 0.1, 0.1], fcn="offset_exp", tol=1e-10)
+    assert fd.fused and fd.error is None and fd.dof == N
+    assert np.max(np.abs(fd.pmean - fo.x) / o_psdev) < 1e-5
+    assert abs(fd.chi2 - o_chi2) <= 1e-9 * o_chi2
+    assert _rel_cov(fd.cov, fo.cov) < 1e-7
+    assert abs(fd.logGBF - o_logGBF) <= 1e-9 * abs(o_logGBF)
+    np.testing.assert_allclose(np.sqrt(np.diag(fd.p_cov)), fd.psdev, rtol=1e-6)      # D C D^T == cov (check_roundoff)
+    # the fused kernel's normal equations == those of the materialised Jacobian
+    p = fd.x
+    g1 = fd.jacobian(p)[2].clone()
+    A1 = fd.A.clone()
+    fdm, _, g2 = fd.jacobian(p, materialize=True)
+    assert float(torch_max_rel(A1, fd.A)) < 1e-12 and float(torch_max_rel(g1, g2, scale=float(fd.A.abs().max()) ** 0.5)) < 1e-9
+    # ---- (c)
+    xs = np.array([0.1, 0.3, 0.5, 0.7, 0.95])
+    ym = np.array([0.5351, 0.6762, 0.9227, 1.3803, 4.0145]); ys = np.array([0.0054, 0.0067, 0.0091, 0.0131, 0.0399])
+    pr = (np.zeros(25), np.full(25, 0.6012))
+    fo = ofit("poly", xs[:, None], ym, ys, prior_mean=pr[0], prior_cov=pr[1], tol=TIGHT, x_scale="jac")
+    fb = lb.nonlinear_fit(data=(xs, ym, ys), fcn="poly", prior=pr, tol=(1e-14, 0, 0), polish=4)
+    fd = DenseFit((xs, ym, ys), pr, fcn="poly", tol=(1e-14, 0, 0), polish=4)
+    for f_ in (fb, fd):
+        assert f_.error is None
+        assert np.max(np.abs(f_.pmean - fo.pmean) / fo.psdev) < 1e-8
+        assert abs(f_.chi2 - fo.chi2) <= 1e-9 * fo.chi2
+        assert _rel_cov(f_.cov, fo.cov) < 1e-8
+    # ---- (d)
+    from test_oracle_golden import _spline_problem
+    g, xsp = _spline_problem()
+    fd = DenseFit((xsp, g["ymean"], np.array(g["ycov"])), (g["prior_mean"], g["prior_sdev"]), fcn="spline_poly")
+    assert gvfmt.agrees_g(fd.logGBF, g["out"]["logGBF"], 5) and gvfmt.agrees_g(fd.chi2 / fd.dof, g["out"]["chi2_dof"], 2)
+
+
+def torch_max_rel(a, b, scale=None):
+    import torch
+    s = float(b.abs().max()) if scale is None else scale
+    return (a - b).abs().max() / s
