@@ -83,8 +83,10 @@ def install(lsqfit):
                 spec.np = len(x0)
             b200_lm.__init__(self, x0, n, f, **kargs)
 
+    from .dense import b200_dense
     lsqfit._build_chiv_chivw = _build_chiv_chivw
     lsqfit.nonlinear_fit.FITTERS["b200_lm"] = b200_lm_plugin
+    lsqfit.nonlinear_fit.FITTERS["b200_dense"] = b200_dense
     lsqfit.b200_lm = b200_lm_plugin
     lsqfit._b200lm_installed = True
     return lsqfit

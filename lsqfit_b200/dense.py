@@ -107,13 +107,26 @@ class DenseFit(object):
     """
 
     def __init__(self, data, prior, p0=None, svdcut=False, eps=False, tol=1e-8, maxit=1000, scaler="more",
-                 polish=0, device=0, pdf=None, fcn="multiexp"):
+                 polish=0, device=0, pdf=None, fcn="multiexp", spec=None):
         from .fit import resolve_svdcut_eps
         from .functors import Functor
         svdcut, eps = resolve_svdcut_eps(svdcut, eps)
-        t, ymean, ycov = data
-        pm, pcov = prior
         la = self.la = _LA(device)
+        self.joint = False
+        if spec is not None:
+            # the plugin route (b200_dense below): everything comes from the ChivSpec of the fitter seam -- the joint
+            # whitening of y (+) prior as ONE matrix [Wy | Wp] (data and prior may be correlated with each other)
+            t, fcn, pdf = spec.x, spec.functor, spec.pdf
+            ymean = np.asarray(pdf.mean, dtype=float)[:spec.ny]
+            pm = np.zeros(spec.np) if spec.noprior else np.asarray(pdf.mean, dtype=float)[spec.ny:]
+            ycov, pcov = None, np.ones(spec.np)
+            self.joint = len(pdf.i_invwgts) > 1             # correlated blocks: one dense matrix; only 1x1 weights: vectors
+            if self.joint and float(pdf.nchiv) * float(len(pdf.mean)) > 1.5e9:
+                raise ValueError("b200_dense: the joint whitening matrix would need %.0f GB; give data and prior to "
+                                 "lsqfit_b200.DenseFit separately" % (8e-9 * pdf.nchiv * len(pdf.mean)))
+        else:
+            t, ymean, ycov = data
+            pm, pcov = prior
         ymean = np.asarray(ymean, dtype=float).reshape(-1)
         pm = np.asarray(pm, dtype=float).reshape(-1)
         pcov = np.asarray(pcov, dtype=float)
@@ -144,8 +157,28 @@ class DenseFit(object):
         t0 = time.perf_counter()
         # ---- whitening of the data on the device (a-1): dense block / general block structure / 1x1 weights ----
         ycov = None if ycov is None else np.asarray(ycov, dtype=float)
-        self.Wd = self.wdiag = None
-        if pdf is None and ycov is not None and ycov.ndim <= 1:
+        self.Wd = self.wdiag = self.Wpj = None
+        if spec is not None and self.joint:
+            N = self.ny if spec.noprior else self.ny + self.np
+            Wfull = torch.as_tensor(_dense_weights(pdf, N)).to(dev)
+            self.Wd = Wfull[:, :self.ny].contiguous()
+            self.Wpj = None if spec.noprior else Wfull[:, self.ny:].contiguous()
+            self._Cfull = torch.as_tensor(np.ascontiguousarray(pdf.cov)).to(dev)
+            self._Cd = None
+            self.svdcut, self.eps, self.svdn = pdf.svdcut, pdf.eps, pdf.nmod
+            nd, data_logdet, data_mean = pdf.nchiv, pdf.logdet, ymean
+        elif spec is not None:
+            # only 1x1 weights (possibly millions of them): data and prior weights straight from the PDF
+            idx0, w0 = pdf.i_invwgts[0]
+            wall = np.empty(len(idx0)); wall[np.asarray(idx0)] = np.asarray(w0, dtype=float)
+            sd = 1.0 / wall[:self.ny]
+            self.wdiag = torch.as_tensor(wall[:self.ny].copy()).to(dev)
+            self._Cd = torch.as_tensor(sd ** 2).to(dev)
+            self.svdcut, self.eps, self.svdn = pdf.svdcut, pdf.eps, 0
+            nd, data_logdet, data_mean = self.ny, 2.0 * float(np.sum(np.log(sd))), ymean
+            if not spec.noprior:
+                pcov = 1.0 / wall[self.ny:]
+        elif pdf is None and ycov is not None and ycov.ndim <= 1:
             # uncorrelated data: 1x1 weights (src/lsqfit/_utilities.pyx:85-89), never a matrix
             sd = np.full(self.ny, float(ycov)) if ycov.ndim == 0 else ycov.reshape(-1)
             self.wdiag = torch.as_tensor(1.0 / sd).to(dev)
@@ -175,7 +208,11 @@ class DenseFit(object):
             data_mean = pdf.mean
         # ---- prior: independent (1x1 weights) or correlated (its own whitening, same svdcut / eps) ----
         self.Wp = self._Cp = None
-        if pcov.ndim <= 1:
+        self.noprior_rows = spec is not None and (self.joint or spec.noprior)      # no separate prior residuals
+        if self.noprior_rows:
+            psd = np.ones(self.np)
+            prior_logdet, npr = 0.0, 0
+        elif pcov.ndim <= 1:
             psd = np.full(self.np, float(pcov)) if pcov.ndim == 0 else pcov.reshape(-1)
             prior_logdet = 2.0 * float(np.sum(np.log(psd)))
             npr = self.np
@@ -196,7 +233,7 @@ class DenseFit(object):
         self.d_t = self.d_x[:, 0].contiguous()
         self.d_y = torch.as_tensor(np.ascontiguousarray(data_mean)).to(dev)
         self.d_pm = torch.as_tensor(pm).to(dev)
-        self.d_wp = torch.as_tensor(1.0 / psd).to(dev)
+        self.d_wp = torch.as_tensor(np.zeros(self.np) if self.noprior_rows else 1.0 / psd).to(dev)
         self.prior_mean, self.prior_sdev = pm, psd
         self.logdet_pdf = data_logdet + prior_logdet
         self.nchiv = nd + npr
@@ -250,11 +287,18 @@ class DenseFit(object):
         dp = p - self.d_pm
         return dp * self.d_wp if self.Wp is None else self.la.mm(self.Wp, dp)
 
+    def _data_residual(self, p):
+        if self.wdiag is not None:
+            return self.delta * self.wdiag
+        fd = self.la.mm(self.Wd, self.delta)
+        if self.Wpj is not None:                                 # joint whitening: the rows also see p - prior mean
+            fd += self.la.mm(self.Wpj, p - self.d_pm)
+        return fd
+
     def residual(self, p):
         """(f_data [nd], f_prior) = whitened residuals at p."""
         self._model(p, False)
-        fd = self.delta * self.wdiag if self.wdiag is not None else self.la.mm(self.Wd, self.delta)
-        return fd, self._prior_residual(p)
+        return self._data_residual(p), self._prior_residual(p)
 
     def _add_prior(self, fp, g):
         if self.Wp is None:
@@ -286,8 +330,10 @@ class DenseFit(object):
             fd = self.delta * self.wdiag
             self.J.mul_(self.wdiag[:, None])                    # J = diag(w) G, in place (self.J is self.G)
         else:
-            fd = la.mm(self.Wd, self.delta)
+            fd = self._data_residual(p)
             la.mm(self.Wd, self.G, out=self.J)
+            if self.Wpj is not None:
+                self.J.add_(self.Wpj)
         la.mm(self.J, self.J, transA=True, out=self.A)
         g = la.mm(self.J, fd, transA=True)
         self.cost_data = fd @ fd
@@ -457,7 +503,7 @@ class DenseFit(object):
         self.error = error
         self.x = x
         self.pmean = x.cpu().numpy()
-        self.f = torch.cat([fd, fp])
+        self.f = fd if self.noprior_rows else torch.cat([fd, fp])
         self.chi2 = float(fd @ fd + fp @ fp)
         from .fit import gammaQ, _logGBF
         self.Q = float(gammaQ(self.dof / 2.0, self.chi2 / 2.0))
@@ -504,6 +550,14 @@ class DenseFit(object):
         t0 = time.perf_counter()
         n, ny = self.np, self.ny
         M = la.mm(self.d_cov, self.J, transB=True)               # np x nd   = cov . J_data^T
+        if self.joint:
+            Wfull = self.Wd if self.Wpj is None else torch.cat([self.Wd, self.Wpj], dim=1)
+            D = la.mm(M, Wfull.contiguous())                     # np x N
+            covp = la.mm(la.mm(D, self._Cfull), D, transB=True)
+            torch.cuda.synchronize(la.tdev)
+            self.times["propagate"] = time.perf_counter() - t0
+            self._D, self._p_cov = D, covp
+            return D, covp
         if self.wdiag is not None:
             Dd = M * self.wdiag[None, :]                         # uncorrelated data: W and C are diagonal
             covp = la.mm(Dd * self._Cd[None, :], Dd, transB=True)
@@ -535,3 +589,46 @@ class DenseFit(object):
         if self._D is None:
             self.propagate()
         return self._D.cpu().numpy()
+
+
+class b200_dense(object):
+    """The single-fit path with the reference's plugin signature (``FITTERS[name](p0, nf, chiv, tol=, maxit=, **fitterargs)``,
+    src/lsqfit/__init__.py:662-664; result attributes as src/lsqfit/_scipy.py:115-181): one fit spread over the whole GPU
+    -- for parameter counts the batched kernels are not compiled for (np > 25 for most models, any np for 'multiexp'), for
+    millions of uncorrelated points, or on request (``fitter='b200_dense'``).  ``b200_lm`` routes here by itself when no
+    batched kernel exists for the model's parameter count.  Extra fitterargs: ``scaler`` ('more' | 'levenberg'), ``device``,
+    ``polish``."""
+
+    def __init__(self, x0, n, f, tol=(1e-8, 1e-10, 1e-10), maxit=1000, scaler="more", device=0, polish=0, **extra_args):
+        if extra_args:
+            raise ValueError("b200_dense: unknown fitter arguments: " + ", ".join(sorted(extra_args)))
+        spec = getattr(f, "b200", None)
+        if spec is None:
+            raise ValueError("the b200_dense fitter needs a device functor: use lsqfit_b200.Functor(...) as fcn "
+                             "and install the hook with lsqfit_b200.register() (no CPU fallback exists)")
+        self.tol, self.maxit, self.n = normalize_tol(tol), maxit, n
+        self.x0 = np.array(x0, dtype=float)
+        if spec.np < 0:
+            spec.np = self.x0.size
+        self.description = "dense    scaler = {}    device = cuda:{}".format(scaler, device)
+        fit = DenseFit(None, None, p0=spec.to_device(self.x0), tol=self.tol, maxit=maxit, scaler=scaler, polish=polish,
+                       device=device, spec=spec)
+        if n != fit.nchiv:
+            raise ValueError("b200_dense: n=%d does not match the whitening (%d residuals)" % (n, fit.nchiv))
+        self.dense = fit
+        if fit.cov is None:
+            self.cov = np.full((spec.np, spec.np), np.nan)
+        x, cov, J = spec.from_device(fit.pmean, fit.cov if fit.cov is not None else self.cov, fit.J.cpu().numpy())
+        self.x, self.cov = x, cov
+        self.f = fit.f.cpu().numpy()
+        # chiv rows: data (+ joint) rows, then the separate 1x1 prior rows
+        if fit.noprior_rows:
+            self.J = J
+        else:
+            Jp = np.diag(1.0 / fit.prior_sdev) if fit.Wp is None else fit.Wp.cpu().numpy()
+            self.J = np.concatenate([J, spec.from_device(J=Jp)[2]], axis=0)
+        self.nit = fit.nit
+        self.logdet_JtJ = getattr(fit, "logdet_JtJ", float("nan"))
+        self.results = dict(status=fit.status, nfev=fit.nit, chi2=fit.chi2, logdet_JtJ=self.logdet_JtJ, times=dict(fit.times))
+        self.stopping_criterion = fit.stopping_criterion
+        self.error = fit.error

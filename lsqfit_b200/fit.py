@@ -67,8 +67,13 @@ def _logGBF(logdet_JtJ, pdf_logdet, chi2, dof):
     return 0.5 * (-logdet_JtJ - pdf_logdet - chi2 - dof * np.log(2. * np.pi))
 
 
+def _dense_plugin(*args, **kargs):
+    from .dense import b200_dense
+    return b200_dense(*args, **kargs)
+
+
 class nonlinear_fit(object):
-    FITTERS = {"b200_lm": b200_lm}
+    FITTERS = {"b200_lm": b200_lm, "b200_dense": _dense_plugin}
 
     def __init__(self, data=None, fcn=None, prior=None, p0=None, svdcut=False, eps=False,
                  tol=1e-8, maxit=1000, fitter="b200_lm", yp_cov=None, _yp_pdf=None,
@@ -158,11 +163,19 @@ class nonlinear_fit(object):
         self.logGBF = None if noprior else _logGBF(fit.logdet_JtJ, pdf.logdet, self.chi2, self.dof)
         self._p = None
         self._L = None
+        self._dense = getattr(fit, "dense", None)            # single-fit path: its own propagation kernels
         self._spec = spec
         self.time = time.perf_counter() - clock
 
     # ---- fit.p : __init__.py:897-922 ---------------------------------------------------
     def _getp(self):
+        if self._p is None and self._dense is not None:
+            D, covp = self._dense.propagate()
+            D, covp = D.cpu().numpy(), covp.cpu().numpy()
+            if self._spec.pperm is not None:
+                inv = self._spec._inv()
+                D, covp = D[inv], covp[inv][:, inv]
+            self._D, self._p = D, (self.pmean, covp)
         if self._p is None:
             plan = self._spec.plan(self.device)
             D, covp = plan.propagate(self.pmean.reshape(1, -1), self.cov.reshape(1, -1), self.yp_pdf.cov)

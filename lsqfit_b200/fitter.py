@@ -189,6 +189,20 @@ class b200_lm(object):
             self.description = "methods = {}/{}/{}    device = cuda:{}".format(alg, scaler, solver, device)
         else:
             self.description = "scaler = {}    device = cuda:{}".format(scaler, device)
+        from ._cabi import B200LMError, functor_table
+        if spec.np < 0:
+            spec.np = self.x0.size
+        if not any(fam == spec.functor.family and m == spec.np for fam, m, _, _ in functor_table()):
+            # no batched kernel for this parameter count: one fit over the whole GPU instead (lsqfit_b200/dense.py)
+            if gsl:
+                raise ValueError("b200_lm: policy='gsl' needs a batched kernel; none is compiled for %s with np=%d"
+                                 % (spec.functor.name, spec.np))
+            from .dense import b200_dense
+            d = b200_dense(x0, n, f, tol=tol, maxit=maxit, scaler=scaler, device=device, polish=polish)
+            for k in ("x", "cov", "f", "J", "nit", "logdet_JtJ", "results", "stopping_criterion", "error", "dense"):
+                setattr(self, k, getattr(d, k))
+            self.description = d.description
+            return
         plan = spec.plan(device)
         if n != plan.nchiv:
             raise ValueError("b200_lm: n=%d does not match the whitening (%d residuals)" % (n, plan.nchiv))

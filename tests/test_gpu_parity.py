@@ -1024,3 +1024,56 @@ def torch_max_rel(a, b, scale=None):
     import torch
     s = float(b.abs().max()) if scale is None else scale
     return (a - b).abs().max() / s
+
+
+def test_dense_plugin_routes():
+    """fitter='b200_dense' and the automatic route of b200_lm (no batched kernel for the parameter count) through
+    lsqfit_b200.nonlinear_fit: (a) 40 parameters (multiexp K = 20) on 120 correlated points, default fitter -> dense path,
+    vs the oracle; (b) examples/y-noerr.out nexp = 2 with fitter='b200_dense': data and prior correlated WITH EACH OTHER
+    (joint whitening matrix); (c) 1e5 uncorrelated points through the plugin signature (1x1 weights only)."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from lsqfit_b200 import configs
+    from oracle import gvfmt
+    from oracle.fit import nonlinear_fit as ofit
+    from parity_util import _y_noerr_problem, Y_NOERR_OUT
+    # ---- (a)
+    cfg = configs.c5(ny=120, K=20, seed=7)
+    kw = dict(svdcut=cfg["svdcut"])
+    fo = ofit("multiexp", cfg["x"], cfg["ymean"], cfg["ycov"], prior_mean=cfg["prior_mean"], prior_cov=cfg["prior_sdev"],
+              tol=TIGHT, x_scale="jac", **kw)
+    xe, fe, Je, cove = exact_minimum(fo)
+    fd = lb.nonlinear_fit(data=(cfg["t"], cfg["ymean"], cfg["ycov"]), prior=(cfg["prior_mean"], cfg["prior_sdev"]),
+                          fcn="multiexp", tol=(1e-14, 0, 0), polish=6, **kw)
+    assert fd.error is None and fd.description.startswith("dense") and fd.svdn == fo.svdn and fd.dof == fo.dof
+    assert np.max(np.abs(fd.pmean - xe) / fo.psdev) < 1e-8
+    assert abs(fd.chi2 - fe @ fe) <= 1e-9 * (fe @ fe)
+    assert _rel_cov(fd.cov, cove) < 1e-8
+    assert abs(fd.logGBF - fo.logGBF) <= 1e-8 * abs(fo.logGBF)
+    np.testing.assert_allclose(fd.p_sdev, fd.psdev, rtol=1e-5)               # D C D^T == cov
+    assert fd.residuals.shape == (fo.yp_pdf.nchiv,) and fd.J.shape == (fo.yp_pdf.nchiv, 40)
+    # ---- (b)
+    x, ymod, cov, pm = _y_noerr_problem(1)
+    f1 = lb.nonlinear_fit(data=(x, ymod, None), prior=(pm, np.ones(2)), yp_cov=cov, fcn="multiexp", svdcut=1e-12, tol=1e-15)
+    x, ymod, cov, pm = _y_noerr_problem(2)
+    p0 = np.array([f1.pmean[0], pm[1], f1.pmean[1], pm[3]])
+    for fitter in ("b200_lm", "b200_dense"):
+        fit = lb.nonlinear_fit(data=(x, ymod, None), prior=(pm, np.ones(4)), yp_cov=cov, fcn="multiexp", p0=p0,
+                               svdcut=1e-12, tol=1e-15, fitter=fitter)
+        chi2dof, dof, Q, logGBF, svdn, a_exp, E_exp = Y_NOERR_OUT[2]
+        assert fit.error is None and fit.dof == dof and fit.svdn == svdn, fitter
+        assert gvfmt.agrees_g(fit.chi2 / fit.dof, chi2dof, 2) and abs(fit.logGBF - float(logGBF)) < 1.5e-3, fitter
+        for m, sd, e in zip(fit.pmean, fit.psdev, a_exp + E_exp):
+            assert gvfmt.agrees(m, sd, e, slack=1.01), (fitter, m, sd, e)
+        for m, sd, e in zip(fit.pmean, fit.p_sdev, a_exp + E_exp):           # propagated through the joint covariance
+            assert gvfmt.agrees(m, sd, e, slack=1.01), (fitter, m, sd, e)
+    # ---- (c)
+    rng = np.random.default_rng(3)
+    N = 100000
+    xs = np.linspace(0.2, 2.0, N)
+    ys = 0.5 + 0.4 * np.exp(-0.7 * xs) + 1e-3 * rng.standard_normal(N)
+    fa = lb.nonlinear_fit(data=(xs, ys, np.full(N, 1e-3)), prior=(np.zeros(3), np.ones(3)), fcn="offset_exp",
+                          p0=[0.1, 0.1, 0.1], fitter="b200_dense", tol=1e-10)
+    assert fa.error is None and fa.dof == N and fa._dense.fused
+    assert np.max(np.abs(fa.pmean - [0.5, 0.4, 0.7]) / fa.psdev) < 5.0
+    assert 0.97 < fa.chi2 / fa.dof < 1.03
