@@ -16,6 +16,7 @@ from .fitter import b200_lm, ChivSpec, DeviceChiv
 from .fit import nonlinear_fit, gammaQ, BatchFits, FitView, wavg, WAvg
 from .dense import DenseFit
 from .bootstrap import bootstrap_means, normals
+from .multifit import MultiFitter, FunctorModel, SharedExpModel, ChainedFit
 
 __version__ = "0.1.0"
 
