@@ -281,18 +281,62 @@ def extras_single_gpu(torch, lb, configs, dev, peak):
         md = torch.as_tensor(configs.bootstrap_means(cfg, Bs, cfg["seed"] + 7, cov=pdf.cov[:ny, :ny])).to(dev)
         p0 = torch.as_tensor(cfg["p0"]).to(dev)
         rows = {}
-        for team in (1, 4):
+        for team in (1, 4, 32):
             plan = lb.Plan("multiexp", npar, ny, cfg["x"], pdf.i_invwgts, device=dev.index, team=team)
             out = plan.fit_batch(md, p0, tol=cfg["tol"], maxit=cfg["maxit"], want_cov=True)
             ms, _ = _timed(torch, lambda: plan.fit_batch(md, p0, tol=cfg["tol"], maxit=cfg["maxit"], out=out), reps=2)
             nfev, njev, nfac = plan.last_stats()
             fl = njev * configs.eval_flops(ny, npar, cfg["K"])
-            rows["warps_per_fit_%d" % team] = dict(ms=ms, fits_per_s=Bs / ms * 1e3, tflops=fl / (ms * 1e-3) / 1e12,
-                                                   frac=fl / (ms * 1e-3) / 1e12 / peak)
+            key = "wave_kernel" if team == 32 else "warps_per_fit_%d" % team
+            rows[key] = dict(ms=ms, fits_per_s=Bs / ms * 1e3, tflops=fl / (ms * 1e-3) / 1e12,
+                             frac=fl / (ms * 1e-3) / 1e12 / peak, kernel_used=plan.last_team())
             plan.close()
-        ex["c3_saturated"] = dict(B=Bs, **rows)
+        ex["c3_saturated"] = dict(B=Bs, note="wave_kernel = lm_wave.cuh (b200lm_set_team(h, 32)): 32 fits per CTA in lock-step "
+                                  "phases, one DMMA GEMM per chunk of 8 fits; its time includes the finalisation pass "
+                                  "(covariances) of the one-warp kernel", **rows)
     except Exception as e:                                   # noqa: BLE001
         ex["c3_saturated"] = dict(error=repr(e))
+    # ---- one fit with millions of uncorrelated points (examples/uncorrelated.py:30-41; BASELINE.md's first row):
+    # the one-pass normal-equation kernel is HBM bound -- 24 B per row (x, y, 1/sigma) are read once
+    try:
+        from lsqfit_b200.dense import DenseFit
+        hbm = None
+        try:
+            hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:                                    # noqa: BLE001
+            pass
+        Nu = 2000000
+        rng = np.random.default_rng(12)
+        xu = np.linspace(0.2, 2.0, Nu)
+        yu = 0.5 + 0.4 * np.exp(-0.7 * xu) + 1e-3 * rng.standard_normal(Nu)
+        fit = None
+        for _ in range(2):
+            del fit
+            fit = DenseFit((xu, yu, np.full(Nu, 1e-3)), (np.zeros(3), np.ones(3)), p0=[0.1, 0.1, 0.1], fcn="offset_exp",
+                           tol=1e-10, device=dev.index)
+        import ctypes as C
+        from lsqfit_b200 import _cabi
+
+        def nd():
+            _cabi.check(_cabi.lib.b200lm_normal_diag(fit._h, fit.x.data_ptr(), fit.d_y.data_ptr(), fit.wdiag.data_ptr(),
+                                                     fit.nacc.data_ptr(), fit.la.stream()), fit._h)
+        # inputs (48 MB) are smaller than L2 (126 MB): flush between timed launches
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            t1, _ = _timed(torch, nd, reps=1)
+            ts.append(t1)
+        ms_k = float(np.median(ts))
+        gbs = 24.0 * Nu / (ms_k * 1e-3) / 1e9
+        ex["uncorrelated_2e6"] = dict(ny=Nu, np=3, fit_s=fit.times["fit"], nit=int(fit.nit), chi2_dof=float(fit.chi2 / fit.dof),
+                                      fused_kernel=bool(fit.fused), normal_diag_ms=ms_k, algorithmic_bytes=24 * Nu,
+                                      achieved_gbs=gbs, hbm_peak_gbs=hbm, frac=(gbs / hbm) if hbm else None,
+                                      l2="flushed before every timed launch (256 MiB memset)",
+                                      note="reference: ~2 minutes for this fit (examples/uncorrelated.py:36)")
+        del fit, flush
+    except Exception as e:                                   # noqa: BLE001
+        ex["uncorrelated_2e6"] = dict(error=repr(e))
     # ---- C1: examples/simple.py, one fit: latency
     try:
         g = json.load(open(os.path.join(ROOT, "tests", "golden", "examples.json")))["examples"]["simple"]
@@ -360,7 +404,7 @@ def extras_single_gpu(torch, lb, configs, dev, peak):
     return ex
 
 
-def c4_strong(torch, dist, lb, configs, lbdist, dev, rank, world, B=1000000):
+def c4_strong(torch, dist, lb, configs, lbdist, dev, rank, world, B=1000000, comm=None):
     """BASELINE config 4: 10^6 simulated fits of a 3-exp correlator SHARDED over the ranks (strong scaling):
     every rank generates its shard of the Philox stream on its own GPU, fits it, then one all-gather of the
     packed results and one all-reduce of the moments.  Timed on the device, max over ranks."""
@@ -381,8 +425,8 @@ def c4_strong(torch, dist, lb, configs, lbdist, dev, rank, world, B=1000000):
         means = bs.bootstrap_means(m0d, Ld, hi - lo, cfg["seed"], first=lo, device=dev.index)
         out = plan.fit_batch(means, p0d, tol=cfg["tol"], maxit=cfg["maxit"], want_cov=False)
         packed = lbdist.pack_results(out.x, out.chi2, out.nit, out.status)
-        allp = lbdist.gather_results(packed, B_total=B)
-        m, c, n = lbdist.moments(out.x, out.status > 0)
+        allp = lbdist.gather_results(packed, B_total=B, comm=comm)
+        m, c, n = lbdist.moments(out.x, out.status > 0, comm=comm)
         return allp, m, c, n
 
     def barrier():
@@ -467,12 +511,21 @@ def run_ours(args, rank, local_rank, world):
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # 256 MiB > 126 MB L2
 
     out = plan.fit_batch(means_d, p0_d, tol=cfg["tol"], maxit=cfg["maxit"])          # allocates outputs
+    # data-path collectives through the library's own C ABI (b200lm_gather / b200lm_allreduce_sum, csrc/comm.cu);
+    # torch.distributed only ships the NCCL id and runs the timing barriers
+    nccl_comm, nccl_comm_note = None, None
+    if world > 1:
+        try:
+            nccl_comm = lbdist.Comm(local_rank)
+            nccl_comm_note = "b200lm_gather / b200lm_allreduce_sum (NCCL behind the C ABI)"
+        except Exception as e:                               # noqa: BLE001
+            nccl_comm_note = "torch.distributed (C-ABI communicator unavailable: %r)" % (e,)
 
     def step():
         plan.fit_batch(means_d, p0_d, tol=cfg["tol"], maxit=cfg["maxit"], out=out)
         if world > 1:
             packed = lbdist.pack_results(out.x, out.chi2, out.nit, out.status)
-            return lbdist.gather_results(packed)
+            return lbdist.gather_results(packed, comm=nccl_comm)
         return None
 
     def barrier():
@@ -499,7 +552,7 @@ def run_ours(args, rank, local_rank, world):
         kev[k][1].record()
         if world > 1:
             packed = lbdist.pack_results(out.x, out.chi2, out.nit, out.status)
-            lbdist.gather_results(packed)
+            lbdist.gather_results(packed, comm=nccl_comm)
         ev[k][1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -576,7 +629,7 @@ def run_ours(args, rank, local_rank, world):
     extras = {}
     if not args.no_extras:
         try:
-            extras["c4_strong"] = c4_strong(torch, dist, lb, configs, lbdist, dev, rank, world)
+            extras["c4_strong"] = c4_strong(torch, dist, lb, configs, lbdist, dev, rank, world, comm=nccl_comm)
         except Exception as e:                               # noqa: BLE001
             extras["c4_strong"] = dict(error=repr(e))
         if world == 1:
@@ -587,7 +640,8 @@ def run_ours(args, rank, local_rank, world):
         comm = dict(backend=dist.get_backend(), nranks=dist.get_world_size(),
                     nccl_version=".".join(str(v) for v in torch.cuda.nccl.version()),
                     nccl_debug=os.environ.get("NCCL_DEBUG"), log="stderr (NCCL_DEBUG_FILE=/dev/stderr)",
-                    collectives_per_step="1 all_gather_into_tensor of [B, np+3] fp64 rows; no host synchronisation")
+                    collectives_per_step="1 all-gather of [B, np+3] fp64 rows; no host synchronisation",
+                    data_path=nccl_comm_note)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -35,6 +35,7 @@ extern "C" {
 #define B200LM_ESIZE      -5        /* problem does not fit the kernel's shared-memory plan */
 
 typedef struct b200lm_handle_s* b200lm_handle;
+typedef struct b200lm_comm_s* b200lm_comm;
 
 /* ---- library ------------------------------------------------------------------------ */
 int b200lm_version(void);
@@ -235,6 +236,23 @@ int b200lm_normals(int device, long long first, long long count, unsigned long l
 int b200lm_bootstrap_means(int device, long long B, long long first, int N, int M, const double* d_mean,
                            const double* d_L, int ldl, unsigned long long seed, double* d_z,
                            double* d_out, long long out_stride, void* stream);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink / NVSwitch ----------------------------
+ * Batches shard over the ranks by fit index and are fitted without any exchange; afterwards the packed per-fit results
+ * are gathered and moment buffers summed.  The reference has no counterpart (its iterators run copy by copy in one
+ * process, src/lsqfit/__init__.py:1612-1624); these calls are what a multi-process driver binds.
+ *   b200lm_comm_unique_id  rank 0 creates the 128-byte NCCL id; the caller ships it to the other ranks (any host channel)
+ *   b200lm_comm_init       every rank, with the same id
+ *   b200lm_gather          d_recv[world * count] = concatenation in rank order of every rank's d_send[count]
+ *   b200lm_allreduce_sum   d_buf[count] <- sum over ranks, in place
+ * Device pointers, fp64, asynchronous on `stream`.  NCCL is bound at run time (libnccl.so.2). */
+int b200lm_comm_unique_id(char* out128);
+int b200lm_comm_init(int device, int rank, int world, const char* id128, b200lm_comm* out);
+void b200lm_comm_destroy(b200lm_comm c);
+int b200lm_comm_rank(b200lm_comm c);
+int b200lm_comm_world(b200lm_comm c);
+int b200lm_gather(b200lm_comm c, const double* d_send, double* d_recv, long long count_per_rank, void* stream);
+int b200lm_allreduce_sum(b200lm_comm c, double* d_buf, long long count, void* stream);
 
 #ifdef __cplusplus
 }

@@ -45,13 +45,16 @@ void fill_params(b200lm_handle_s* h, FitParams& P) {
 }  // namespace b200lm
 
 namespace b200lm {
-// fixed-order sum of the per-CTA partial rows of normal_diag_kernel (lm_rows.cuh): deterministic results
+// fixed-order sum of the per-CTA partial rows of normal_diag_kernel (lm_rows.cuh): one warp per accumulator, lane l
+// adds rows l, l + 32, ... in order, then a shuffle tree -- the same association on every run (deterministic results)
+// without the serial chain of nparts dependent loads
 __global__ void sum_partials_kernel(int nparts, int nacc, const double* __restrict__ partial, double* __restrict__ out) {
-    for (int k = threadIdx.x; k < nacc; k += blockDim.x) {
-        double v = 0.0;
-        for (int q = 0; q < nparts; ++q) v += partial[(size_t)q * nacc + k];
-        out[k] = v;
-    }
+    const int k = blockIdx.x, lane = threadIdx.x;
+    if (k >= nacc) return;
+    double v = 0.0;
+    for (int q = lane; q < nparts; q += 32) v += partial[(size_t)q * nacc + k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) out[k] = v;
 }
 }  // namespace b200lm
 

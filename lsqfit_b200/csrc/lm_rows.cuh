@@ -91,13 +91,14 @@ template <class F>
 cudaError_t launch_normal_diag(int ny, int nx, const double* x, const double* p, const double* y, const double* w,
                                double* partial, int max_parts, double* out, int sm_count, cudaStream_t stream) {
     constexpr int NACC = NormalAccLayout<F::NP>::NACC;
-    int grid = (ny + 255) / 256;
+    int grid = (ny + 1023) / 1024;                   // >= 4 rows per thread: the accumulator reduction is amortised
     if (grid > 4 * sm_count) grid = 4 * sm_count;
     if (grid > max_parts) grid = max_parts;
+    if (grid < 1) grid = 1;
     normal_diag_kernel<F><<<grid, 256, 0, stream>>>(ny, nx, x, p, y, w, partial);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    sum_partials_kernel<<<1, 128, 0, stream>>>(grid, NACC, partial, out);
+    sum_partials_kernel<<<NACC, 32, 0, stream>>>(grid, NACC, partial, out);
     return cudaGetLastError();
 }
 

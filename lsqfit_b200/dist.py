@@ -6,8 +6,50 @@ NVLink/NVSwitch) is used only after the fit: an all-gather of the packed per-fit
 and an all-reduce of first/second moments for bootstrap averages.
 The same code runs on the gloo backend with CPU tensors for the world_size-2 tests.
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
+
+
+class Comm(object):
+    """NCCL communicator behind the C ABI (b200lm_comm_init / b200lm_gather / b200lm_allreduce_sum, csrc/comm.cu).
+    ``torch.distributed`` is used only to ship the 128-byte NCCL id from rank 0 to the others (any host channel
+    would do); the collectives on the data path are the library's own calls."""
+
+    def __init__(self, device, rank=None, world=None, group=None):
+        from . import _cabi
+        self._cabi = _cabi
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        ident = C.create_string_buffer(128)
+        if self.rank == 0:
+            _cabi.check(_cabi.lib.b200lm_comm_unique_id(ident))
+        obj = [ident.raw]
+        dist.broadcast_object_list(obj, src=0, group=group)
+        self._h = C.c_void_p()
+        self.device = int(device)
+        _cabi.check(_cabi.lib.b200lm_comm_init(self.device, self.rank, self.world, obj[0], C.byref(self._h)))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(torch.device("cuda", self.device)).cuda_stream)
+
+    def gather(self, t):
+        """rows of every rank, in rank order (equal shards)"""
+        t = t.contiguous()
+        out = t.new_empty((self.world * t.shape[0],) + tuple(t.shape[1:]))
+        self._cabi.check(self._cabi.lib.b200lm_gather(self._h, t.data_ptr(), out.data_ptr(), t.numel(), self._stream()))
+        return out
+
+    def allreduce_sum(self, t):
+        assert t.is_contiguous() and t.dtype == torch.float64
+        self._cabi.check(self._cabi.lib.b200lm_allreduce_sum(self._h, t.data_ptr(), t.numel(), self._stream()))
+        return t
+
+    def close(self):
+        if self._h:
+            self._cabi.lib.b200lm_comm_destroy(self._h)
+            self._h = C.c_void_p()
 
 
 def shard_range(B, rank, world):
@@ -29,7 +71,7 @@ def unpack_results(packed):
             packed[:, npar + 2].to(torch.int32))
 
 
-def gather_results(packed, B_total=None, group=None):
+def gather_results(packed, B_total=None, group=None, comm=None):
     """All-gather the packed results of every rank in rank order: ONE collective, no host
     synchronisation.  Shards follow ``shard_range`` (sizes differ by at most one row), so every
     rank can compute all shard sizes from ``B_total`` alone; without ``B_total`` the shards are
@@ -48,14 +90,17 @@ def gather_results(packed, B_total=None, group=None):
     pad = packed
     if n < nmax:
         pad = torch.cat([packed, packed.new_zeros((nmax - n, packed.shape[1]))])
-    out = packed.new_empty((world * nmax, packed.shape[1]))
-    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    if comm is not None:
+        out = comm.gather(pad)                                   # b200lm_gather (C ABI)
+    else:
+        out = packed.new_empty((world * nmax, packed.shape[1]))
+        dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
     if min(sizes) == nmax:
         return out
     return torch.cat([out[r * nmax: r * nmax + sizes[r]] for r in range(world)])
 
 
-def moments(x, ok, group=None):
+def moments(x, ok, group=None, comm=None):
     """Mean and covariance of the converged best-fit parameters over ALL ranks
     (one all-reduce of count, sum x, sum x x^T)."""
     okb = ok.to(torch.bool)[:, None]
@@ -63,7 +108,9 @@ def moments(x, ok, group=None):
     xs = torch.where(okb, x, torch.zeros_like(x))
     npar = x.shape[1]
     buf = torch.cat([okb.sum().to(x.dtype).reshape(1), xs.sum(dim=0), (xs.T @ xs).reshape(-1)])
-    if dist.is_available() and dist.is_initialized():
+    if comm is not None:
+        comm.allreduce_sum(buf)                                  # b200lm_allreduce_sum (C ABI)
+    elif dist.is_available() and dist.is_initialized():
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     n = buf[0]
     m = buf[1:1 + npar] / n
