@@ -81,6 +81,73 @@ class _LA(object):
         return X
 
 
+# ---- bound constraints: the reflective step selection of scipy's trf (the solver behind lsqfit.scipy_least_squares with
+# ``bounds=``, reference src/lsqfit/_scipy.py:56-79, tests/test_lsqfit.py:1779-1808).  scipy is third party; its published
+# algorithm (scipy/optimize/_lsq/trf.py: trf_bounds, select_step; common.py: CL_scaling_vector, step_size_to_bound,
+# intersect_trust_region, minimize_quadratic_1d, make_strictly_feasible) is restated here on length-np host vectors --
+# the O(np^2) products stay on the device.
+def _in_bounds(x, lb, ub):
+    return bool(np.all((x >= lb) & (x <= ub)))
+
+
+def _make_strictly_feasible(x, lb, ub, rstep=1e-10):
+    xn = x.copy()
+    if rstep == 0:
+        lo, up = x <= lb, x >= ub
+        xn[lo] = np.nextafter(lb[lo], ub[lo])
+        xn[up] = np.nextafter(ub[up], lb[up])
+    else:
+        ld, ud = x - lb, ub - x
+        lt, ut = rstep * np.maximum(1, np.abs(lb)), rstep * np.maximum(1, np.abs(ub))
+        lo = np.isfinite(lb) & (ld <= np.minimum(ud, lt))
+        up = np.isfinite(ub) & (ud <= np.minimum(ld, ut))
+        xn[lo] = lb[lo] + rstep * np.maximum(1, np.abs(lb[lo]))
+        xn[up] = ub[up] - rstep * np.maximum(1, np.abs(ub[up]))
+    tight = (xn < lb) | (xn > ub)
+    xn[tight] = 0.5 * (lb[tight] + ub[tight])
+    return xn
+
+
+def _cl_scaling_vector(x, g, lb, ub):
+    v, dv = np.ones_like(x), np.zeros_like(x)
+    m = (g < 0) & np.isfinite(ub)
+    v[m] = ub[m] - x[m]; dv[m] = -1
+    m = (g > 0) & np.isfinite(lb)
+    v[m] = x[m] - lb[m]; dv[m] = 1
+    return v, dv
+
+
+def _step_size_to_bound(x, s, lb, ub):
+    nz = np.nonzero(s)
+    steps = np.full_like(x, np.inf)
+    with np.errstate(over="ignore", invalid="ignore"):
+        steps[nz] = np.maximum((lb - x)[nz] / s[nz], (ub - x)[nz] / s[nz])
+    m = np.min(steps)
+    return m, np.equal(steps, m) * np.sign(s).astype(int)
+
+
+def _intersect_trust_region(x, s, Delta):
+    a = s @ s
+    b = x @ s
+    c = x @ x - Delta ** 2
+    d = np.sqrt(max(b * b - a * c, 0.0))
+    q = -(b + np.copysign(d, b))
+    t1, t2 = q / a, c / q
+    return (t1, t2) if t1 < t2 else (t2, t1)
+
+
+def _minimize_quadratic_1d(a, b, lb, ub, c=0.0):
+    t = [lb, ub]
+    if a != 0:
+        e = -0.5 * b / a
+        if lb < e < ub:
+            t.append(e)
+    t = np.asarray(t)
+    y = t * (a * t + b) + c
+    i = int(np.argmin(y))
+    return t[i], y[i]
+
+
 def _dense_weights(pdf, n):
     """the whitening of a PDF (``i_invwgts``: 1x1 weights + block matrices) as ONE dense [nchiv, n] matrix"""
     W = np.zeros((pdf.nchiv, n))
@@ -107,7 +174,7 @@ class DenseFit(object):
     """
 
     def __init__(self, data, prior, p0=None, svdcut=False, eps=False, tol=1e-8, maxit=1000, scaler="more",
-                 polish=0, device=0, pdf=None, fcn="multiexp", spec=None):
+                 polish=0, device=0, pdf=None, fcn="multiexp", spec=None, bounds=None):
         from .fit import resolve_svdcut_eps
         from .functors import Functor
         svdcut, eps = resolve_svdcut_eps(svdcut, eps)
@@ -253,6 +320,15 @@ class DenseFit(object):
         self._triu = torch.triu_indices(n, n, device=dev)
         self.polish = int(polish)
         x0 = pm.copy() if p0 is None else np.asarray(p0, dtype=float).reshape(-1)
+        self.lb = self.ub = None
+        if bounds is not None:
+            lb, ub = (np.broadcast_to(np.asarray(b, dtype=float), (n,)).copy() for b in bounds)
+            if not np.all(lb < ub):
+                raise ValueError("Each lower bound must be strictly less than each upper bound.")     # scipy least_squares
+            if not _in_bounds(x0, lb, ub):
+                raise ValueError("`x0` is infeasible.")
+            self.lb, self.ub = lb, ub
+            x0 = _make_strictly_feasible(x0, lb, ub)
         t0 = time.perf_counter()
         self._fit(torch.as_tensor(x0).to(dev))
         torch.cuda.synchronize(dev)
@@ -393,6 +469,72 @@ class DenseFit(object):
             raise FloatingPointError("normal matrix is not positive definite at any damping")
         return p * (Delta / float(torch.linalg.vector_norm(p))), alpha
 
+    def _select_step(self, x, g_h, p_h, d, Delta, theta):
+        """scipy trf.py: select_step -- the trust-region step if it stays inside the bounds, else the best of: that step
+        cut back to the bound, its reflection off the bound, and the (cut back) anti-gradient step, compared on the
+        quadratic model  q(s) = 1/2 s^T As s + g_h^T s  (As = d J^T J d + C, on the device)."""
+        lb, ub = self.lb, self.ub
+        dev_t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=float)).to(self.la.tdev)
+        gh = g_h.cpu().numpy()
+        p_h = p_h.cpu().numpy().copy()
+
+        def As_dot(s):
+            return self.la.mm(self.As, dev_t(s)).cpu().numpy()
+
+        def quad(s):
+            return 0.5 * float(s @ As_dot(s)) + float(gh @ s)
+
+        def quad_1d(s, s0=None):
+            As_s = As_dot(s)
+            a = 0.5 * float(s @ As_s)
+            b = float(gh @ s)
+            if s0 is None:
+                return a, b
+            b += float(s0 @ As_s)
+            return a, b, quad(s0)
+        p = d * p_h
+        if _in_bounds(x + p, lb, ub):
+            return p, p_h, -quad(p_h)
+        p_stride, hits = _step_size_to_bound(x, p, lb, ub)
+        r_h = p_h.copy()
+        r_h[hits.astype(bool)] *= -1
+        r = d * r_h
+        p = p * p_stride
+        p_h = p_h * p_stride
+        x_on_bound = x + p
+        _, to_tr = _intersect_trust_region(p_h, r_h, Delta)
+        to_bound, _ = _step_size_to_bound(x_on_bound, r, lb, ub)
+        r_stride = min(to_bound, to_tr)
+        if r_stride > 0:
+            r_stride_l = (1 - theta) * p_stride / r_stride
+            r_stride_u = theta * to_bound if r_stride == to_bound else to_tr
+        else:
+            r_stride_l, r_stride_u = 0, -1
+        if r_stride_l <= r_stride_u:
+            a, b, c = quad_1d(r_h, s0=p_h)
+            r_stride, r_value = _minimize_quadratic_1d(a, b, r_stride_l, r_stride_u, c=c)
+            r_h = r_h * r_stride + p_h
+            r = r_h * d
+        else:
+            r_value = np.inf
+        p = p * theta
+        p_h = p_h * theta
+        p_value = quad(p_h)
+        ag_h = -gh
+        ag = d * ag_h
+        to_tr = Delta / np.linalg.norm(ag_h)
+        to_bound, _ = _step_size_to_bound(x, ag, lb, ub)
+        ag_stride = theta * to_bound if to_bound < to_tr else to_tr
+        a, b = quad_1d(ag_h)
+        ag_stride, ag_value = _minimize_quadratic_1d(a, b, 0, ag_stride)
+        ag_h = ag_h * ag_stride
+        ag = ag * ag_stride
+        if p_value < r_value and p_value < ag_value:
+            return p, p_h, -p_value
+        if r_value < p_value and r_value < ag_value:
+            return r, r_h, -r_value
+        return ag, ag_h, -ag_value
+
     # ---- the fit (a-3) ---------------------------------------------------------------------
     def _fit(self, x):
         la = self.la
@@ -410,26 +552,56 @@ class DenseFit(object):
             scale_inv[scale_inv == 0] = 1.0
         else:
             scale_inv = torch.ones_like(x)
-        Delta = float(torch.linalg.vector_norm(x * scale_inv)) or 1.0
+        bounded = self.lb is not None
+        dev_t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=float)).to(la.tdev)
+        if bounded:
+            lbn, ubn = self.lb, self.ub
+            v, dv = _cl_scaling_vector(x.cpu().numpy(), g.cpu().numpy(), lbn, ubn)
+            si = scale_inv.cpu().numpy()
+            v[dv != 0] *= si[dv != 0]
+            Delta = float(np.linalg.norm(x.cpu().numpy() * si / v ** 0.5)) or 1.0
+        else:
+            Delta = float(torch.linalg.vector_norm(x * scale_inv)) or 1.0
         alpha = 0.0
         status = None
         error = None
         while True:
-            if float(torch.max(torch.abs(g))) < gtol:
+            if bounded:
+                xh, gh_ = x.cpu().numpy(), g.cpu().numpy()
+                v, dv = _cl_scaling_vector(xh, gh_, lbn, ubn)
+                g_norm = float(np.max(np.abs(gh_ * v)))
+            else:
+                g_norm = float(torch.max(torch.abs(g)))
+            if g_norm < gtol:
                 status = 1
             if status is not None or nfev >= self.maxit:
                 break
-            d = 1.0 / scale_inv
+            if bounded:
+                si = scale_inv.cpu().numpy()
+                v[dv != 0] *= si[dv != 0]
+                dh = v ** 0.5 / si                                   # "hat" space: x = d x_h
+                diag_h = gh_ * dv / si                               # diagonal term of the Coleman-Li model
+                theta = max(0.995, 1 - g_norm)
+                d = dev_t(dh)
+            else:
+                d = 1.0 / scale_inv
             torch.mul(self.A, d[:, None] * d[None, :], out=self.As)
+            if bounded:
+                self.As.diagonal().add_(dev_t(diag_h))
             gs = d * g
             cache = {}
             actual = -1.0
             while actual <= 0 and nfev < self.maxit:
                 step_h, alpha = self._solve_tr(gs, Delta, alpha, cache)
-                As_step = la.mm(self.As, step_h)
-                predicted = -float(0.5 * (step_h @ As_step) + gs @ step_h)
-                step = d * step_h
-                x_new = x + step
+                if bounded:
+                    step, step_h, predicted = self._select_step(xh, gs, step_h, dh, Delta, theta)
+                    x_new = dev_t(_make_strictly_feasible(xh + step, lbn, ubn, rstep=0))
+                    step, step_h = dev_t(step), dev_t(step_h)
+                else:
+                    As_step = la.mm(self.As, step_h)
+                    predicted = -float(0.5 * (step_h @ As_step) + gs @ step_h)
+                    step = d * step_h
+                    x_new = x + step
                 fd_new, fp_new = self.residual(x_new)
                 nfev += 1
                 shn = float(torch.linalg.vector_norm(step_h))
@@ -479,7 +651,7 @@ class DenseFit(object):
             torch.mul(self.A, dd, out=self.As)
             ok, sh, _, _ = self._factor_solve(0.0, d * g)
             return ok, sh, (-float((d * g) @ sh) if ok else np.inf)
-        if self.polish > 0:
+        if self.polish > 0 and not bounded:                      # (undamped steps would leave the feasible region)
             ok, sh, dec = gn(g)
             for _ in range(self.polish):
                 if not ok or not (dec > 1e-30 * max(1.0, 2 * cost)):
@@ -595,11 +767,14 @@ class b200_dense(object):
     """The single-fit path with the reference's plugin signature (``FITTERS[name](p0, nf, chiv, tol=, maxit=, **fitterargs)``,
     src/lsqfit/__init__.py:662-664; result attributes as src/lsqfit/_scipy.py:115-181): one fit spread over the whole GPU
     -- for parameter counts the batched kernels are not compiled for (np > 25 for most models, any np for 'multiexp'), for
-    millions of uncorrelated points, or on request (``fitter='b200_dense'``).  ``b200_lm`` routes here by itself when no
-    batched kernel exists for the model's parameter count.  Extra fitterargs: ``scaler`` ('more' | 'levenberg'), ``device``,
-    ``polish``."""
+    millions of uncorrelated points, fits with BOUNDS, or on request (``fitter='b200_dense'``).  ``b200_lm`` routes here by
+    itself when no batched kernel exists for the model's parameter count or when ``bounds`` are given.  Extra fitterargs:
+    ``scaler`` ('more' | 'levenberg'), ``device``, ``polish``, ``bounds=(lower, upper)`` (scipy's argument of
+    ``lsqfit.scipy_least_squares``, reference src/lsqfit/_scipy.py:77, tests/test_lsqfit.py:1779-1808: the reflective
+    trust-region step selection of scipy's trf)."""
 
-    def __init__(self, x0, n, f, tol=(1e-8, 1e-10, 1e-10), maxit=1000, scaler="more", device=0, polish=0, **extra_args):
+    def __init__(self, x0, n, f, tol=(1e-8, 1e-10, 1e-10), maxit=1000, scaler="more", device=0, polish=0, bounds=None,
+                 **extra_args):
         if extra_args:
             raise ValueError("b200_dense: unknown fitter arguments: " + ", ".join(sorted(extra_args)))
         spec = getattr(f, "b200", None)
@@ -611,8 +786,11 @@ class b200_dense(object):
         if spec.np < 0:
             spec.np = self.x0.size
         self.description = "dense    scaler = {}    device = cuda:{}".format(scaler, device)
+        if bounds is not None:                                    # (lower, upper) in the caller's parameter order (scipy's argument)
+            bounds = tuple(spec.to_device(np.broadcast_to(np.asarray(b, dtype=float), self.x0.shape)) for b in bounds)
+            self.description += "    bounds"
         fit = DenseFit(None, None, p0=spec.to_device(self.x0), tol=self.tol, maxit=maxit, scaler=scaler, polish=polish,
-                       device=device, spec=spec)
+                       device=device, spec=spec, bounds=bounds)
         if n != fit.nchiv:
             raise ValueError("b200_dense: n=%d does not match the whitening (%d residuals)" % (n, fit.nchiv))
         self.dense = fit

@@ -155,13 +155,15 @@ class b200_lm(object):
                   LDL^T solve of the damped normal equations), ``factor_up``, ``factor_down``, ``avmax`` (read by GSL's
                   dogleg / lmaccel methods only) are accepted.
       ``scaler``  'more' (default) | 'levenberg' | 'marquardt' (gsl policy only)   (_gsl.pyx:621-653)
+      ``bounds``  (lower, upper): scipy's bound constraints (``lsqfit.scipy_least_squares(bounds=...)``); such fits run on
+                  the single-fit path (lsqfit_b200/dense.py) with scipy trf's reflective step selection.
       ``device``  CUDA index;  ``polish``  max Gauss-Newton refinement steps after the trust-region loop (default 0 =
                   stop where the reference's solver stops).
     """
 
     def __init__(self, x0, n, f, tol=(1e-8, 1e-10, 1e-10), maxit=1000, scaler="more", device=0,
                  polish=0, policy="trf", alg="lm", solver="qr", factor_up=3.0, factor_down=2.0, avmax=0.75,
-                 **extra_args):
+                 bounds=None, **extra_args):
         if extra_args:
             raise ValueError("b200_lm: unknown fitter arguments: " + ", ".join(sorted(extra_args)))
         from .engine import POLICY, SCALER
@@ -192,13 +194,14 @@ class b200_lm(object):
         from ._cabi import B200LMError, functor_table
         if spec.np < 0:
             spec.np = self.x0.size
-        if not any(fam == spec.functor.family and m == spec.np for fam, m, _, _ in functor_table()):
-            # no batched kernel for this parameter count: one fit over the whole GPU instead (lsqfit_b200/dense.py)
+        if bounds is not None or not any(fam == spec.functor.family and m == spec.np for fam, m, _, _ in functor_table()):
+            # no batched kernel for this parameter count, or bound constraints (scipy's ``bounds``): one fit over the
+            # whole GPU instead (lsqfit_b200/dense.py)
             if gsl:
-                raise ValueError("b200_lm: policy='gsl' needs a batched kernel; none is compiled for %s with np=%d"
+                raise ValueError("b200_lm: policy='gsl' needs a batched kernel without bounds (model %s, np=%d)"
                                  % (spec.functor.name, spec.np))
             from .dense import b200_dense
-            d = b200_dense(x0, n, f, tol=tol, maxit=maxit, scaler=scaler, device=device, polish=polish)
+            d = b200_dense(x0, n, f, tol=tol, maxit=maxit, scaler=scaler, device=device, polish=polish, bounds=bounds)
             for k in ("x", "cov", "f", "J", "nit", "logdet_JtJ", "results", "stopping_criterion", "error", "dense"):
                 setattr(self, k, getattr(d, k))
             self.description = d.description

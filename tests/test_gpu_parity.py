@@ -1077,3 +1077,40 @@ def test_dense_plugin_routes():
     assert fa.error is None and fa.dof == N and fa._dense.fused
     assert np.max(np.abs(fa.pmean - [0.5, 0.4, 0.7]) / fa.psdev) < 5.0
     assert 0.97 < fa.chi2 / fa.dof < 1.03
+
+
+def test_bounds(nist_problems):
+    """scipy's ``bounds`` (lsqfit.scipy_least_squares(bounds=...), reference tests/test_lsqfit.py:1779-1808) on the
+    single-fit path: (a) the reference's own test -- fcn(p) = p, data 0.9(1), 2.2(2), no prior, bounds [0, 0.5] x [0, 1]
+    -> the fit ends ON the upper bounds; (b) NIST problems with a box that cuts off the certified minimum for some
+    parameters, against scipy's own bounded trf (the oracle passes ``bounds`` through): same constrained minimum."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    from oracle.fit import nonlinear_fit as ofit
+    # ---- (a)
+    fit = lb.nonlinear_fit(data=(np.array([0.0, 1.0]), [0.9, 2.2], [0.1, 0.2]), fcn="gather", p0=[0.25, 0.5],
+                           bounds=([0.0, 0.0], [0.5, 1.0]))
+    assert abs(fit.pmean[0] - 0.5) < 1e-7 and abs(fit.pmean[1] - 1.0) < 1e-7          # assertAlmostEqual (7 places)
+    assert "bounds" in fit.description
+    # ---- (b)
+    for name in ("misra1a", "chwirut2", "gauss1", "rat42", "thurber"):
+        pr = next(q for q in nist_problems if q["name"] == name)
+        cert, p0 = np.array(pr["certified"]), np.array(pr["p0"])
+        lo = np.minimum(cert, p0) - 0.5 * np.abs(cert - p0) - 1e-3 * np.abs(cert)
+        hi = np.maximum(cert, p0) + 0.5 * np.abs(cert - p0) + 1e-3 * np.abs(cert)
+        # cut the box so that the first parameter cannot reach its certified value
+        mid = 0.5 * (cert[0] + p0[0])
+        if p0[0] < cert[0]:
+            hi[0] = mid
+        else:
+            lo[0] = mid
+        fo = ofit(pr["form"], np.array(pr["x"]), pr["y"], pr["ysdev"], prior_mean=pr["prior_mean"], prior_cov=pr["prior_sdev"],
+                  p0=p0, tol=1e-10, x_scale="jac", bounds=(lo, hi))
+        fd = _device_nist(pr, 1e-10, bounds=(lo, hi))
+        assert fd.error is None, name
+        assert np.all(fd.pmean >= lo) and np.all(fd.pmean <= hi), name
+        assert abs(fd.pmean[0] - mid) <= 1e-6 * abs(mid), (name, fd.pmean[0], mid)          # on the bound
+        assert abs(fo.pmean[0] - mid) <= 1e-6 * abs(mid), name
+        assert abs(fd.chi2 - fo.chi2) <= 1e-6 * fo.chi2, (name, fd.chi2, fo.chi2)
+        free = np.arange(1, len(cert))
+        assert np.max(np.abs(fd.pmean[free] - fo.pmean[free]) / fo.psdev[free]) < 1e-3, name
