@@ -539,10 +539,19 @@ __global__ void __launch_bounds__(WaveLayout<F, S_, CF_>::THREADS, MINB) fit_wav
             if (valid) {
                 if (lane < NP) pw[lane] = (req == 1 ? PV : PN)[lane * S1 + slot];
                 __syncwarp();
-                for (int r = lane; r < nk4; r += 32) {
+                // the means of this fit's rows come from global memory: issue the loads before the model arithmetic
+                double mpre[(WL::KMAX + 31) / 32];
+#pragma unroll
+                for (int u = 0; u < (WL::KMAX + 31) / 32; ++u) {
+                    const int r = lane + 32 * u;
+                    mpre[u] = r < bd.n_in ? mean[s_bidx[r]] : 0.0;
+                }
+                int u_row = 0;
+                for (int r = lane; r < nk4; r += 32, ++u_row) {
                     double* zr = Z + r * LDZ + NC * warp;
                     if (r < bd.n_in) {
                         const int idx = s_bidx[r];
+                        const double mean_r = u_row == 0 ? mpre[0] : mpre[(WL::KMAX + 31) / 32 - 1];
                         double dlt;
                         if (idx < P.ny) {
                             // functors that can split their terms evaluate both halves in one lane: the two
@@ -555,12 +564,12 @@ __global__ void __launch_bounds__(WaveLayout<F, S_, CF_>::THREADS, MINB) fit_wav
                             } else {
                                 f = F::value_grad(P.x + (size_t)idx * P.nx, idx, pw, 1.0, zr);
                             }
-                            dlt = f - mean[idx];
+                            dlt = f - mean_r;
                         } else {
                             const int j0 = idx - P.ny;
 #pragma unroll
                             for (int j = 0; j < NP; ++j) zr[j] = (j == j0) ? 1.0 : 0.0;
-                            dlt = pw[j0] - mean[idx];
+                            dlt = pw[j0] - mean_r;
                         }
                         zr[NP] = dlt;
                     } else {

@@ -226,9 +226,8 @@ class nonlinear_fit(object):
             seed = fresh_seed()
         self.last_seed = int(seed)
         if self._L is None:
-            C = self.yp_pdf.cov
-            val, vec = np.linalg.eigh(C)
-            self._L = vec * np.sqrt(np.clip(val, 0.0, None))
+            # L L^T = corrected covariance, from the device whitening's factors (no second eigen-decomposition on the host)
+            self._L = self.yp_pdf.sqrt_cov()
         return bootstrap_means(self.yp_pdf.mean, self._L, n, int(seed), first=first,
                                device=self.device)
 

@@ -25,23 +25,22 @@ def cov_blocks(cov):
     n = cov.shape[0]
     offdiag = (cov != 0)
     np.fill_diagonal(offdiag, False)
-    label = -np.ones(n, dtype=np.int64)
     if not offdiag.any():
         return np.arange(n, dtype=np.intp), []
+    # connected components of the non-zero pattern (compiled graph search; a Python DFS over a 7000 x 7000 pattern
+    # took seconds); rows without off-diagonal entries are the 1x1 blocks
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import connected_components
+    ncomp, comp = connected_components(csr_matrix(offdiag), directed=False)
+    single = ~offdiag.any(axis=1)
+    label = np.where(single, -1, comp).astype(np.int64)
     nlab = 0
-    rows_with = np.nonzero(offdiag.any(axis=1))[0]
-    for i in rows_with:
-        if label[i] >= 0:
-            continue
-        stack = [i]
-        label[i] = nlab
-        while stack:
-            j = stack.pop()
-            for k in np.nonzero(offdiag[j])[0]:
-                if label[k] < 0:
-                    label[k] = nlab
-                    stack.append(k)
-        nlab += 1
+    remap = {}
+    for l in label[label >= 0]:
+        if l not in remap:
+            remap[l] = nlab
+            nlab += 1
+    label = np.array([remap[l] if l >= 0 else -1 for l in label], dtype=np.int64)
     diag = np.nonzero(label < 0)[0].astype(np.intp)
     blocks = [np.nonzero(label == l)[0].astype(np.intp) for l in range(nlab)]
     blocks.sort(key=lambda b: b[0])
@@ -105,12 +104,30 @@ class PDF(object):
     @property
     def cov(self):
         """Corrected covariance of y (+) prior (the reference's ``yp_pdf.distribution``)."""
-        if self.cov_in is None:
-            return np.diag(self._cov_diag_only)
-        c = self.cov_in.copy()
-        for b, cb in self._corrected_blocks:
-            c[np.ix_(b, b)] = cb
-        return c
+        if getattr(self, "_cov_cache", None) is None:
+            if self.cov_in is None:
+                c = np.diag(self._cov_diag_only)
+            else:
+                c = self.cov_in.copy()
+                for b, cb in self._corrected_blocks:
+                    c[np.ix_(b, b)] = cb
+            c.setflags(write=False)                      # shared between accesses: read-only
+            self._cov_cache = c
+        return self._cov_cache
+
+    def sqrt_cov(self):
+        """L [N, M] with L L^T = the corrected covariance, WITHOUT another eigen-decomposition: per block
+        C_b W_b^T = D V Lambda^1/2 (W_b = Lambda^-1/2 V^T D^-1 from the device whitening); 1x1 entries: their sdev.
+        Used by the bootstrap generator (mean + L z; reference src/lsqfit/__init__.py:1615-1623 via gvar.bootstrap_iter)."""
+        idx0, w0 = self.i_invwgts[0]
+        M = len(idx0) + sum(W.shape[0] for _, W in self.i_invwgts[1:])
+        L = np.zeros((self.size, M))
+        L[idx0, np.arange(len(idx0))] = 1.0 / np.asarray(w0, dtype=float)
+        o = len(idx0)
+        for (b, W), (_, Cb) in zip(self.i_invwgts[1:], self._corrected_blocks):
+            L[np.ix_(b, np.arange(o, o + W.shape[0]))] = Cb @ W.T
+            o += W.shape[0]
+        return L
 
     def copy_with_mean(self, mean):
         """Simulated fits re-use the whitening and swap only the mean
