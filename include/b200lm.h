@@ -16,7 +16,8 @@
  *     never throws; b200lm_last_error() gives the message.  Non-convergence of a
  *     fit is data (status[] / stopping criterion), not an error -- the reference's
  *     convention (src/lsqfit/_gsl.pyx:686-717, src/lsqfit/_scipy.py:177-181)
- *   - a handle is thread-compatible: one handle per host thread
+ *   - a handle is thread-compatible: one handle per host thread, and ONE batch in flight per handle (its work queue and
+ *     statistics buffers belong to the launch in progress: use one handle per stream for concurrent batches)
  */
 #ifndef B200LM_H
 #define B200LM_H
@@ -156,7 +157,8 @@ int b200lm_residual_jacobian(b200lm_handle h, int B, const double* d_p, long lon
  * pivoted Cholesky + one-sided block Jacobi over the whole GPU, two-sided block Jacobi as fallback), then
  *   svdcut > 0 : eigenvalues < svdcut*max are replaced by svdcut*max (nmod counts them)
  *   svdcut < 0 : those modes are dropped (nout[k] < n[k])
- *   use_eps    : corr += eps*norm_inf(corr) I and inverse-Cholesky instead
+ *   use_eps    : corr += eps*norm_inf(corr) I and inverse-Cholesky instead; a non-positive pivot (block not positive
+ *                definite after the shift) is reported as d_nmod[k] = -(pivot index + 1)
  * Outputs: d_w (same layout as d_cov) rows W[i] = val_i^-1/2 vec_i D, largest eigenvalue
  * first, unused rows zero (for blocks > 112 the rows of the clamped null space are an arbitrary
  * orthonormal basis of it -- W^T W, i.e. the inverse of the corrected covariance, is the same); d_cov_out the corrected covariance; d_nout, d_nmod [nblk];

@@ -92,8 +92,16 @@ __global__ void __launch_bounds__(WH_THREADS) whiten_kernel(const __grid_constan
         for (int i = tid; i < n; i += WH_THREADS) A[i * ld + i] += shift;
         __syncthreads();
         // right-looking Cholesky, lower triangle of A
+        __shared__ int s_bad;
+        if (tid == 0) s_bad = 0;
         for (int j = 0; j < n; ++j) {
-            if (tid == 0) A[j * ld + j] = sqrt(A[j * ld + j]);
+            if (tid == 0) {
+                const double piv = A[j * ld + j];
+                // a non-positive pivot (eps <= 0, or a shift too small for an indefinite / rank-deficient block) would
+                // put NaNs into W, logdet and the corrected covariance: flag it (nmod = -(first bad pivot + 1))
+                if (!(piv > 0.0) && s_bad == 0) s_bad = j + 1;
+                A[j * ld + j] = sqrt(piv);
+            }
             __syncthreads();
             const double ljj = A[j * ld + j];
             for (int i = j + 1 + tid; i < n; i += WH_THREADS) A[i * ld + j] /= ljj;
@@ -131,7 +139,7 @@ __global__ void __launch_bounds__(WH_THREADS) whiten_kernel(const __grid_constan
         if (tid == 0) {
             a.logdet[blk] = s_red[0];
             a.nout[blk] = n;
-            a.nmod[blk] = shift > 0.0 ? n : 0;
+            a.nmod[blk] = s_bad ? -s_bad : (shift > 0.0 ? n : 0);
         }
         return;
     }

@@ -161,6 +161,11 @@ def whiten_blocks(ns, cov_flat, svdcut, eps, device=0, as_torch=False):
         float(svdcut) if svdcut is not None else 0.0, float(eps) if eps is not None else 0.0, use_eps,
         d_w.data_ptr(), d_cc.data_ptr(), d_nout.data_ptr(), d_nmod.data_ptr(), d_ld.data_ptr(),
         C.c_void_p(stream)))
+    nmod_h = d_nmod.cpu().numpy()
+    if use_eps and np.any(nmod_h < 0):
+        k = int(np.nonzero(nmod_h < 0)[0][0])
+        raise ValueError("eps regulator: block %d (n = %d) is not positive definite after the shift (pivot %d <= 0); "
+                         "increase eps or use svdcut" % (k, int(ns[k]), -int(nmod_h[k]) - 1))
     if as_torch:
         return d_w, d_cc, d_nout.cpu().numpy(), d_nmod.cpu().numpy(), d_ld.cpu().numpy()
     return (d_w.cpu().numpy(), d_cc.cpu().numpy(), d_nout.cpu().numpy(), d_nmod.cpu().numpy(),

@@ -1116,3 +1116,19 @@ def test_bounds(nist_problems):
         assert abs(fd.chi2 - fo.chi2) <= 1e-6 * fo.chi2, (name, fd.chi2, fo.chi2)
         free = np.arange(1, len(cert))
         assert np.max(np.abs(fd.pmean[free] - fo.pmean[free]) / fo.psdev[free]) < 1e-3, name
+
+
+def test_eps_regulator_flags_indefinite_block():
+    """eps branch of the whitening (inverse Cholesky): a block that is not positive definite after the shift must be
+    reported, not turned into NaN weights (small blocks: d_nmod < 0 -> ValueError; large blocks: B200LM_EINVAL)."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((6, 3))
+    cov = a @ a.T                                   # rank 3 of 6
+    cov[0, 0] -= 2.0 * abs(cov[0, 0])               # and indefinite
+    with pytest.raises(ValueError, match="not positive definite"):
+        lb.PDF(np.zeros(6), cov, svdcut=None, eps=1e-12)
+    good = a @ a.T + 0.5 * np.eye(6)
+    pdf = lb.PDF(np.zeros(6), good, svdcut=None, eps=1e-12)
+    assert np.isfinite(pdf.logdet) and all(np.all(np.isfinite(w)) for _, w in pdf.i_invwgts)
