@@ -60,7 +60,9 @@ def build(force=False, verbose=True):
     os.makedirs(BUILD, exist_ok=True)
     hdig = _headers_digest()
     srcs = _sources()
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+    # largest translation units first, one nvcc per core
+    srcs.sort(key=lambda f: -os.path.getsize(os.path.join(CSRC, f)) if not f.startswith("inst_") else -10 ** 9)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(os.cpu_count() or 8, len(srcs))) as ex:
         results = list(ex.map(lambda s: _compile(s, hdig, force), srcs))
     objs = [o for o, _ in results]
     rebuilt = any(ch for _, ch in results)

@@ -69,6 +69,7 @@ static std::vector<FunctorEntry>& registry() {
         e = registry_nist_b(&n);   r.insert(r.end(), e, e + n);
         e = registry_misc(&n);     r.insert(r.end(), e, e + n);
         e = registry_misc_b(&n);   r.insert(r.end(), e, e + n);
+        e = registry_poly_b(&n);   r.insert(r.end(), e, e + n);
     }
     return r;
 }
@@ -317,6 +318,7 @@ int b200lm_fit_batch(b200lm_handle h, int B,
     // (B200LM_TEAM = 0/1, 2, 4 overrides the default policy)
     int team = default_team(h);
     if (const char* env = getenv("B200LM_TEAM")) team = atoi(env);
+    if (h->policy == 1) team = 1;            // the GSL decisions are compiled into the one-warp kernel only (fit_kernel<F, 1>)
     const int ti = team == 4 ? 1 : (team == 2 ? 0 : -1);
     if (team == 32 && wave_ok(h)) {
         // wave kernel: the trust-region loops of 32 fits per CTA in lock step, then covariance / log det / f / J

@@ -1,15 +1,9 @@
-// Kernel instantiations: the spline model of examples/spline.py, larger polynomials (tests/test_lsqfit.py:878-880 fits 25 coefficients) and the
+// Kernel instantiations: the spline model of examples/spline.py and the
 // shared-energy composite models of simultaneous (MultiFitter) correlator fits.
 #define B200LM_DEFINE_ENTRIES
 #include "registry.h"
 namespace b200lm {
 static const FunctorEntry kEntries[] = {
-    B200LM_ENTRY(F_POLY, "poly", Poly<8>),
-    B200LM_ENTRY(F_POLY, "poly", Poly<10>),
-    B200LM_ENTRY(F_POLY, "poly", Poly<12>),
-    B200LM_ENTRY(F_POLY, "poly", Poly<16>),
-    B200LM_ENTRY(F_POLY, "poly", Poly<20>),
-    B200LM_ENTRY(F_POLY, "poly", Poly<25>),
     B200LM_ENTRY(F_SPLINE_POLY, "spline_poly", SplinePoly<4, 5>),      // examples/spline.py
     B200LM_ENTRY(F_SPLINE_POLY, "spline_poly", SplinePoly<4, 0>),
     B200LM_ENTRY(F_SPLINE_POLY, "spline_poly", SplinePoly<6, 0>),

@@ -1010,7 +1010,10 @@ struct PhaseClock {
 };
 
 
-template <class F, class EV>
+// MODE selects what is COMPILED into a kernel (the trust-region loop is the hot code: every policy it does not run
+// would only cost registers and instruction cache):  0 = scipy TRF decisions (the default kernels),  1 = GSL trust/lm
+// decisions (b200lm_set_policy),  2 = no loop at all: finalisation of fits the wave kernel has already converged.
+template <class F, class EV, int MODE = 0>
 __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& P, int b,
                                         unsigned long long& tot_nfev, unsigned long long& tot_njev,
                                         unsigned long long& tot_nfac, PhaseClock& pk) {
@@ -1032,7 +1035,7 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
         int nfev = 1, njev = 1, nfac = 0;
         int status = -2;                         // -2: running
         if (!isfinite(cost)) status = -1;
-        else if (P.finalize_only) status = P.status[b];      // the wave kernel has done the trust-region loop (lm_wave.cuh)
+        else if (MODE == 2) status = P.status[b];            // the wave kernel has done the trust-region loop (lm_wave.cuh)
         // scale_inv_j = |J_j| = sqrt(A_jj)   (More': running max; scaler 0: 1)
         double sinv = 1.0;
         if (act && P.scaler == 1) {
@@ -1047,7 +1050,7 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
         lm.valid = false; lm.a = 0.0; lm.b = 0.0;
 
         int nit_report = -1;                      // what P.nit reports when it is not nfev (GSL policy: iterations)
-        if (P.policy == 1 && status == -2) {
+        if (MODE == 1 && status == -2) {
             // ---- GSL trust-region driver with the Levenberg-Marquardt sub-problem (gsl_multifit_nlinear: trust.c,
             // lm.c, nielsen.c, scaling.c, convergence.c, fdf.c as called by the reference's src/lsqfit/_gsl.pyx:563-723;
             // CPU restatement: oracle/gsl_lm.py).  One factorisation per trial: (D^-1 J^T J D^-1 + mu I) (D dx) = -D^-1 g.
@@ -1137,7 +1140,7 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
             sinv = diag;
         }
 
-        while (status == -2) {
+        while (MODE == 0 && status == -2) {
             const double gi = act ? c.g[lane] : 0.0;
             // |g|_inf and |x|^2 of the current point in one reduction (x does not change until a step is accepted)
             double xx = 0.0, g_norm = fabs(gi);
@@ -1328,7 +1331,7 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
         if (act) P.x_out[(size_t)b * NP + lane] = c.p[lane];
         if (lane == 0) {
             P.chi2[b] = 2.0 * cost;
-            if (!P.finalize_only) {
+            if (MODE != 2) {
                 P.nit[b] = nit_report >= 0 ? nit_report : nfev;
                 P.status[b] = status;
             } else if (nfev > 1) {
@@ -1336,14 +1339,14 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
             }
             if (P.logdet) P.logdet[b] = ld;
         }
-        if (P.finalize_only) { --nfev; --njev; }
+        if (MODE == 2) { --nfev; --njev; }
         tot_nfev += nfev; tot_njev += njev; tot_nfac += nfac;
         pk.total += B200LM_CLOCK() - t_fit0;
         __syncwarp();
     }
 }
 
-template <class F>
+template <class F, int MODE = 0>
 __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(const __grid_constant__ FitParams P) {
     typedef FitLayout<F> Lay;
     static_assert(Lay::NP <= 32, "one lane per parameter");
@@ -1361,7 +1364,7 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
         if (lane == 0) b = atomicAdd(P.counter, 1);
         b = __shfl_sync(B200LM_FULL, b, 0);
         if (b >= P.B) break;
-        fit_one<F>(c, ev, P, b, tot_nfev, tot_njev, tot_nfac, pk);
+        fit_one<F, WarpEval<F>, MODE>(c, ev, P, b, tot_nfev, tot_njev, tot_nfac, pk);
     }
     if (lane == 0 && P.stats) {
         atomicAdd(&P.stats[0], tot_nfev);
@@ -1431,15 +1434,22 @@ inline cudaError_t plan_launch(FitParams& P, int sm_count, size_t smem_budget, L
     return cudaSuccess;
 }
 
+template <class F, int MODE>
+cudaError_t launch_fit_mode(const FitParams& P, const LaunchInfo& li, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(fit_kernel<F, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)li.smem);
+    if (e != cudaSuccess) return e;
+    fit_kernel<F, MODE><<<li.grid, li.block, li.smem, stream>>>(P);
+    return cudaGetLastError();
+}
+
 template <class F>
 cudaError_t launch_fit(FitParams P, int sm_count, size_t smem_budget, cudaStream_t stream) {
     LaunchInfo li;
     cudaError_t e = plan_launch<F>(P, sm_count, smem_budget, li);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(fit_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)li.smem);
-    if (e != cudaSuccess) return e;
-    fit_kernel<F><<<li.grid, li.block, li.smem, stream>>>(P);
-    return cudaGetLastError();
+    if (P.finalize_only) return launch_fit_mode<F, 2>(P, li, stream);
+    if (P.policy == 1) return launch_fit_mode<F, 1>(P, li, stream);
+    return launch_fit_mode<F, 0>(P, li, stream);
 }
 
 template <class F>

@@ -33,6 +33,7 @@ const FunctorEntry* registry_nist_a(int* n);
 const FunctorEntry* registry_nist_b(int* n);
 const FunctorEntry* registry_misc(int* n);
 const FunctorEntry* registry_misc_b(int* n);
+const FunctorEntry* registry_poly_b(int* n);
 
 }  // namespace b200lm
 
