@@ -8,7 +8,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/bench_under_ncu_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:fit_ -s 3 -c 1 -f -o /tmp/prof_$TAG \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/bench_under_ncu2_$TAG.log 2>&1
-B200LM_WAVE_CFG=1 ncu --set full --clock-control none --import-source on -k regex:fit_wave -s 1 -c 1 -f -o /tmp/prof_${TAG}_wave \
+ncu --set full --clock-control none --import-source on -k regex:fit_wave -s 1 -c 1 -f -o /tmp/prof_${TAG}_wave \
     python tools/wave_prof.py 160000 > gpurun_out/prof_${TAG}_wave.log 2>&1
 for t in $TAG ${TAG}_wave; do
   { python tools/ncu_stalls.py /tmp/prof_$t.ncu-rep; python tools/ncu_funcs.py /tmp/prof_$t.ncu-rep 2>/dev/null | head -25; python tools/ncu_lines.py /tmp/prof_$t.ncu-rep 25; } > gpurun_out/ncu_$t.txt 2>&1

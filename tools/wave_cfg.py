@@ -18,7 +18,7 @@ def main():
     tol, maxit = (1e-8, 1e-10, 1e-10), 1000
     means = torch.as_tensor(configs.bootstrap_means(cfg, 2000, 11, cov=pdf.cov[:ny, :ny])).cuda()
     a, _, sa = run(plan, means, p0, 1, tol, maxit)
-    for wc in (0, 1, 2):
+    for wc in (0,):
         os.environ["B200LM_WAVE_CFG"] = str(wc)
         b, _, sb = run(plan, means, p0, 32, tol, maxit)
         r = compare(a, b)
@@ -26,7 +26,7 @@ def main():
         print(json.dumps(r), flush=True)
     for B in sizes:
         means = torch.as_tensor(configs.bootstrap_means(cfg, B, 12345, cov=pdf.cov[:ny, :ny])).cuda()
-        for team, wc in ((1, 0), (4, 0), (32, 0), (32, 1), (32, 2)):
+        for team, wc in ((1, 0), (4, 0), (32, 0)):
             os.environ["B200LM_WAVE_CFG"] = str(wc)
             _, ms, st = run(plan, means, p0, team, tol, maxit, reps=3)
             print(json.dumps(dict(B=B, team=plan.last_team(), wave_cfg=wc if team == 32 else None, ms=round(ms, 3),
