@@ -418,7 +418,11 @@ def c4_strong(torch, dist, lb, configs, lbdist, dev, rank, world, B=1000000, com
     val, vec = np.linalg.eigh(pdf.cov)
     L = vec * np.sqrt(np.clip(val, 0, None)); L[ny:, :] = 0.0      # simulated fits: prior means fixed
     Ld, m0d, p0d = torch.as_tensor(L).to(dev), torch.as_tensor(mean0).to(dev), torch.as_tensor(cfg["p0"]).to(dev)
-    plan = lb.Plan("multiexp", npar, ny, cfg["x"], pdf.i_invwgts, device=dev.index)
+    # BENCH kernel choice for this job: the wave kernel (lm_wave.cuh) -- a million fits saturate every kernel, which is
+    # its regime (measured on this shape: 21.3 M vs 18.4 M fits/s for one warp per fit; same parity bars,
+    # tests/test_gpu_configs.py); B200LM_C4_TEAM overrides (0 = the default kernel of the shape)
+    c4_team = int(os.environ.get("B200LM_C4_TEAM", "32"))
+    plan = lb.Plan("multiexp", npar, ny, cfg["x"], pdf.i_invwgts, device=dev.index, team=c4_team or None)
     lo, hi = lbdist.shard_range(B, rank, world)
 
     def job():
@@ -448,12 +452,13 @@ def c4_strong(torch, dist, lb, configs, lbdist, dev, rank, world, B=1000000, com
     tt = torch.tensor([float(nfev)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt)
+    kernel_used = plan.last_team()
     plan.close()
     ms = float(t[0])
     bias = float(torch.max(torch.abs(m - p0d) / torch.sqrt(torch.diagonal(c)) * (n ** 0.5)))
     return dict(workload="C4: 3-exp correlator, 10^6 simulated fits sharded over the ranks (generate + fit + gather + moments)",
                 B=B, n_gpus=world, ms=ms, fits_per_s=B / ms * 1e3, scaling="strong", converged=int(n),
-                gathered_rows=int(allp.shape[0]), nfev_per_fit=float(tt[0]) / B,
+                gathered_rows=int(allp.shape[0]), nfev_per_fit=float(tt[0]) / B, kernel_used=kernel_used,
                 pmean_minus_pexact_in_sigma_of_mean=bias,
                 note="the mean of the best-fit parameters is BIASED with respect to pexact at second order in the noise "
                      "(nonlinear model, prior pull); tests/test_gpu_parity.py::test_c4_bias_matches_oracle shows the CPU "
