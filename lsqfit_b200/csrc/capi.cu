@@ -44,19 +44,6 @@ void fill_params(b200lm_handle_s* h, FitParams& P) {
 }
 }  // namespace b200lm
 
-namespace b200lm {
-// fixed-order sum of the per-CTA partial rows of normal_diag_kernel (lm_rows.cuh): one warp per accumulator, lane l
-// adds rows l, l + 32, ... in order, then a shuffle tree -- the same association on every run (deterministic results)
-// without the serial chain of nparts dependent loads
-__global__ void sum_partials_kernel(int nparts, int nacc, const double* __restrict__ partial, double* __restrict__ out) {
-    const int k = blockIdx.x, lane = threadIdx.x;
-    if (k >= nacc) return;
-    double v = 0.0;
-    for (int q = lane; q < nparts; q += 32) v += partial[(size_t)q * nacc + k];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) out[k] = v;
-}
-}  // namespace b200lm
 
 static std::vector<FunctorEntry>& registry() {
     static std::vector<FunctorEntry> r;
@@ -402,18 +389,26 @@ int b200lm_normal_diag(b200lm_handle h, const double* d_p, const double* d_y, co
     if (!h->fe->normal_diag) return set_error(h, B200LM_ESIZE, "normal_diag needs np <= 8 (use b200lm_model_rows + b200lm_dgemm)");
     CUDA_TRY(h, cudaSetDevice(h->device), "cudaSetDevice");
     const int nacc = h->np * (h->np + 1) / 2 + h->np + 1;
-    const int max_parts = 4 * h->sm_count;
-    const size_t need = (size_t)max_parts * nacc * sizeof(double);
+    const int max_parts = b200lm::ND_MAX_PARTS_PER_SM * h->sm_count;
+    // per-CTA partial rows + the arrival counter of the in-kernel reduction (zero between launches: the kernel resets it;
+    // b200lm_propagate shares this buffer as plain scratch, so it is cleared again whenever the two calls alternate)
+    const size_t need = (size_t)max_parts * nacc * sizeof(double) + sizeof(double);
     if (need > h->scratch_bytes) {
         if (h->d_scratch) cudaFree(h->d_scratch);
         h->d_scratch = nullptr; h->scratch_bytes = 0;
         CUDA_TRY(h, cudaMalloc((void**)&h->d_scratch, need), "scratch allocation");
         h->scratch_bytes = need;
+        h->scratch_counter_clean = false;
+    }
+    if (!h->scratch_counter_clean) {
+        CUDA_TRY(h, cudaMemsetAsync((char*)h->d_scratch + (size_t)max_parts * nacc * sizeof(double), 0, sizeof(double),
+                                    (cudaStream_t)stream), "reset arrival counter");
+        h->scratch_counter_clean = true;
     }
     CUDA_TRY(h, h->fe->normal_diag(h->ny, h->nx, h->d_x, d_p, d_y, d_w, h->d_scratch, max_parts, d_out, h->sm_count,
                                    (cudaStream_t)stream), "normal_diag kernel launch");
     h->last_stream = (cudaStream_t)stream;
-    h->launches += 2;
+    h->launches += 1;
     return B200LM_OK;
 }
 

@@ -39,6 +39,7 @@ struct b200lm_handle_s {
     cudaStream_t own_stream = nullptr;
     // scratch for propagate
     double* d_scratch = nullptr; size_t scratch_bytes = 0;
+    bool scratch_counter_clean = false;       // normal_diag's arrival counter (behind its partial rows) is zero
     std::string err;
 };
 

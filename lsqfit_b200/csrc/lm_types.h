@@ -17,6 +17,9 @@ struct BlockDesc {
     int wt2_off;     // offset into blk_wt2[]
 };
 
+// normal_diag_kernel (lm_rows.cuh): rows of the per-CTA partial buffer that b200lm_normal_diag allocates per SM
+constexpr int ND_MAX_PARTS_PER_SM = 8;
+
 struct FitParams {
     // ---- problem description (shared by every fit of the batch) ----------
     int ny, np, N, nchiv, nx, noprior;

@@ -55,6 +55,7 @@ extern "C" int b200lm_propagate(b200lm_handle h, int B, const double* d_x, const
         if (e != cudaSuccess) return cuda_fail(h, e, "scratch allocation");
         h->scratch_bytes = need;
     }
+    h->scratch_counter_clean = false;          // (b200lm_normal_diag keeps an arrival counter in this buffer)
     double* dJ = h->d_scratch;
     double* dM = dJ + nJ;
     double* dT = dM + nM;

@@ -60,6 +60,30 @@ class _LA(object):
         assert (B2.shape[1] if transB else B2.shape[0]) == K
         if out is None:
             out = self.empty(M, N) if (B.dim() == 2 or transB) else self.empty(M)
+        if transA and not transB and M <= 128 and N <= 128 and K >= 65536:
+            # A^T B with a small result and a very long contraction (J^T J of a fit with a handful of parameters and
+            # millions of rows): one output tile would leave the whole sum to ONE CTA.  Split K over the batch
+            # dimension of b200lm_dgemm -- chunk c of A and B starts c * Kc rows further down -- and add the
+            # partial products in a fixed order (deterministic).
+            Kc = 2048
+            S = K // Kc
+            part = self.empty(S, M, N)
+            _cabi.check(_cabi.lib.b200lm_dgemm(self.device, 1, 0, S, M, N, Kc, 1.0, A2.data_ptr(), Kc * A2.stride(0),
+                                               A2.stride(0), B2.data_ptr(), Kc * B2.stride(0), B2.stride(0), 0.0,
+                                               part.data_ptr(), M * N, N, self.stream()))
+            self.launches += 1
+            res = part.sum(0)
+            if K > S * Kc:
+                tail = self.empty(M, N)
+                self.gemm(True, False, M, N, K - S * Kc, 1.0, A2[S * Kc:], A2.stride(0), B2[S * Kc:], B2.stride(0), 0.0,
+                          tail, N)
+                res += tail
+            res = res.reshape(out.shape)
+            if beta == 0.0:
+                out.copy_(res if alpha == 1.0 else alpha * res)
+            else:
+                out.mul_(beta).add_(res, alpha=alpha)
+            return out
         self.gemm(transA, transB, M, N, K, alpha, A2, A2.stride(0), B2, B2.stride(0), beta, out,
                   out.stride(0) if out.dim() == 2 else 1)
         return out

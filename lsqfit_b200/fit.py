@@ -77,9 +77,16 @@ class nonlinear_fit(object):
 
     def __init__(self, data=None, fcn=None, prior=None, p0=None, svdcut=False, eps=False,
                  tol=1e-8, maxit=1000, fitter="b200_lm", yp_cov=None, _yp_pdf=None,
-                 **fitterargs):
+                 noise=False, noise_seed=None, **fitterargs):
         clock = time.perf_counter()
         svdcut, eps = resolve_svdcut_eps(svdcut, eps)
+        # noise = (svd noise, prior noise), a bool meaning both (src/lsqfit/__init__.py:493-499, 516)
+        self.noise = (bool(noise), bool(noise)) if isinstance(noise, (bool, np.bool_)) else tuple(bool(v) for v in noise)
+        if len(self.noise) != 2:
+            raise ValueError("noise must be a bool or a pair of bools")
+        if any(self.noise) and noise_seed is None:
+            noise_seed = fresh_seed()
+        self.noise_seed = noise_seed
         if fitter not in nonlinear_fit.FITTERS:
             raise ValueError("unknown fitter: " + str(fitter))      # __init__.py:529-530
         if isinstance(fcn, str):
@@ -107,6 +114,13 @@ class nonlinear_fit(object):
             pmean = np.array(prior[0], dtype=float).reshape(-1)
             npar = pmean.size
             pcov = _cov2(prior[1], npar)
+            if self.noise[1]:
+                # __init__.py:535-536: prior means fluctuate by one sample of the prior's own distribution
+                # (device Philox normals; the factor of an np x np covariance is host work)
+                from .bootstrap import normals
+                Lp = np.linalg.cholesky(pcov) if np.count_nonzero(pcov - np.diag(np.diag(pcov))) else np.diag(np.sqrt(np.diag(pcov)))
+                pmean = pmean + Lp @ normals(npar, int(noise_seed) ^ 0x9E3779B97F4A7C15,
+                                             device=int(fitterargs.get("device", 0))).cpu().numpy()
         N = ny if noprior else ny + npar
         mean = ymean if noprior else np.concatenate([ymean, pmean])
         # ---- whitening (device) : __init__.py:539-561 ------------------------------
@@ -122,7 +136,12 @@ class nonlinear_fit(object):
                     yp_cov[:ny, :ny] = _cov2(yerr, ny)
                     if not noprior:
                         yp_cov[ny:, ny:] = pcov
-            pdf = PDF(mean, yp_cov, svdcut=svdcut, eps=eps, device=self.device)
+            pdf = PDF(mean, yp_cov, svdcut=svdcut, eps=eps, device=self.device, noise=self.noise[0],
+                      noise_seed=noise_seed)
+            mean = pdf.mean                       # with the svd noise, if any (y.flat = yp_pdf.distribution, __init__.py:1896-1900)
+            ymean = mean[:ny]
+            if not noprior:
+                pmean = mean[ny:]
         else:
             pdf = _yp_pdf.copy_with_mean(mean)
         self.yp_pdf = pdf

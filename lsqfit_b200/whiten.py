@@ -51,7 +51,7 @@ class PDF(object):
     """Whitened Gaussian distribution of y (+) prior (attribute-compatible with gvar.PDF
     as far as lsqfit reads it)."""
 
-    def __init__(self, mean, cov, svdcut=1e-12, eps=None, device=0):
+    def __init__(self, mean, cov, svdcut=1e-12, eps=None, device=0, noise=False, noise_seed=None):
         mean = np.array(mean, dtype=float).reshape(-1)
         cov = np.asarray(cov, dtype=float)
         if cov.ndim == 1:
@@ -100,6 +100,32 @@ class PDF(object):
                 nchiv += int(nout[k])
                 o += n * n
         self.nchiv = nchiv
+        self.noise = bool(noise)
+        self.noise_seed = None
+        if self.noise:
+            # gvar.PDF(..., noise=True) as called at src/lsqfit/__init__.py:1895,1898: the means receive one random
+            # sample of the uncertainty ADDED by the svd cut / eps regulator (covariance: corrected - original)
+            from .fit import fresh_seed
+            self.noise_seed = fresh_seed() if noise_seed is None else int(noise_seed)
+            self.mean += self.svd_noise(1, self.noise_seed)[0]
+
+    def svd_noise(self, n, seed, first=0):
+        """[n, N] samples of N(0, corrected covariance - input covariance): the noise ``noise=True`` adds to the means
+        (zero for entries the regulator did not touch).  Factor of the correction by Cholesky with a relative shift of
+        1e-13 (the correction is positive semi-definite and usually of low rank), normals from the device Philox
+        stream of ``seed``, the product by the bootstrap generator's GEMM."""
+        from .bootstrap import bootstrap_means
+        out = np.zeros((n, self.size))
+        for k, (b, cb) in enumerate(self._corrected_blocks):
+            d = cb - self.cov_in[np.ix_(b, b)]
+            d = 0.5 * (d + d.T)
+            scale = float(np.max(np.diag(cb)))
+            if not np.any(np.abs(d) > 1e-15 * scale):
+                continue
+            L = _psd_factor(d, 1e-13 * scale, self.device)
+            # one Philox key per block: the blocks' samples are independent
+            out[:, b] = bootstrap_means(np.zeros(b.size), L, n, int(seed) + k, first=first, device=self.device).cpu().numpy()
+        return out
 
     @property
     def cov(self):
@@ -137,6 +163,23 @@ class PDF(object):
         new.mean = np.array(mean, dtype=float).reshape(-1)
         new.meanflat = new.mean
         return new
+
+
+def _psd_factor(d, shift, device):
+    """L with L L^T = d + shift I for a positive semi-definite d: LAPACK on the host for small blocks, the library's own
+    blocked Cholesky (b200lm_potrf) above that."""
+    n = d.shape[0]
+    if n <= 256:
+        return np.linalg.cholesky(d + shift * np.eye(n))
+    from .dense import _LA
+    la = _LA(device)
+    A = torch.as_tensor(np.ascontiguousarray(d)).to(la.tdev)
+    L = la.empty(n, n)
+    linv = la.empty(n, n)
+    info = torch.zeros(1, dtype=torch.int32, device=la.tdev)
+    if not la.potrf(A, shift, L, linv, info):
+        raise ValueError("svd noise: the covariance correction is not positive semi-definite")
+    return torch.tril(L)
 
 
 def whiten_blocks(ns, cov_flat, svdcut, eps, device=0, as_torch=False):
