@@ -172,6 +172,33 @@ def _minimize_quadratic_1d(a, b, lb, ub, c=0.0):
     return t[i], y[i]
 
 
+# ---- robust loss functions: scipy's ``loss`` / ``f_scale`` (lsqfit.scipy_least_squares passes them on, reference
+# src/lsqfit/_scipy.py:56-79, 156-161).  scipy is third party; restated from scipy/optimize/_lsq/least_squares.py
+# (IMPLEMENTED_LOSSES, construct_loss_function) and common.py (scale_for_robust_loss_function): the cost is
+# 1/2 C^2 sum rho(f_i^2 / C^2), and the trust-region model uses rows of J and f scaled by functions of rho', rho''.
+LOSSES = ("linear", "huber", "soft_l1", "cauchy", "arctan")
+_EPS = float(np.finfo(float).eps)
+
+
+def _rho(loss, z):
+    """(rho, rho', rho'') at z = (f / f_scale)^2 as device vectors."""
+    if loss == "huber":
+        m = z <= 1.0
+        zs = torch.where(m, torch.ones_like(z), z)              # (keeps the unused branch finite)
+        return (torch.where(m, z, 2.0 * zs ** 0.5 - 1.0), torch.where(m, torch.ones_like(z), zs ** -0.5),
+                torch.where(m, torch.zeros_like(z), -0.5 * zs ** -1.5))
+    if loss == "soft_l1":
+        t = 1.0 + z
+        return 2.0 * (t ** 0.5 - 1.0), t ** -0.5, -0.5 * t ** -1.5
+    if loss == "cauchy":
+        t = 1.0 + z
+        return torch.log1p(z), 1.0 / t, -1.0 / t ** 2
+    if loss == "arctan":
+        t = 1.0 + z ** 2
+        return torch.atan(z), 1.0 / t, -2.0 * z / t ** 2
+    raise ValueError("`loss` must be one of %s" % (LOSSES,))
+
+
 def _dense_weights(pdf, n):
     """the whitening of a PDF (``i_invwgts``: 1x1 weights + block matrices) as ONE dense [nchiv, n] matrix"""
     W = np.zeros((pdf.nchiv, n))
@@ -198,8 +225,15 @@ class DenseFit(object):
     """
 
     def __init__(self, data, prior, p0=None, svdcut=False, eps=False, tol=1e-8, maxit=1000, scaler="more",
-                 polish=0, device=0, pdf=None, fcn="multiexp", spec=None, bounds=None):
+                 polish=0, device=0, pdf=None, fcn="multiexp", spec=None, bounds=None, loss="linear", f_scale=1.0):
         from .fit import resolve_svdcut_eps
+        if loss not in LOSSES:
+            raise ValueError("`loss` must be one of %s" % (LOSSES,))
+        self.loss, self.f_scale = loss, float(f_scale)
+        if not self.f_scale > 0.0:
+            raise ValueError("`f_scale` must be positive")
+        self.robust = loss != "linear"
+        self._prow = None                                       # row scale of the prior residuals (robust loss only)
         from .functors import Functor
         svdcut, eps = resolve_svdcut_eps(svdcut, eps)
         la = self.la = _LA(device)
@@ -331,7 +365,8 @@ class DenseFit(object):
         self.dof = self.nchiv - self.np
         # ---- workspaces ----
         n = self.np
-        self.fused = self.wdiag is not None and self._h is not None and n <= 8      # b200lm_normal_diag in the loop
+        # b200lm_normal_diag in the loop (a robust loss rescales every row: materialised passes)
+        self.fused = self.wdiag is not None and self._h is not None and n <= 8 and not self.robust
         self.G = la.empty(self.ny, n)
         self.delta = la.empty(self.ny)
         self.J = self.G if self.wdiag is not None else la.empty(nd, n)             # (uncorrelated: J = diag(w) G in place)
@@ -401,16 +436,42 @@ class DenseFit(object):
         return self._data_residual(p), self._prior_residual(p)
 
     def _add_prior(self, fp, g):
+        if self._prow is not None:                               # robust loss: prior rows scaled like every other row
+            if self.Wp is None:
+                w = self.d_wp * self._prow
+                self.A.diagonal().add_(w ** 2)
+                return g + w * fp
+            Wps = self.Wp * self._prow[:, None]
+            self.la.mm(Wps, Wps, transA=True, out=self.A, beta=1.0)
+            return g + self.la.mm(Wps, fp, transA=True)
         if self.Wp is None:
             self.A.diagonal().add_(self.d_wp ** 2)
             return g + self.d_wp * fp
         self.A.add_(self.PtP)
         return g + self.la.mm(self.Wp, fp, transA=True)
 
-    def jacobian(self, p, materialize=False):
+    def _cost(self, fd, fp):
+        """1/2 |f|^2, or scipy's robust cost 1/2 C^2 sum rho((f/C)^2) over data AND prior residuals."""
+        if not self.robust:
+            return 0.5 * float(fd @ fd + fp @ fp)
+        c = self.f_scale                                         # z = (f / C)^2 exactly as scipy forms it (same side of huber's kink)
+        return 0.5 * c * c * float(torch.sum(_rho(self.loss, (fd / c) ** 2)[0]) + torch.sum(_rho(self.loss, (fp / c) ** 2)[0]))
+
+    def _robust_rows(self, f):
+        """scale_for_robust_loss_function: (row scale of J, scaled residuals)."""
+        z = (f / self.f_scale) ** 2
+        _, r1, r2 = _rho(self.loss, z)
+        js = torch.sqrt(torch.clamp(r1 + 2.0 * (r2 / self.f_scale ** 2) * f ** 2, min=_EPS))     # (scipy's order of operations)
+        return js, f * r1 / js
+
+    def jacobian(self, p, materialize=False, robust=None):
         """Normal matrix into self.A (and J_data = W.G into self.J unless the fused one-pass kernel is used);
-        returns (fd, fp, g).  In fused mode fd is None and self.cost_data holds f_data . f_data."""
+        returns (fd, fp, g).  In fused mode fd is None and self.cost_data holds f_data . f_data.  With a robust loss
+        (``robust``, default self.robust) J, f and the prior rows are the SCALED ones of scipy's trust-region model and
+        self.cost_true holds the robust cost of the unscaled residuals."""
         la = self.la
+        robust = self.robust if robust is None else robust
+        self._prow = None
         fp = self._prior_residual(p)
         self.nfev_jac += 1
         if self.fused and not materialize:
@@ -434,6 +495,11 @@ class DenseFit(object):
             la.mm(self.Wd, self.G, out=self.J)
             if self.Wpj is not None:
                 self.J.add_(self.Wpj)
+        if robust:
+            self.cost_true = self._cost(fd, fp)
+            jd, fd = self._robust_rows(fd)
+            self._prow, fp = self._robust_rows(fp)
+            self.J.mul_(jd[:, None])
         la.mm(self.J, self.J, transA=True, out=self.A)
         g = la.mm(self.J, fd, transA=True)
         self.cost_data = fd @ fd
@@ -566,7 +632,7 @@ class DenseFit(object):
         self.nfev_jac = self.nfac = 0
         fd, fp, g = self.jacobian(x)
         nfev = 1
-        cost = 0.5 * float(self.cost_data + fp @ fp)
+        cost = self.cost_true if self.robust else 0.5 * float(self.cost_data + fp @ fp)
         more = self.scaler == "more"
 
         def colnorm():
@@ -629,7 +695,7 @@ class DenseFit(object):
                 fd_new, fp_new = self.residual(x_new)
                 nfev += 1
                 shn = float(torch.linalg.vector_norm(step_h))
-                cost_new = 0.5 * float(fd_new @ fd_new + fp_new @ fp_new)
+                cost_new = self._cost(fd_new, fp_new)
                 if not np.isfinite(cost_new):
                     Delta = 0.25 * shn
                     continue
@@ -675,7 +741,7 @@ class DenseFit(object):
             torch.mul(self.A, dd, out=self.As)
             ok, sh, _, _ = self._factor_solve(0.0, d * g)
             return ok, sh, (-float((d * g) @ sh) if ok else np.inf)
-        if self.polish > 0 and not bounded:                      # (undamped steps would leave the feasible region)
+        if self.polish > 0 and not bounded and not self.robust:   # (undamped steps would leave the feasible region)
             ok, sh, dec = gn(g)
             for _ in range(self.polish):
                 if not ok or not (dec > 1e-30 * max(1.0, 2 * cost)):
@@ -699,6 +765,10 @@ class DenseFit(object):
         self.error = error
         self.x = x
         self.pmean = x.cpu().numpy()
+        prow = self._prow                                        # (scaled rows: the covariance below is that of scipy's fit.jac)
+        if self.robust:
+            fd, fp = self.residual(x)                            # the reference reports the TRUE residuals (fit.f = f(x))
+            self.cost = self._cost(fd, fp)
         self.f = fd if self.noprior_rows else torch.cat([fd, fp])
         self.chi2 = float(fd @ fd + fp @ fp)
         from .fit import gammaQ, _logGBF
@@ -722,10 +792,12 @@ class DenseFit(object):
         A2 = la.mm(Q1, Q1, transA=True)
         del Q1
         if self.Wp is None:
-            Xp = X * (self.d_wp * d)[None, :]                            # prior rows: diag(wp d) X^T
+            wp = self.d_wp if prow is None else self.d_wp * prow
+            Xp = X * (wp * d)[None, :]                                   # prior rows: diag(wp d) X^T
             la.mm(Xp, Xp, transB=True, out=A2, beta=1.0)
         else:
-            Q1p = la.mm(self.Wp * d[None, :], X, transB=True)            # prior rows of Q1
+            Wp = self.Wp if prow is None else self.Wp * prow[:, None]
+            Q1p = la.mm(Wp * d[None, :], X, transB=True)                 # prior rows of Q1
             la.mm(Q1p, Q1p, transA=True, out=A2, beta=1.0)
         if la.potrf(A2, 0.0, self.L, self.linv, self.info):
             eye = torch.eye(n, dtype=torch.float64, device=la.tdev)
@@ -737,6 +809,14 @@ class DenseFit(object):
         self.cov = self.d_cov.cpu().numpy()
         self.psdev = np.sqrt(np.diag(self.cov))
         self.logdet_JtJ = logdet - 2.0 * float(torch.sum(torch.log(d)))
+        if self.robust:
+            # fit.J of the reference's plugin is the TRUE Jacobian (Dfun(x), src/lsqfit/_scipy.py:166): restore it for
+            # fit.p's propagation and take log det(J^T J) from it (src/lsqfit/__init__.py:712-725)
+            self.jacobian(x, robust=False)
+            torch.mul(self.A, dd, out=self.As)
+            if la.potrf(self.As, 0.0, self.L, self.linv, self.info):
+                self.logdet_JtJ = (2.0 * float(torch.sum(torch.log(torch.diagonal(self.L))))
+                                   - 2.0 * float(torch.sum(torch.log(d))))
         self.logGBF = _logGBF(self.logdet_JtJ, self.logdet_pdf, self.chi2, self.dof)
 
     # ---- fit.p propagation (a-6; src/lsqfit/__init__.py:897-922) ------------------------------
@@ -798,9 +878,11 @@ class b200_dense(object):
     trust-region step selection of scipy's trf)."""
 
     def __init__(self, x0, n, f, tol=(1e-8, 1e-10, 1e-10), maxit=1000, scaler="more", device=0, polish=0, bounds=None,
-                 **extra_args):
+                 loss="linear", f_scale=1.0, method=None, **extra_args):
         if extra_args:
             raise ValueError("b200_dense: unknown fitter arguments: " + ", ".join(sorted(extra_args)))
+        if method not in (None, "trf"):
+            raise ValueError("b200_dense implements scipy's method='trf' only (got %r)" % (method,))
         spec = getattr(f, "b200", None)
         if spec is None:
             raise ValueError("the b200_dense fitter needs a device functor: use lsqfit_b200.Functor(...) as fcn "
@@ -813,8 +895,10 @@ class b200_dense(object):
         if bounds is not None:                                    # (lower, upper) in the caller's parameter order (scipy's argument)
             bounds = tuple(spec.to_device(np.broadcast_to(np.asarray(b, dtype=float), self.x0.shape)) for b in bounds)
             self.description += "    bounds"
+        if loss != "linear":
+            self.description += "    loss = {}".format(loss)
         fit = DenseFit(None, None, p0=spec.to_device(self.x0), tol=self.tol, maxit=maxit, scaler=scaler, polish=polish,
-                       device=device, spec=spec, bounds=bounds)
+                       device=device, spec=spec, bounds=bounds, loss=loss, f_scale=f_scale)
         if n != fit.nchiv:
             raise ValueError("b200_dense: n=%d does not match the whitening (%d residuals)" % (n, fit.nchiv))
         self.dense = fit

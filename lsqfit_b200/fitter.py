@@ -157,15 +157,22 @@ class b200_lm(object):
       ``scaler``  'more' (default) | 'levenberg' | 'marquardt' (gsl policy only)   (_gsl.pyx:621-653)
       ``bounds``  (lower, upper): scipy's bound constraints (``lsqfit.scipy_least_squares(bounds=...)``); such fits run on
                   the single-fit path (lsqfit_b200/dense.py) with scipy trf's reflective step selection.
+      ``loss``, ``f_scale``  scipy's robust loss functions ('linear' | 'huber' | 'soft_l1' | 'cauchy' | 'arctan';
+                  ``lsqfit.scipy_least_squares(loss=...)``, src/lsqfit/_scipy.py:77): also on the single-fit path.
+      ``method``  None | 'trf' (scipy's other methods are different solvers and are refused).
       ``device``  CUDA index;  ``polish``  max Gauss-Newton refinement steps after the trust-region loop (default 0 =
                   stop where the reference's solver stops).
     """
 
     def __init__(self, x0, n, f, tol=(1e-8, 1e-10, 1e-10), maxit=1000, scaler="more", device=0,
                  polish=0, policy="trf", alg="lm", solver="qr", factor_up=3.0, factor_down=2.0, avmax=0.75,
-                 bounds=None, **extra_args):
+                 bounds=None, loss="linear", f_scale=1.0, method=None, **extra_args):
         if extra_args:
             raise ValueError("b200_lm: unknown fitter arguments: " + ", ".join(sorted(extra_args)))
+        if method not in (None, "trf"):
+            # scipy's other methods ('dogbox', MINPACK 'lm': src/lsqfit/_scipy.py:56-71) are different solvers
+            raise ValueError("b200_lm implements scipy's method='trf' (policy='trf') and GSL's 'lm' (policy='gsl') only; "
+                             "got method=%r" % (method,))
         from .engine import POLICY, SCALER
         if policy not in POLICY:
             raise ValueError("b200_lm: unknown policy " + str(policy))
@@ -194,14 +201,17 @@ class b200_lm(object):
         from ._cabi import B200LMError, functor_table
         if spec.np < 0:
             spec.np = self.x0.size
-        if bounds is not None or not any(fam == spec.functor.family and m == spec.np for fam, m, _, _ in functor_table()):
-            # no batched kernel for this parameter count, or bound constraints (scipy's ``bounds``): one fit over the
-            # whole GPU instead (lsqfit_b200/dense.py)
+        robust = loss != "linear"
+        if bounds is not None or robust or not any(fam == spec.functor.family and m == spec.np
+                                                   for fam, m, _, _ in functor_table()):
+            # no batched kernel for this parameter count, bound constraints (scipy's ``bounds``) or a robust loss
+            # (scipy's ``loss`` / ``f_scale``): one fit over the whole GPU instead (lsqfit_b200/dense.py)
             if gsl:
-                raise ValueError("b200_lm: policy='gsl' needs a batched kernel without bounds (model %s, np=%d)"
+                raise ValueError("b200_lm: policy='gsl' needs a batched kernel without bounds / loss (model %s, np=%d)"
                                  % (spec.functor.name, spec.np))
             from .dense import b200_dense
-            d = b200_dense(x0, n, f, tol=tol, maxit=maxit, scaler=scaler, device=device, polish=polish, bounds=bounds)
+            d = b200_dense(x0, n, f, tol=tol, maxit=maxit, scaler=scaler, device=device, polish=polish, bounds=bounds,
+                           loss=loss, f_scale=f_scale)
             for k in ("x", "cov", "f", "J", "nit", "logdet_JtJ", "results", "stopping_criterion", "error", "dense"):
                 setattr(self, k, getattr(d, k))
             self.description = d.description

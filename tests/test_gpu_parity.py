@@ -9,7 +9,7 @@ sqrt(cov_ii cov_jj).
 import numpy as np
 import pytest
 
-from parity_util import TIGHT, exact_minimum, rel_cov as _rel_cov
+from parity_util import TIGHT, correlator_problem, exact_minimum, rel_cov, rel_cov as _rel_cov
 
 pytestmark = pytest.mark.gpu
 
@@ -1116,6 +1116,66 @@ def test_bounds(nist_problems):
         assert abs(fd.chi2 - fo.chi2) <= 1e-6 * fo.chi2, (name, fd.chi2, fo.chi2)
         free = np.arange(1, len(cert))
         assert np.max(np.abs(fd.pmean[free] - fo.pmean[free]) / fo.psdev[free]) < 1e-3, name
+
+
+def _ocost(fo):
+    """scipy's final (robust) cost of an oracle fit"""
+    r = fo.fitter_results
+    return float(getattr(r, "results", r).cost)
+
+
+def test_robust_loss(nist_problems):
+    """scipy's ``loss`` / ``f_scale`` (lsqfit.scipy_least_squares passes them to least_squares, reference
+    src/lsqfit/_scipy.py:77, 156-161) on the single-fit path, against scipy itself (the oracle passes the arguments
+    through): NIST problems with three gross outliers planted in the data.  Same robust minimum (parameters, robust
+    covariance = that of scipy's scaled ``fit.jac``, chi2 of the TRUE residuals), far from the plain least-squares
+    answer, for every loss function; ``b200_lm(loss=...)`` routes to the single-fit path; a correlated data block too."""
+    _need_gpu()
+    import copy
+    import lsqfit_b200 as lb
+    from oracle.fit import nonlinear_fit as ofit
+    for name in ("misra1a", "chwirut2", "gauss1", "thurber"):
+        pr = copy.deepcopy(next(q for q in nist_problems if q["name"] == name))
+        y, sd = np.array(pr["y"], dtype=float), np.array(pr["ysdev"], dtype=float) * np.ones(len(pr["y"]))
+        for k, i in enumerate((1, len(y) // 2, len(y) - 2)):
+            y[i] += (12.0 + 5.0 * k) * sd[i] * (-1) ** k
+        pr["y"] = y
+        plain = ofit(pr["form"], np.array(pr["x"]), y, pr["ysdev"], prior_mean=pr["prior_mean"], prior_cov=pr["prior_sdev"],
+                     p0=pr["p0"], tol=1e-10, x_scale="jac")
+        for loss, fs in (("soft_l1", 1.0), ("huber", 1.5), ("cauchy", 2.0), ("arctan", 3.0)):
+            fo = ofit(pr["form"], np.array(pr["x"]), y, pr["ysdev"], prior_mean=pr["prior_mean"], prior_cov=pr["prior_sdev"],
+                      p0=pr["p0"], tol=1e-10, x_scale="jac", loss=loss, f_scale=fs)
+            fd = _device_nist(pr, 1e-10, loss=loss, f_scale=fs)
+            tag = (name, loss)
+            assert fd.error is None and "loss = " + loss in fd.description, tag
+            assert fo.stopping_criterion > 0 and fd.stopping_criterion > 0, tag
+            # both stop within their own tolerance of the same robust minimum: the robust cost is stationary there
+            # (second order in the distance), the chi2 of the TRUE residuals is not (first order)
+            assert np.max(np.abs(fd.pmean - fo.pmean) / fo.psdev) < 1e-4, (tag, fd.pmean, fo.pmean)
+            assert abs(fd._dense.cost - _ocost(fo)) <= 1e-9 * _ocost(fo), (tag, fd._dense.cost)
+            assert abs(fd.chi2 - fo.chi2) <= 1e-5 * fo.chi2, (tag, fd.chi2, fo.chi2)
+            assert rel_cov(fd.cov, fo.cov) < 1e-4, tag
+            assert abs(fd.logGBF - fo.logGBF) < 1e-5 * max(1.0, abs(fo.logGBF)), (tag, fd.logGBF, fo.logGBF)
+            # ... which is NOT the least-squares answer the outliers drag away
+            if loss == "soft_l1":
+                assert np.max(np.abs(fo.pmean - plain.pmean) / plain.psdev) > 0.5, tag
+    # correlated data block + robust loss (dense weights, joint rows): the C3-like correlator with one outlier
+    prob, _ = correlator_problem(3)
+    prob = dict(prob, p0=prob["prior_mean"] * 1.05)
+    ymean = prob["f"] * (1.0 + 1e-4 * np.sin(np.arange(prob["ny"])))
+    ymean[7] += 25.0 * np.sqrt(prob["ycov"][7, 7])
+    fo = ofit("multiexp", prob["x"], ymean, prob["ycov"], prior_mean=prob["prior_mean"], prior_cov=prob["prior_sdev"],
+              p0=prob["p0"], tol=1e-10, x_scale="jac", loss="soft_l1", f_scale=2.0)
+    fd = lb.nonlinear_fit(data=(prob["x"], ymean, prob["ycov"]), fcn="multiexp", prior=(prob["prior_mean"], prob["prior_sdev"]),
+                          p0=prob["p0"], tol=1e-10, loss="soft_l1", f_scale=2.0)
+    assert np.max(np.abs(fd.pmean - fo.pmean) / fo.psdev) < 1e-3          # (measured 1.3e-4: both stop on ftol)
+    assert abs(fd._dense.cost - _ocost(fo)) <= 1e-9 * _ocost(fo)
+    assert abs(fd.chi2 - fo.chi2) <= 1e-5 * fo.chi2
+    assert rel_cov(fd.cov, fo.cov) < 1e-4
+    with pytest.raises(ValueError):
+        _device_nist(pr, 1e-10, loss="nonsense")
+    with pytest.raises(ValueError):
+        _device_nist(pr, 1e-10, method="dogbox")
 
 
 def test_eps_regulator_flags_indefinite_block():
