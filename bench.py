@@ -681,6 +681,11 @@ def run_ours(args, rank, local_rank, world):
                     flops_per_launch_survey_formula=nfev_all * F_eval / world,
                     nfev_per_fit=nfev_all / (B * world), njev_per_fit=njev_all / (B * world),
                     chol_per_fit=nfac_all / (B * world), max_nfev_of_a_fit=max_nit, kernel_ms=tk_ms / args.steps,
+                    queue_order=int(plan.last_order()),
+                    queue_order_note="1: the work queue hands out the fits with the largest start-point chi2 first "
+                                     "(b200lm_set_order default policy for this shape); kernel_ms then spans the "
+                                     "start-point pass (one evaluation per fit, NOT counted in the flops), the ranking "
+                                     "kernel and the fit kernel",
                     note="FP64 pipe (DMMA/DFMA share one pipe; tcgen05 has no FP64 kind).  The step is bounded by the "
                          "latency of its slowest fits, not by throughput: see extras.c3_saturated for the saturated batch")
 

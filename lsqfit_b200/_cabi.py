@@ -55,6 +55,8 @@ SIGNATURES = {
     "b200lm_last_stats_ex": (C.c_int, [handle_t, C.POINTER(C.c_ulonglong), C.c_int]),
     "b200lm_last_team": (C.c_int, [handle_t]),
     "b200lm_set_team": (C.c_int, [handle_t, C.c_int]),
+    "b200lm_set_order": (C.c_int, [handle_t, C.c_int]),
+    "b200lm_last_order": (C.c_int, [handle_t]),
     "b200lm_comm_unique_id": (C.c_int, [C.c_char_p]),
     "b200lm_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
     "b200lm_comm_destroy": (None, [C.c_void_p]),

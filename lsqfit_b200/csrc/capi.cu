@@ -76,6 +76,49 @@ static int default_team(b200lm_handle_s* h) {
     return 1;
 }
 
+// ---- queue order ------------------------------------------------------------------------------------------------
+// A batch whose fits need very different numbers of trial points (C3: median 19, 1 % above 117, longest 379) ends when
+// its slowest fit ends, and with the queue in input order that fit may START late.  Measured on the C3 batch of 10^4
+// copies (tools/order_probe.py, team of four warps): input order 12.34 ms, longest fit first with the evaluation counts
+// known in advance 9.39 ms (the best any order can do), ordered by chi2 at the start point -- the one thing known
+// before the fit, at the price of one evaluation per fit -- 11.58 ms.  The order is a permutation of the work queue
+// only: every fit is computed exactly as before.
+//   rank[b] = #{ j : key[j] > key[b]  or  key[j] == key[b] and j < b },  order[rank[b]] = b      (O(B^2), B <= 40000)
+static const int ORDER_MAX_B = 40000;
+__global__ void __launch_bounds__(256) queue_order_kernel(int B, const double* __restrict__ key, int* __restrict__ order) {
+    __shared__ double tile[1024];
+    const int b = blockIdx.x * 256 + threadIdx.x;
+    double kb = b < B ? key[b] : 0.0;
+    if (!(kb == kb) || kb > 1e300) kb = 1e300;                 // non-finite start: first (it ends at once)
+    int rank = 0;
+    for (int j0 = 0; j0 < B; j0 += 1024) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < 1024; t += 256) {
+            double k = j0 + t < B ? key[j0 + t] : 0.0;
+            if (!(k == k) || k > 1e300) k = 1e300;
+            tile[t] = k;
+        }
+        __syncthreads();
+        const int n = B - j0 < 1024 ? B - j0 : 1024;
+        for (int t = 0; t < n; ++t) {
+            const double k = tile[t];
+            rank += (k > kb || (k == kb && j0 + t < b)) ? 1 : 0;
+        }
+    }
+    if (b < B) order[rank] = b;
+}
+
+// default: on for the shapes whose trial points are expensive (the shapes that get the team kernel) when the batch is
+// several fits per resident warp but small enough to be bounded by its slowest fits
+static bool order_wanted(b200lm_handle_s* h, int B) {
+    if (const char* env = getenv("B200LM_ORDER")) return atoi(env) != 0 && B <= ORDER_MAX_B && B >= 2;
+    if (h->order_request == 0 || B > ORDER_MAX_B || B < 2) return false;
+    if (h->order_request == 1) return true;
+    int big = 0;
+    for (const auto& b : h->h_blk) big = b.n_in > big ? b.n_in : big;
+    return big >= 32 && h->np >= 12 && B >= 2048;
+}
+
 // shapes the wave kernel takes (lm_wave.cuh): one correlated block of <= 64 points, every other entry a 1x1 prior
 // row, np <= 16, the scipy policy
 static bool wave_ok(b200lm_handle_s* h) {
@@ -169,6 +212,7 @@ void b200lm_destroy(b200lm_handle h) {
     cudaFree(h->d_dfn_idx); cudaFree(h->d_dfn_w); cudaFree(h->d_dpr_idx); cudaFree(h->d_dpr_w);
     cudaFree(h->d_blk); cudaFree(h->d_blk_idx); cudaFree(h->d_blk_wt); cudaFree(h->d_blk_wt2); cudaFree(h->d_wfull);
     cudaFree(h->d_counter); cudaFree(h->d_stats); cudaFree(h->d_stage); cudaFree(h->d_scratch);
+    cudaFree(h->d_order_key); cudaFree(h->d_order);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -301,6 +345,27 @@ int b200lm_fit_batch(b200lm_handle h, int B,
     P.f_out = d_f; P.J_out = d_J;
     CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s), "reset work queue");
     CUDA_TRY(h, cudaMemsetAsync(h->d_stats, 0, 16 * sizeof(unsigned long long), s), "reset stats");
+    // queue order: chi2 at the start point of every fit (one evaluation each, resjac kernel without f / J outputs),
+    // ranked on the device
+    h->last_order = 0;
+    if (order_wanted(h, B)) {
+        if (B > h->order_cap) {
+            if (h->d_order_key) cudaFree(h->d_order_key);
+            if (h->d_order) cudaFree(h->d_order);
+            h->d_order_key = nullptr; h->d_order = nullptr; h->order_cap = 0;
+            CUDA_TRY(h, cudaMalloc((void**)&h->d_order_key, (size_t)B * sizeof(double)), "queue order buffers");
+            CUDA_TRY(h, cudaMalloc((void**)&h->d_order, (size_t)B * sizeof(int)), "queue order buffers");
+            h->order_cap = B;
+        }
+        FitParams R = P;
+        R.f_out = nullptr; R.J_out = nullptr; R.chi2 = h->d_order_key; R.x_out = nullptr; R.cov = nullptr;
+        CUDA_TRY(h, h->fe->resjac(R, h->sm_count, h->smem_budget, s), "start-point chi2 launch");
+        queue_order_kernel<<<(B + 255) / 256, 256, 0, s>>>(B, h->d_order_key, h->d_order);
+        CUDA_TRY(h, cudaGetLastError(), "queue order launch");
+        P.order = h->d_order;
+        h->last_order = 1;
+        h->launches += 2;
+    }
     // kernel choice: one warp per fit, or a team of 2 / 4 warps per fit where the functor has one
     // (B200LM_TEAM = 0/1, 2, 4 overrides the default policy)
     int team = default_team(h);
@@ -314,7 +379,7 @@ int b200lm_fit_batch(b200lm_handle h, int B,
         CUDA_TRY(h, h->fe->fit_wave(P, h->sm_count, h->smem_budget, s), "wave kernel launch");
         CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s), "reset work queue");
         FitParams Q = P;
-        Q.finalize_only = 1; Q.p0 = d_x; Q.p0_stride = h->np; Q.team = 1;
+        Q.finalize_only = 1; Q.p0 = d_x; Q.p0_stride = h->np; Q.team = 1; Q.order = nullptr;
         CUDA_TRY(h, h->fe->fit(Q, h->sm_count, h->smem_budget, s), "finalize kernel launch");
         h->launches += 1;
     } else if (ti >= 0 && h->fe->fit_team[ti] &&
@@ -359,6 +424,15 @@ int b200lm_set_team(b200lm_handle h, int team) {
     h->team_request = team;
     return B200LM_OK;
 }
+
+int b200lm_set_order(b200lm_handle h, int mode) {
+    if (!h) return set_error(h, B200LM_EINVAL, "NULL handle");
+    if (mode < -1 || mode > 1) return set_error(h, B200LM_EINVAL, "order must be -1 (default), 0 (input order) or 1 (by start-point chi2)");
+    h->order_request = mode;
+    return B200LM_OK;
+}
+
+int b200lm_last_order(b200lm_handle h) { return h ? h->last_order : B200LM_EINVAL; }
 
 int b200lm_set_policy(b200lm_handle h, int policy) {
     if (!h) return set_error(h, B200LM_EINVAL, "NULL handle");

@@ -33,6 +33,10 @@ struct b200lm_handle_s {
     int team_request = 0;       // 0: default policy; 1, 2, 4: warps per fit asked for by b200lm_set_team
     int policy = 0;             // trust-region decisions: 0 scipy TRF, 1 GSL trust/lm (b200lm_set_policy)
     int last_team = 1;          // warps per fit of the last fit_batch launch
+    // queue order (longest-expected fits first): key = chi2 at the start point, one evaluation per fit
+    int order_request = -1;     // -1: default policy (by problem shape and batch size); 0: off; 1: on  (b200lm_set_order)
+    int last_order = 0;         // 1 if the last fit_batch launch used an ordered queue
+    double* d_order_key = nullptr; int* d_order = nullptr; int order_cap = 0;
     // staging for the host-pointer API
     void* d_stage = nullptr; size_t stage_bytes = 0;
     void* h_pinned = nullptr; size_t pinned_bytes = 0;

@@ -1361,7 +1361,10 @@ __global__ void __launch_bounds__(FitLayout<F>::MAX_WARPS * 32, 1) fit_kernel(co
 
     for (;;) {
         int b = 0;
-        if (lane == 0) b = atomicAdd(P.counter, 1);
+        if (lane == 0) {
+            b = atomicAdd(P.counter, 1);
+            if (P.order && b < P.B) b = P.order[b];
+        }
         b = __shfl_sync(B200LM_FULL, b, 0);
         if (b >= P.B) break;
         fit_one<F, WarpEval<F>, MODE>(c, ev, P, b, tot_nfev, tot_njev, tot_nfac, pk);

@@ -695,7 +695,10 @@ fit_team_kernel(const __grid_constant__ FitParams P) {
         ev.tc = &tc;
         for (;;) {
             int b = 0;
-            if (lane == 0) b = atomicAdd(P.counter, 1);
+            if (lane == 0) {
+                b = atomicAdd(P.counter, 1);
+                if (P.order && b < P.B) b = P.order[b];
+            }
             b = __shfl_sync(B200LM_FULL, b, 0);
             if (b >= P.B) break;
             fit_one<F>(c, ev, P, b, tot_nfev, tot_njev, tot_nfac, pk);

@@ -70,6 +70,7 @@ struct FitParams {
     double* f_out;              // [B][nchiv]
     double* J_out;              // [B][nchiv][np]
     int* counter;               // work-queue head (zeroed before launch)
+    const int* order;           // optional: the queue hands out fit order[i] instead of fit i (longest-expected first)
     unsigned long long* stats;  // [0] total nfev, [1] total jacobian evals, [2] total factorisations
 };
 

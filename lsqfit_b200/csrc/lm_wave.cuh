@@ -725,7 +725,10 @@ __global__ void __launch_bounds__(WaveLayout<F, S_, CF_>::THREADS, MINB) fit_wav
         }
         if (st == 0 && !queue_empty) {
             int b = 0;
-            if (lead) b = atomicAdd(P.counter, 1);
+            if (lead) {
+                b = atomicAdd(P.counter, 1);
+                if (P.order && b < P.B) b = P.order[b];
+            }
             b = __shfl_sync(gm, b, lane & ~7);
             if (b < P.B) {
                 fit = b; st = 1; cur = 0;

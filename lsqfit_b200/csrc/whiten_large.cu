@@ -27,6 +27,74 @@
 #include "jacobi_core.cuh"
 #include "dgemm.cuh"
 #include "dense_linalg.h"
+#include <mutex>
+
+// ---- workspace cache ------------------------------------------------------------------------------------------------
+// One whitening of a 5000 x 5000 block allocates ~1.5 GB in two dozen buffers.  cudaMalloc / cudaFree of buffers that
+// size map and unmap device memory: measured on the config-5 block, the SAME 13 sweeps took 325 ... 614 ms per call
+// depending on what the driver had to do (tools/c5_whiten_repeat.py).  Freed buffers are therefore kept per device and
+// handed out again (first block of at least the requested size and at most twice that); at most B200LM_WL_CACHE_MB
+// (default 8192, 0 = no cache) stay cached.  As cudaFree did, a release waits for the device first, so a block is never
+// handed out while an earlier call's kernels may still touch it.
+namespace {
+struct WlBlock { void* p; size_t bytes; int dev; };
+std::mutex g_wl_mu;
+std::vector<WlBlock> g_wl_free, g_wl_live;
+size_t g_wl_cached = 0;
+size_t wl_cache_limit() {
+    static const size_t lim = [] { const char* e = getenv("B200LM_WL_CACHE_MB"); return (size_t)(e ? atoll(e) : 8192) << 20; }();
+    return lim;
+}
+cudaError_t wl_malloc(void** out, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (bytes == 0) bytes = 8;
+    {
+        std::lock_guard<std::mutex> lk(g_wl_mu);
+        for (size_t i = 0; i < g_wl_free.size(); ++i) {
+            const WlBlock b = g_wl_free[i];
+            if (b.dev == dev && b.bytes >= bytes && b.bytes <= 2 * bytes + 4096) {
+                g_wl_free.erase(g_wl_free.begin() + i);
+                g_wl_cached -= b.bytes;
+                g_wl_live.push_back(b);
+                *out = b.p;
+                return cudaSuccess;
+            }
+        }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {
+        // out of memory: give the cached blocks back and try once more
+        std::vector<WlBlock> drop;
+        { std::lock_guard<std::mutex> lk(g_wl_mu); drop.swap(g_wl_free); g_wl_cached = 0; }
+        for (const auto& b : drop) cudaFree(b.p);
+        cudaGetLastError();
+        e = cudaMalloc(out, bytes);
+        if (e != cudaSuccess) return e;
+    }
+    std::lock_guard<std::mutex> lk(g_wl_mu);
+    g_wl_live.push_back(WlBlock{*out, bytes, dev});
+    return cudaSuccess;
+}
+cudaError_t wl_free(void* p) {
+    if (!p) return cudaSuccess;
+    cudaDeviceSynchronize();
+    WlBlock b{p, 0, 0};
+    {
+        std::lock_guard<std::mutex> lk(g_wl_mu);
+        for (size_t i = 0; i < g_wl_live.size(); ++i)
+            if (g_wl_live[i].p == p) { b = g_wl_live[i]; g_wl_live.erase(g_wl_live.begin() + i); break; }
+        if (b.bytes && g_wl_cached + b.bytes <= wl_cache_limit()) {
+            g_wl_free.push_back(b);
+            g_wl_cached += b.bytes;
+            return cudaSuccess;
+        }
+    }
+    return cudaFree(p);
+}
+}  // namespace
+#define cudaMalloc(pp, n) wl_malloc((void**)(pp), (n))
+#define cudaFree(p) wl_free((void*)(p))
 
 namespace b200lm {
 

@@ -218,6 +218,14 @@ class Plan(object):
         _cabi.check(_cabi.lib.b200lm_last_stats_ex(self._h, buf, int(n)), self._h)
         return [int(v) for v in buf[:n]]
 
+    def set_order(self, mode):
+        """Order of the work queue: None / -1 = default policy, 0 = input order, 1 = largest start-point chi2 first
+        (b200lm_set_order: scheduling only, results unchanged)."""
+        _cabi.check(_cabi.lib.b200lm_set_order(self._h, -1 if mode is None else int(mode)), self._h)
+
+    def last_order(self):
+        return int(_cabi.lib.b200lm_last_order(self._h))
+
     def set_team(self, team):
         """Kernel choice: 0/None = default policy (by problem shape), 1 = one warp per fit (saturated batches),
         2 / 4 = team kernel (lowest latency per trial point)."""

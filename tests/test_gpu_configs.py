@@ -236,3 +236,40 @@ def test_c5_full_size_vs_oracle():
     assert abs(fit.chi2 - g["chi2"]) <= 1e-9 * g["chi2"]
     assert np.max(np.abs(fit.psdev / g["psdev"] - 1)) <= 1e-8
     assert abs(fit.logGBF - g["logGBF"]) <= 1e-9 * abs(g["logGBF"])
+
+
+@pytest.mark.parametrize("team", [1, 4, 32], ids=["one-warp", "team-4", "wave"])
+def test_ordered_queue_changes_nothing_but_the_schedule(team):
+    """b200lm_set_order: the work queue hands out the fits with the largest start-point chi2 first (a batch is bounded by
+    its slowest fits).  Scheduling only -- every fit must come out BIT-identical to the input-order run, for every
+    kernel; the default policy turns it on for this shape (np = 16, 64-point block) from 2048 fits on."""
+    _need_gpu()
+    import torch
+    import lsqfit_b200 as lb
+    cfg, opdf = correlator_problem(8)
+    pdf = lb.PDF(opdf.mean, opdf.cov_in, svdcut=1e-12)
+    B = 2500
+    means = _copies(cfg, pdf, B, 4242, True)
+    means[7, :] = np.nan                                  # a poisoned copy must not disturb the ranking of the others
+    plan = lb.Plan("multiexp", cfg["np"], cfg["ny"], cfg["x"], pdf.i_invwgts)
+    plan.set_team(team)
+    md = torch.as_tensor(means).cuda()
+    p0 = torch.as_tensor(cfg["prior_mean"]).cuda()
+    res = {}
+    for mode in (0, 1, None):
+        plan.set_order(mode)
+        o = plan.fit_batch(md, p0, tol=BENCH_TOL, maxit=1000)
+        torch.cuda.synchronize()
+        assert plan.last_order() == (0 if mode == 0 else 1), mode            # None: default policy -> on for this shape
+        res[mode] = o
+    for mode in (1, None):
+        a, b = res[0], res[mode]
+        ok = torch.arange(B, device=md.device) != 7
+        assert torch.equal(a.status, b.status) and torch.equal(a.nit, b.nit)
+        assert int(a.status[7]) == -1
+        assert torch.equal(a.x[ok], b.x[ok]) and torch.equal(a.chi2[ok], b.chi2[ok]) and torch.equal(a.cov[ok], b.cov[ok])
+    # a small batch stays in input order under the default policy
+    plan.set_order(None)
+    plan.fit_batch(md[:100], p0, tol=BENCH_TOL, maxit=1000)
+    assert plan.last_order() == 0
+    plan.close()
