@@ -703,7 +703,10 @@ def run_ours(args, rank, local_rank, world):
                 clocks=clocks,
                 e2e=dict(value=world * B * args.steps / te, unit=UNIT, h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=d2h, ms_per_step=1e3 * te / args.steps,
-                         api="lsqfit_b200.Plan.fit_batch_host -> b200lm_fit_batch_host (pinned host buffers)"),
+                         api="lsqfit_b200.Plan.fit_batch_host -> b200lm_fit_batch_host (pinned host buffers)",
+                         d2h_route="covariances: stored by the kernels straight into the pinned host buffer over PCIe "
+                                   "(B200LM_NO_ZEROCOPY=1: device copy + D2H transfer); x, chi2, log det, nit, status: "
+                                   "D2H copies after the launch"),
                 gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, queued=queued, comm=comm, extras=extras)
     emit(json.dumps(line))
     if world > 1:

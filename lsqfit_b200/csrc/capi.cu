@@ -552,16 +552,29 @@ int b200lm_fit_batch_host(b200lm_handle h, int B,
     CUDA_TRY(h, cudaMemcpyAsync(d + o_p0, h_p0, n_p0 * sizeof(double), cudaMemcpyHostToDevice, s), "H2D p0");
     int* d_nit = (int*)(d + o_int);
     int* d_status = d_nit + B;
+    // The large write-only outputs (cov, f, J) go STRAIGHT to the caller's buffer when that is pinned, mapped host
+    // memory: the kernels' stores travel over PCIe while other fits are still running, instead of a device copy
+    // followed by a D2H transfer after the last fit (C3, 10^4 fits: 20 MB of covariances).  x, chi2, nit and status
+    // stay on the device (the finalisation pass of the wave kernel reads x back) and are copied as before.
+    auto alias = [](void* hp) -> double* {
+        if (!hp || getenv("B200LM_NO_ZEROCOPY")) return nullptr;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, hp) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return (at.type == cudaMemoryTypeHost && at.devicePointer) ? (double*)at.devicePointer : nullptr;
+    };
+    double* z_cov = alias(h_cov);
+    double* z_f = alias(h_f);
+    double* z_J = alias(h_J);
     rc = b200lm_fit_batch(h, B, d + o_mean, mean_stride, d + o_p0, p0_stride, xtol, gtol, ftol, maxit, scaler, polish,
-                          d + o_x, d + o_chi2, h_cov ? d + o_cov : nullptr, d + o_ld, d_nit, d_status,
-                          h_f ? d + o_f : nullptr, h_J ? d + o_J : nullptr, (void*)s);
+                          d + o_x, d + o_chi2, h_cov ? (z_cov ? z_cov : d + o_cov) : nullptr, d + o_ld, d_nit, d_status,
+                          h_f ? (z_f ? z_f : d + o_f) : nullptr, h_J ? (z_J ? z_J : d + o_J) : nullptr, (void*)s);
     if (rc) return rc;
     CUDA_TRY(h, cudaMemcpyAsync(h_x, d + o_x, B * np * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H x");
     CUDA_TRY(h, cudaMemcpyAsync(h_chi2, d + o_chi2, B * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H chi2");
     if (h_logdet) CUDA_TRY(h, cudaMemcpyAsync(h_logdet, d + o_ld, B * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H logdet");
-    if (h_cov) CUDA_TRY(h, cudaMemcpyAsync(h_cov, d + o_cov, B * np * np * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H cov");
-    if (h_f) CUDA_TRY(h, cudaMemcpyAsync(h_f, d + o_f, B * nchiv * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H f");
-    if (h_J) CUDA_TRY(h, cudaMemcpyAsync(h_J, d + o_J, B * nchiv * np * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H J");
+    if (h_cov && !z_cov) CUDA_TRY(h, cudaMemcpyAsync(h_cov, d + o_cov, B * np * np * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H cov");
+    if (h_f && !z_f) CUDA_TRY(h, cudaMemcpyAsync(h_f, d + o_f, B * nchiv * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H f");
+    if (h_J && !z_J) CUDA_TRY(h, cudaMemcpyAsync(h_J, d + o_J, B * nchiv * np * sizeof(double), cudaMemcpyDeviceToHost, s), "D2H J");
     CUDA_TRY(h, cudaMemcpyAsync(h_nit, d_nit, B * sizeof(int), cudaMemcpyDeviceToHost, s), "D2H nit");
     CUDA_TRY(h, cudaMemcpyAsync(h_status, d_status, B * sizeof(int), cudaMemcpyDeviceToHost, s), "D2H status");
     CUDA_TRY(h, cudaStreamSynchronize(s), "stream sync");

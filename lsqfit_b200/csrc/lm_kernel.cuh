@@ -914,7 +914,10 @@ __device__ double covariance_from_chol(WarpCtx<F>& c, double* cov_out) {
             double s = 0.0;
             const int k0 = a > b ? a : b;
             for (int k = k0; k < NP; ++k) s = fma(c.A[k * LDA + a] * c.idg[k], c.A[k * LDA + b], s);
-            cov_out[a * NP + b] = s * c.dsc[a] * c.dsc[b];
+            // element (a, b) goes to its mirror position (b, a): for a fixed b the lanes write one contiguous row
+            // (the matrix is symmetric; stride-NP stores would be 16 partial sectors per instruction -- and the output
+            // may be pinned HOST memory written over PCIe, b200lm_fit_batch_host)
+            cov_out[b * NP + a] = s * c.dsc[a] * c.dsc[b];
         }
     }
     __syncwarp();
@@ -946,7 +949,7 @@ __device__ double covariance_from_qr(WarpCtx<F>& c, double* cov_out) {
             double s = 0.0;
             const int k0 = a > b ? a : b;
             for (int k = k0; k < NP; ++k) s = fma(c.L[a * LDA + k], c.L[b * LDA + k], s);
-            cov_out[a * NP + b] = s * c.dsc[a] * c.dsc[b];
+            cov_out[b * NP + a] = s * c.dsc[a] * c.dsc[b];               // (mirror position: contiguous rows, as above)
         }
     }
     __syncwarp();

@@ -273,3 +273,44 @@ def test_ordered_queue_changes_nothing_but_the_schedule(team):
     plan.fit_batch(md[:100], p0, tol=BENCH_TOL, maxit=1000)
     assert plan.last_order() == 0
     plan.close()
+
+
+def test_host_call_writes_pinned_outputs_in_place():
+    """b200lm_fit_batch_host: covariances (and f / J) go straight to the caller's buffer when it is pinned, mapped host
+    memory (the kernels store over PCIe while other fits still run) and through a device copy + D2H transfer otherwise.
+    Both routes must deliver the same bits; B200LM_NO_ZEROCOPY=1 switches the direct route off."""
+    _need_gpu()
+    import os
+    import torch
+    import lsqfit_b200 as lb
+    cfg, opdf = correlator_problem(3)
+    pdf = lb.PDF(opdf.mean, opdf.cov_in, svdcut=1e-12)
+    B = 300
+    means = _copies(cfg, pdf, B, 99, False)
+    plan = lb.Plan("multiexp", cfg["np"], cfg["ny"], cfg["x"], pdf.i_invwgts)
+    npar, nchiv = cfg["np"], plan.nchiv
+
+    def buffers(pinned):
+        mk = (lambda *sh, dt=torch.float64: torch.zeros(sh, dtype=dt).pin_memory().numpy()) if pinned else \
+             (lambda *sh, dt=torch.float64: torch.zeros(sh, dtype=dt).numpy())
+        return dict(x=mk(B, npar), chi2=mk(B), cov=mk(B, npar, npar), logdet=mk(B), nit=mk(B, dt=torch.int32),
+                    status=mk(B, dt=torch.int32), f=mk(B, nchiv), J=mk(B, nchiv, npar))
+    runs = {}
+    for name, pinned, env in (("pageable", False, None), ("pinned", True, None), ("pinned-staged", True, "1")):
+        if env:
+            os.environ["B200LM_NO_ZEROCOPY"] = env
+        else:
+            os.environ.pop("B200LM_NO_ZEROCOPY", None)
+        out = buffers(pinned)
+        plan.fit_batch_host(means, cfg["ptrue"], tol=BENCH_TOL, maxit=1000, out=out, want_fJ=True)
+        runs[name] = out
+    os.environ.pop("B200LM_NO_ZEROCOPY", None)
+    ref = runs["pageable"]
+    assert np.all(ref["status"] > 0) and np.all(np.isfinite(ref["cov"]))
+    for name in ("pinned", "pinned-staged"):
+        for k in ("x", "chi2", "cov", "logdet", "nit", "status", "f", "J"):
+            assert np.array_equal(ref[k], runs[name][k]), (name, k)
+    # the covariance is symmetric to rounding (its elements are stored at their mirror positions, row by row)
+    c = ref["cov"]
+    assert np.max(np.abs(c - c.transpose(0, 2, 1)) / np.sqrt(np.einsum("bii,bjj->bij", c, c))) < 1e-12
+    plan.close()
