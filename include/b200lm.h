@@ -123,16 +123,18 @@ int b200lm_last_stats(b200lm_handle h, unsigned long long out[3]);
 int b200lm_last_stats_ex(b200lm_handle h, unsigned long long* out, int n);
 /* warps per fit used by the last fit_batch launch: 1 (one warp per fit), 2 or 4 (team kernel) */
 int b200lm_last_team(b200lm_handle h);
-/* choose the kernel: 0 = default policy (by problem shape only: four warps per fit where one trial point is
- * expensive -- np >= 12 and a correlated block of >= 32 points -- else one), 1 = one warp per fit (highest
- * throughput on saturated batches), 2 / 4 = team kernel (lowest latency per trial point).  The two kernels
- * sum in a different order: results agree to rounding, not bit for bit. */
+/* choose the kernel: 0 = default policy (by problem shape only, never by batch size -- a fit's bits must not depend on
+ * the batch it is in: two warps per fit where one trial point is expensive -- np >= 12 and a correlated block of >= 32
+ * points -- else one), 1 = one warp per fit, 2 / 4 = team kernel (4: lowest latency per trial point, best for batches
+ * of a few hundred fits), 32 = wave kernel (highest throughput on saturated batches).  The kernels sum in a different
+ * order: results agree to rounding, not bit for bit. */
 int b200lm_set_team(b200lm_handle h, int team);
-/* order of the work queue: -1 = default policy (on for the shapes that get the team kernel when 2048 <= B <= 40000),
- * 0 = input order, 1 = fits with the largest chi2 at their start point first (one extra evaluation per fit + a device
- * ranking pass).  A batch is bounded by its slowest fits; handing out the fits expected to run longest first shortens
- * it (C3, 10^4 copies: 12.3 -> 11.6 ms).  Scheduling only: every fit is computed exactly as in input order (the
- * reference's iterators, src/lsqfit/__init__.py:1548-1642, run the copies one after the other in input order).
+/* order of the work queue: -1 / 0 = input order (default), 1 = fits with the largest chi2 at their start point first
+ * (one extra evaluation per fit + a device ranking pass; B <= 40000).  A batch is bounded by its slowest fits, and handing
+ * out the fits expected to run longest first CAN shorten it (one C3 batch of 10^4 copies: 12.3 -> 11.6 ms) -- but the
+ * start-point chi2 predicts the evaluation count only weakly, and over eight different batches the mean gain is zero
+ * (tools/order_seeds.py), so it is off unless asked for.  Scheduling only: every fit is computed exactly as in input
+ * order (the reference's iterators, src/lsqfit/__init__.py:1548-1642, run the copies one after the other).
  * b200lm_last_order: 1 if the last fit_batch used an ordered queue. */
 int b200lm_set_order(b200lm_handle h, int mode);
 int b200lm_last_order(b200lm_handle h);

@@ -62,17 +62,22 @@ static std::vector<FunctorEntry>& registry() {
 }
 
 // default number of warps per fit.  The choice depends on the problem's shape only, never on the batch
-// size: a fit's result must not depend on how many other fits share its launch (the two kernels sum in a
-// different order).  Measured on C3 (np = 16, one 64 x 64 block; tools/team_check.py, profiles/team_r02.json):
-// a team of four warps halves the latency of one trial point, which decides every batch that is bounded by
-// its slowest fits (B = 1000: 4.7 ms instead of 8.2 ms; B = 10^4: 12.4 vs 12.9 ms); a saturated batch is
-// bounded by the number of fits in flight per SM, where one warp per fit wins (B = 160 k: 117 vs 157 ms).
-// For small np (C4: np = 6) the evaluation is too short to split.  b200lm_set_team overrides.
+// size: a fit's result must not depend on how many other fits share its launch (the kernels sum in a different
+// order), so that a bootstrap copy gives the same bits in a batch of 500, of 10^4, or in the shard of a multi-GPU job.
+// Measured on C3 (np = 16, one 64 x 64 block), ms per batch for one warp / team of 2 / team of 4 / wave kernel
+// (tools/team_order_sweep.py, and the mean over eight different batches of tools/order_seeds.py at B = 10^4):
+//     B = 1000:  8.0 /  5.6 /  5.1 / 11.7        B = 10^4:   13.2 / 11.7 / 12.7 /  -
+//     B = 2048:  8.4 /  6.2 /  5.5 / 11.7        B = 4 10^4: 37.0 / 36.8 / 42.8 / 34.7
+//     B = 5000: 10.0 /  8.3 /  8.6 / 12.3        B = 1.6 10^5: 125 /  -  / 160  / 87
+// Four warps give the shortest trial point (batches of a few fits per team), one warp the most fits in flight
+// (saturated batches); TWO warps per fit are within 10 % of the best warp-per-fit choice everywhere and the best from
+// ~5000 fits up to saturation, which is where the reference's bootstrap sizes sit (10^3 ... 10^4 copies) -- the default.
+// For small np (C4: np = 6) the evaluation is too short to split.  b200lm_set_team overrides (32 = wave kernel).
 static int default_team(b200lm_handle_s* h) {
     if (h->team_request > 0) return h->team_request;
     int big = 0;
     for (const auto& b : h->h_blk) big = b.n_in > big ? b.n_in : big;
-    if (big >= 32 && h->np >= 12) return 4;
+    if (big >= 32 && h->np >= 12) return h->fe->fit_team[0] ? 2 : 4;
     return 1;
 }
 
@@ -81,8 +86,8 @@ static int default_team(b200lm_handle_s* h) {
 // its slowest fit ends, and with the queue in input order that fit may START late.  Measured on the C3 batch of 10^4
 // copies (tools/order_probe.py, team of four warps): input order 12.34 ms, longest fit first with the evaluation counts
 // known in advance 9.39 ms (the best any order can do), ordered by chi2 at the start point -- the one thing known
-// before the fit, at the price of one evaluation per fit -- 11.58 ms.  The order is a permutation of the work queue
-// only: every fit is computed exactly as before.
+// before the fit, at the price of one evaluation per fit -- 11.58 ms ON THAT BATCH (see order_wanted below for the
+// average over batches).  The order is a permutation of the work queue only: every fit is computed exactly as before.
 //   rank[b] = #{ j : key[j] > key[b]  or  key[j] == key[b] and j < b },  order[rank[b]] = b      (O(B^2), B <= 40000)
 static const int ORDER_MAX_B = 40000;
 __global__ void __launch_bounds__(256) queue_order_kernel(int B, const double* __restrict__ key, int* __restrict__ order) {
@@ -108,15 +113,15 @@ __global__ void __launch_bounds__(256) queue_order_kernel(int B, const double* _
     if (b < B) order[rank] = b;
 }
 
-// default: on for the shapes whose trial points are expensive (the shapes that get the team kernel) when the batch is
-// several fits per resident warp but small enough to be bounded by its slowest fits
+// OFF by default: over eight different C3 batches of 10^4 copies (tools/order_seeds.py) the ordered queue changes the
+// mean batch time by +0.6 % (team of four), +2.3 % (team of two), +2.3 % (one warp) -- single batches move by -10 % ...
+// +11 % depending on where their long fits happen to sit in the input order, and the start-point chi2 is too weak a
+// predictor (rank correlation 0.18 with the evaluation count) to pay for its own pass on average.  On request:
+// b200lm_set_order(h, 1) or B200LM_ORDER=1.
 static bool order_wanted(b200lm_handle_s* h, int B) {
-    if (const char* env = getenv("B200LM_ORDER")) return atoi(env) != 0 && B <= ORDER_MAX_B && B >= 2;
-    if (h->order_request == 0 || B > ORDER_MAX_B || B < 2) return false;
-    if (h->order_request == 1) return true;
-    int big = 0;
-    for (const auto& b : h->h_blk) big = b.n_in > big ? b.n_in : big;
-    return big >= 32 && h->np >= 12 && B >= 2048;
+    if (B > ORDER_MAX_B || B < 2) return false;
+    if (const char* env = getenv("B200LM_ORDER")) return atoi(env) != 0;
+    return h->order_request == 1;
 }
 
 // shapes the wave kernel takes (lm_wave.cuh): one correlated block of <= 64 points, every other entry a 1x1 prior

@@ -242,7 +242,7 @@ def test_c5_full_size_vs_oracle():
 def test_ordered_queue_changes_nothing_but_the_schedule(team):
     """b200lm_set_order: the work queue hands out the fits with the largest start-point chi2 first (a batch is bounded by
     its slowest fits).  Scheduling only -- every fit must come out BIT-identical to the input-order run, for every
-    kernel; the default policy turns it on for this shape (np = 16, 64-point block) from 2048 fits on."""
+    kernel.  Off by default (over several batches the mean gain is zero, tools/order_seeds.py)."""
     _need_gpu()
     import torch
     import lsqfit_b200 as lb
@@ -260,18 +260,14 @@ def test_ordered_queue_changes_nothing_but_the_schedule(team):
         plan.set_order(mode)
         o = plan.fit_batch(md, p0, tol=BENCH_TOL, maxit=1000)
         torch.cuda.synchronize()
-        assert plan.last_order() == (0 if mode == 0 else 1), mode            # None: default policy -> on for this shape
+        assert plan.last_order() == (1 if mode == 1 else 0), mode            # None: default policy = input order
         res[mode] = o
     for mode in (1, None):
-        a, b = res[0], res[mode]
+        a, b = res[0], res[mode]                              # (None: the default policy, i.e. the same run again)
         ok = torch.arange(B, device=md.device) != 7
         assert torch.equal(a.status, b.status) and torch.equal(a.nit, b.nit)
         assert int(a.status[7]) == -1
         assert torch.equal(a.x[ok], b.x[ok]) and torch.equal(a.chi2[ok], b.chi2[ok]) and torch.equal(a.cov[ok], b.cov[ok])
-    # a small batch stays in input order under the default policy
-    plan.set_order(None)
-    plan.fit_batch(md[:100], p0, tol=BENCH_TOL, maxit=1000)
-    assert plan.last_order() == 0
     plan.close()
 
 
