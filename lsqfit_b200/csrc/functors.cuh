@@ -66,6 +66,31 @@ struct ADFunctor {
 };
 
 // ---------------------------------------------------------------------------
+// examples/uncorrelated.py:30-31:  b0 + b1 exp(-b2 x), hand-written gradient (1, e, -b1 x e).  The one-pass
+// normal-equation kernel of the single-fit path (lm_rows.cuh) runs this model over millions of rows at the machine's
+// ridge point: the dual-number form costs ~50 FP64 instructions per row (products with derivative slots that are
+// identically 0 or 1 cannot be folded under IEEE rules), this one ~28.
+// ---------------------------------------------------------------------------
+struct OffsetExpModel {
+    static constexpr int NP = 3;
+    static constexpr int NX = 1;
+    __device__ __forceinline__ static double value(const double* __restrict__ x, int, const double* p) {
+        return p[0] + p[1] * ::exp(-(p[2] * x[0]));
+    }
+    template <class G>
+    __device__ __forceinline__ static double value_grad(const double* __restrict__ x, int,
+                                                        const double* p, double w, G g) {
+        const double t = x[0];
+        const double e = ::exp(-(p[2] * t));
+        const double we = w * e;
+        g[0] = w;
+        g[1] = we;
+        g[2] = -(p[1] * t) * we;
+        return p[0] + p[1] * e;
+    }
+};
+
+// ---------------------------------------------------------------------------
 // Multi-exponential correlator: sum_k a_k exp(-E_k t); params [a_0..a_K-1, E_0..E_K-1]
 // Hand-written gradient: d/da_k = e_k, d/dE_k = -a_k t e_k.
 // ---------------------------------------------------------------------------

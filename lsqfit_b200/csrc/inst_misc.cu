@@ -3,7 +3,7 @@
 #include "registry.h"
 namespace b200lm {
 typedef ADFunctor<SimpleBody, 2, 2> Simple;
-typedef ADFunctor<OffsetExpBody, 3> OffsetExp;
+typedef OffsetExpModel OffsetExp;
 static const FunctorEntry kEntries[] = {
     B200LM_ENTRY(F_SIMPLE, "simple", Simple),
     B200LM_ENTRY(F_OFFSET_EXP, "offset_exp", OffsetExp),

@@ -49,8 +49,10 @@ template <int NP> struct NormalAccLayout {
 // (the three knobs are compile-time so that tools/micro/nd_bench.cu can sweep them; defaults = the measured best.
 // 2e6 rows x 3 parameters from HBM, us per launch: unroll 1 / 256 threads / 4 CTAs per SM 25.1; 4/256/4 26.8; 8/256/4 24.8;
 // 4/256/8 32.9; 4/128/8 29.0; 4/512/2 21.8 -- fewer, larger CTAs win: the per-CTA reduction of the accumulators is a
-// third of the launch.  With ~50 FP64 instructions per 24-byte row the kernel sits AT the machine's ridge
-// (37 TFLOP/s : 6.5 TB/s = 5.7 flop/B), so neither roofline can be approached alone: 18.7 us with the rows in L2.)
+// third of the launch.  Those figures are for the dual-number form of the model (~50 FP64 instructions per 24-byte
+// row, AT the machine's ridge of 37 TFLOP/s : 6.5 TB/s = 5.7 flop/B; 18.7 us with the rows in L2); with the
+// hand-written gradient (OffsetExpModel, ~28 instructions) 4/512/2 takes 20.6 us from HBM and 16.7 us from L2 -- what
+// is left is the latency of a launch this short (13 rows per thread), not either roofline.)
 #ifndef B200LM_ND_UNROLL
 #define B200LM_ND_UNROLL 4
 #endif

@@ -11,7 +11,11 @@
 #include "../../lsqfit_b200/csrc/lm_rows.cuh"
 #include "../../lsqfit_b200/csrc/functors.cuh"
 
-typedef b200lm::ADFunctor<b200lm::OffsetExpBody, 3> OffsetExp;
+#ifdef ND_BENCH_DUAL
+typedef b200lm::ADFunctor<b200lm::OffsetExpBody, 3> OffsetExp;      // the dual-number form (before)
+#else
+typedef b200lm::OffsetExpModel OffsetExp;
+#endif
 using b200lm::launch_normal_diag;
 using b200lm::ND_MAX_PARTS_PER_SM;
 
