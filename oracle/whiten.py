@@ -65,7 +65,7 @@ def cov_blocks(cov):
 class PDF(object):
     """Whitened description of the Gaussian y(+)prior distribution."""
 
-    def __init__(self, mean, cov, svdcut=1e-12, eps=None):
+    def __init__(self, mean, cov, svdcut=1e-12, eps=None, noise=False, rng=None):
         mean = np.array(mean, dtype=float).reshape(-1)
         cov = np.array(cov, dtype=float)
         if cov.ndim == 1:
@@ -104,6 +104,18 @@ class PDF(object):
             nchiv += W.shape[0]
         self.nchiv = nchiv
         self.correction_cov = self.cov - self.cov_in
+        self.noise = bool(noise)
+        if self.noise:
+            # gvar.PDF(..., noise=True), call sites src/lsqfit/__init__.py:1895,1898: the means get one random sample of
+            # the uncertainty the regulator added (covariance: corrected - input)
+            self.mean += self.noise_samples(1, rng)[0]
+
+    def noise_samples(self, n, rng=None):
+        """[n, N] samples of N(0, corrected - input covariance) (eigen-decomposition of the correction)."""
+        rng = np.random.default_rng() if rng is None else rng
+        val, vec = np.linalg.eigh(0.5 * (self.correction_cov + self.correction_cov.T))
+        L = vec * np.sqrt(np.clip(val, 0.0, None))[None, :]
+        return rng.standard_normal((n, self.size)) @ L.T
 
     # dense helpers used by the oracle fit ----------------------------------
     def icov(self):

@@ -397,3 +397,30 @@ def test_spline_golden(fitter):
         assert gvfmt.agrees(mu, sd, e, slack=1.01), (mu, sd, e)
     if fitter == "gsl":
         assert abs(fit.nit - o["nit"]) <= 1, fit.nit
+
+
+def test_oracle_svd_noise_has_the_correction_covariance():
+    """``noise=True`` of the whitening (gvar.PDF as called at src/lsqfit/__init__.py:1895-1898): the sample added to the
+    means has the covariance the svd cut added (corrected - input), nothing else moves, and no cut means no noise."""
+    from oracle.whiten import PDF
+    rng = np.random.default_rng(2)
+    n = 12
+    sig = 0.1 * (1.0 + rng.random(n))
+    idx = np.arange(n)
+    cov = sig[:, None] * sig[None, :] * 0.95 ** np.abs(idx[:, None] - idx[None, :])
+    full = np.zeros((n + 2, n + 2))
+    full[:n, :n] = cov
+    full[n:, n:] = np.diag([0.3, 0.4]) ** 2
+    mean = np.linspace(0.0, 1.0, n + 2)
+    pdf = PDF(mean, full, svdcut=0.1)
+    assert pdf.nmod > 0 and np.all(np.linalg.eigvalsh(pdf.correction_cov) > -1e-15)
+    z = pdf.noise_samples(60000, np.random.default_rng(5))
+    assert np.all(np.abs(z[:, n:]) < 1e-12)
+    emp = z.T @ z / z.shape[0]
+    scale = np.sqrt(np.outer(np.diag(pdf.correction_cov)[:n], np.diag(pdf.correction_cov)[:n]))
+    assert np.max(np.abs(emp[:n, :n] - pdf.correction_cov[:n, :n]) / scale) < 5.0 * np.sqrt(2.0 / z.shape[0])
+    noisy = PDF(mean, full, svdcut=0.1, noise=True, rng=np.random.default_rng(5))
+    assert np.any(noisy.mean[:n] != mean[:n]) and np.all(noisy.mean[n:] == mean[n:])
+    np.testing.assert_array_equal(noisy.cov, pdf.cov)
+    quiet = PDF(mean, full, svdcut=1e-15, noise=True, rng=np.random.default_rng(5))
+    np.testing.assert_allclose(quiet.mean, mean, rtol=0, atol=1e-12)
