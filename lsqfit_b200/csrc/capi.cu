@@ -217,7 +217,7 @@ void b200lm_destroy(b200lm_handle h) {
     cudaFree(h->d_dfn_idx); cudaFree(h->d_dfn_w); cudaFree(h->d_dpr_idx); cudaFree(h->d_dpr_w);
     cudaFree(h->d_blk); cudaFree(h->d_blk_idx); cudaFree(h->d_blk_wt); cudaFree(h->d_blk_wt2); cudaFree(h->d_wfull);
     cudaFree(h->d_counter); cudaFree(h->d_stats); cudaFree(h->d_stage); cudaFree(h->d_scratch);
-    cudaFree(h->d_order_key); cudaFree(h->d_order);
+    cudaFree(h->d_order_key); cudaFree(h->d_order); cudaFree(h->d_wave_A);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -381,6 +381,20 @@ int b200lm_fit_batch(b200lm_handle h, int B,
         // wave kernel: the trust-region loops of 32 fits per CTA in lock step, then covariance / log det / f / J
         // (and polish) of every fit by the one-warp kernel in finalize_only mode
         P.team = 32;
+        {
+            // hand J^T J at every solution to the finalisation pass (np(np+1)/2 doubles per fit; skipped above 2 GB,
+            // the pass then evaluates the model once more as it did before)
+            const size_t need = (size_t)B * (size_t)(h->np * (h->np + 1) / 2);
+            if (need * sizeof(double) <= ((size_t)2 << 30) && !getenv("B200LM_WAVE_REEVAL")) {
+                if (need > h->wave_A_cap) {
+                    if (h->d_wave_A) cudaFree(h->d_wave_A);
+                    h->d_wave_A = nullptr; h->wave_A_cap = 0;
+                    if (cudaMalloc((void**)&h->d_wave_A, need * sizeof(double)) == cudaSuccess) h->wave_A_cap = need;
+                    else cudaGetLastError();
+                }
+                P.wave_A = h->wave_A_cap >= need ? h->d_wave_A : nullptr;
+            }
+        }
         CUDA_TRY(h, h->fe->fit_wave(P, h->sm_count, h->smem_budget, s), "wave kernel launch");
         CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), s), "reset work queue");
         FitParams Q = P;

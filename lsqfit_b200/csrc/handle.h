@@ -36,6 +36,7 @@ struct b200lm_handle_s {
     // queue order (longest-expected fits first): key = chi2 at the start point, one evaluation per fit
     int order_request = -1;     // -1: default policy (by problem shape and batch size); 0: off; 1: on  (b200lm_set_order)
     int last_order = 0;         // 1 if the last fit_batch launch used an ordered queue
+    double* d_wave_A = nullptr; size_t wave_A_cap = 0;    // packed J^T J per fit, wave kernel -> finalisation pass
     double* d_order_key = nullptr; int* d_order = nullptr; int order_cap = 0;
     // staging for the host-pointer API
     void* d_stage = nullptr; size_t stage_bytes = 0;

@@ -1033,7 +1033,26 @@ __device__ __forceinline__ void fit_one(WarpCtx<F>& c, EV& ev, const FitParams& 
         int cur = 0;                              // buffer holding J^T J, J^T r of the current point
         c.A = c.Abuf[0]; c.g = c.gbuf[0];
         const long long t_fit0 = B200LM_CLOCK();
-        double cost = ev.run(c, c.p, nullptr, nullptr, 0);
+        double cost = 0.0;
+        bool have_A = false;
+        if constexpr (MODE == 2) {
+            // finalisation after the wave kernel: J^T J at the solution comes from the wave kernel (packed lower
+            // triangle, row-major) and chi2 is known -- no evaluation, unless a polish step needs the gradient
+            if (P.wave_A && P.polish == 0 && P.status[b] != -1) {
+                if (act) {
+                    const double* Ap = P.wave_A + (size_t)b * (NP * (NP + 1) / 2) + lane * (lane + 1) / 2;
+                    for (int j = 0; j <= lane; ++j) {
+                        const double v = Ap[j];
+                        c.A[lane * LDA + j] = v;
+                        c.A[j * LDA + lane] = v;
+                    }
+                }
+                cost = 0.5 * P.chi2[b];
+                have_A = true;
+                __syncwarp();
+            }
+        }
+        if (!have_A) cost = ev.run(c, c.p, nullptr, nullptr, 0);
         pk.eval += B200LM_CLOCK() - t_fit0;
         int nfev = 1, njev = 1, nfac = 0;
         int status = -2;                         // -2: running

@@ -70,6 +70,8 @@ struct FitParams {
     double* f_out;              // [B][nchiv]
     double* J_out;              // [B][nchiv][np]
     int* counter;               // work-queue head (zeroed before launch)
+    double* wave_A;             // optional [B][np(np+1)/2]: packed J^T J at the solution, written by the wave kernel for its
+                                // finalisation pass (which then needs no evaluation of its own)
     const int* order;           // optional: the queue hands out fit order[i] instead of fit i (longest-expected first)
     unsigned long long* stats;  // [0] total nfev, [1] total jacobian evals, [2] total factorisations
 };

@@ -715,6 +715,12 @@ __global__ void __launch_bounds__(WaveLayout<F, S_, CF_>::THREADS, MINB) fit_wav
         if (status != -2) {
             if (h0) P.x_out[(size_t)fit * NP + j0] = PV[j0 * S1 + s];      // (the eight lanes hold t8 = 0..7: every entry once)
             if (h1) P.x_out[(size_t)fit * NP + j1] = PV[j1 * S1 + s];
+            if (P.wave_A && status != -1) {
+                // J^T J at the solution (the buffer of the current point) for the finalisation pass
+                const double* Ac = Abuf + cur * NPP * S1 + s;
+                double* Ao = P.wave_A + (size_t)fit * NPP;
+                for (int e = t8; e < NPP; e += 8) Ao[e] = Ac[e * S1];
+            }
             if (lead) {
                 P.chi2[fit] = 2.0 * cost;
                 P.nit[fit] = nfev;
