@@ -793,11 +793,27 @@ cudaError_t launch_fit_wave(FitParams P, int sm_count, size_t smem_budget, cudaS
     typedef WaveLayout<F, 32, 8> WL;
     const size_t smem = WL::bytes(P.wt_total);
     if (smem > smem_budget) return cudaErrorInvalidConfiguration;
+    int grid = sm_count;
+    const int want = (P.B + WL::S / 2 - 1) / (WL::S / 2);      // small batches: spread over the SMs, slots at least half full
+    // Small models (np <= 8) leave room for TWO such CTAs per SM (shared memory: ~95 KB each at np = 6; registers capped at
+    // 128 by the second instantiation): while one CTA is in its latency-bound solve phase the other evaluates.
+    if constexpr (F::NP <= 8) {
+        const char* env = getenv("B200LM_WAVE_CTAS");
+        const int ctas = env ? atoi(env) : 2;
+        if (ctas >= 2 && 2 * (smem + 1024) <= (size_t)227 * 1024) {      // (by shape only: never by batch size)
+            auto kern2 = fit_wave_kernel<F, 32, 8, 2, true>;
+            cudaError_t e2 = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e2 != cudaSuccess) return e2;
+            grid = 2 * sm_count;
+            if (grid > want) grid = want;
+            if (grid < 1) grid = 1;
+            kern2<<<grid, WL::THREADS, smem, stream>>>(P);
+            return cudaGetLastError();
+        }
+    }
     auto kern = fit_wave_kernel<F, 32, 8, 1, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int grid = sm_count;
-    const int want = (P.B + WL::S / 2 - 1) / (WL::S / 2);      // small batches: spread over the SMs, slots at least half full
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     kern<<<grid, WL::THREADS, smem, stream>>>(P);
