@@ -226,10 +226,20 @@ class nonlinear_fit(object):
         args = dict(self.fitterargs)
         args.update(kargs)
         args.pop("device", None)
-        out = plan.fit_batch(means, p0, tol=self.tol if tol is None else tol,
-                             maxit=self.maxit if maxit is None else maxit, want_cov=want_cov,
-                             scaler=args.pop("scaler", "more"), polish=args.pop("polish", 0),
-                             policy=args.pop("policy", "trf"))
+        # kernel=: None (default, by problem shape), 1 / 2 / 4 warps per fit, or 32 / 'wave' -- the wave kernel, the
+        # fastest on saturated batches (10^5 ... 10^6 copies of a small model); see b200lm_set_team
+        kernel = args.pop("kernel", None)
+        kernel = 32 if kernel == "wave" else kernel
+        if kernel is not None:
+            plan.set_team(int(kernel))
+        try:
+            out = plan.fit_batch(means, p0, tol=self.tol if tol is None else tol,
+                                 maxit=self.maxit if maxit is None else maxit, want_cov=want_cov,
+                                 scaler=args.pop("scaler", "more"), polish=args.pop("polish", 0),
+                                 policy=args.pop("policy", "trf"))
+        finally:
+            if kernel is not None:
+                plan.set_team(0)                 # (the plan is cached and shared: back to the default policy)
         return BatchFits(self, out)
 
     def bootstrap_means(self, n, seed=None, first=0):

@@ -310,3 +310,27 @@ def test_host_call_writes_pinned_outputs_in_place():
     c = ref["cov"]
     assert np.max(np.abs(c - c.transpose(0, 2, 1)) / np.sqrt(np.einsum("bii,bjj->bij", c, c))) < 1e-12
     plan.close()
+
+
+def test_batch_drivers_take_a_kernel_argument():
+    """simulated_fits / bootstrapped_fits(kernel='wave'): the wave kernel through the mirror of the reference's iterators;
+    same fits as the default kernel to rounding, and the cached plan goes back to its default policy afterwards."""
+    _need_gpu()
+    import lsqfit_b200 as lb
+    cfg, _ = correlator_problem(3)
+    fit = lb.nonlinear_fit(data=(cfg["x"], cfg["f"], cfg["ycov"]), prior=(cfg["prior_mean"], cfg["prior_sdev"]), fcn="multiexp")
+    a = fit.simulated_fits(3000, pexact=cfg["ptrue"], seed=5)
+    b = fit.simulated_fits(3000, pexact=cfg["ptrue"], seed=5, kernel="wave")
+    plan = fit._spec.plan(fit.device)
+    ra, rb = a.out.numpy(), b.out.numpy()
+    # (the same copies converge; a fit that ends where the ftol and xtol tests both come close may report another of the
+    # converged codes, and the two kernels stop within their tolerance of the minimum, not at the same bits)
+    ok = (ra["status"] > 0) & (rb["status"] > 0)
+    assert ok.mean() > 0.99, (float((ra["status"] > 0).mean()), float((rb["status"] > 0).mean()))
+    sd = np.sqrt(np.einsum("bii->bi", ra["cov"]))
+    dp = np.max(np.abs(ra["x"] - rb["x"]) / sd, axis=1)[ok]
+    assert np.quantile(dp, 0.99) < 1e-3, float(np.quantile(dp, 0.99))
+    dchi = (np.abs(ra["chi2"] - rb["chi2"]) / ra["chi2"])[ok]
+    assert np.quantile(dchi, 0.99) < 1e-7, float(np.quantile(dchi, 0.99))
+    c = fit.simulated_fits(64, pexact=cfg["ptrue"], seed=5)
+    assert plan.last_team() == 1                       # np = 6: one warp per fit by default, again
