@@ -17,7 +17,8 @@ full = np.zeros((N, N)); full[:ny, :ny] = cfg["ycov"]; full[ny:, ny:] = np.diag(
 pdf = lb.PDF(np.concatenate([cfg["f"], cfg["prior_mean"]]), full, svdcut=cfg["svdcut"])
 means = torch.as_tensor(configs.bootstrap_means(cfg, B, cfg["seed"], cov=pdf.cov[:ny, :ny], vary_prior=(K != 3))).cuda()
 plan = lb.Plan("multiexp", npar, ny, cfg["x"], pdf.i_invwgts)
-plan.set_team(32)
+import os
+plan.set_team(int(os.environ.get("C4_TEAM", "32")))
 p0 = torch.as_tensor(cfg["p0"]).cuda()
 out = plan.fit_batch(means, p0, tol=cfg["tol"], maxit=cfg["maxit"])
 torch.cuda.synchronize()
